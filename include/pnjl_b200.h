@@ -1,0 +1,169 @@
+/* pnjl_b200.h — C ABI of libpnjl_b200.so: the B200 (sm_100a) implementation of the batched PNJL
+ * equilibrium solve behind Julia_RelaxTime's
+ *
+ *     PNJL.solve(FixedMu(), T_fm, mu_fm; xi, seed_strategy, p_num, t_num, iterations)      src/pnjl/solver/ImplicitSolver.jl:211-328
+ *     PNJL.solve_multi(FixedMu(), T_fm, mu_fm; ...)                                          src/pnjl/solver/ImplicitSolver.jl:532-559
+ *     the (xi, muB, T) loop of scripts/relaxtime/run_gap_transport_scan.jl                   :407-443
+ *
+ * The reference has no FFI on this path (Julia calling Julia); these entry points are what a Julia
+ * `ccall` shim binds (see julia/PNJLB200.jl and INTEGRATION.md).  Plain pointers and sizes only.
+ *
+ * Conventions
+ *   - All floating point is FP64.  Solver quantities are in fm^-1 units like the reference
+ *     (T_fm = T_MeV / 197.327); the line-scan entry takes MeV like the script does.
+ *   - Results come back as one 32-double RECORD per point (256 B; a Julia Matrix{Float64}(32, n)),
+ *     field offsets PNJL_REC_* below.  Integers (iterations, status, evaluation counts) are stored
+ *     as exactly-representable doubles.
+ *   - Return value 0 = ok, < 0 = call-level error, text via pnjl_last_error().  Per-point trouble
+ *     (no convergence, all seeds failed, non-finite seed residual) is reported in the record's
+ *     status bits, never as a call error: the shim maps PNJL_ST_ALL_SEEDS_FAILED back to the
+ *     reference's `error("All seeds failed ...")` (ImplicitSolver.jl:553,556) where callers rely on it.
+ *   - *_host entry points take caller-owned HOST buffers and do H2D / kernels / D2H internally
+ *     (what `ccall` uses).  *_device entry points take DEVICE pointers and a cudaStream_t passed as
+ *     void* and only enqueue work (what the torch-based multi-GPU driver and bench.py use).
+ *   - One handle per GPU; calls on one handle are not re-entrant.  There is no CPU fallback: every
+ *     entry fails with PNJL_ERR_CUDA if no sm_100 device is usable.
+ */
+#ifndef PNJL_B200_H
+#define PNJL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PNJL_ABI_VERSION 1
+
+/* ---- result record layout (doubles) --------------------------------------------------------- */
+#define PNJL_REC_DOUBLES 32
+#define PNJL_REC_X 0           /* [5] phi_u, phi_d, phi_s, Phi, Phibar      SolverResult.x_state   ImplicitSolver.jl:182 */
+#define PNJL_REC_MASS 5        /* [3] M_u, M_d, M_s (fm^-1)                 SolverResult.masses    :189 */
+#define PNJL_REC_OMEGA 8       /* Omega (fm^-4)                             :184 */
+#define PNJL_REC_PRESSURE 9    /* P = -Omega                                :185 */
+#define PNJL_REC_RHO_NORM 10   /* sum_i rho_i / (3 rho0)                    :186 */
+#define PNJL_REC_ENTROPY 11    /* s = dP/dT                                 :187 */
+#define PNJL_REC_ENERGY 12     /* eps = -P + sum mu_i rho_i + T s           :188 */
+#define PNJL_REC_NQ 13         /* [3] n_u, n_d, n_s        calculate_number_densities  Thermodynamics.jl:255-281 */
+#define PNJL_REC_NQBAR 16      /* [3] n_ubar, n_dbar, n_sbar */
+#define PNJL_REC_RESNORM 19    /* ||F||_inf of the returned nlsolve result  SolverResult.residual_norm :191 */
+#define PNJL_REC_ITER 20       /* iterations of the returned nlsolve result :190 */
+#define PNJL_REC_STATUS 21     /* PNJL_ST_* bits */
+#define PNJL_REC_NEVAL 22      /* Omega-gradient/Jacobian quadrature passes spent on this point (all seeds, all fallbacks) */
+#define PNJL_REC_RHO 23        /* [3] rho_i = dP/dmu_i                      calculate_rho  Thermodynamics.jl:215-220 */
+#define PNJL_REC_NTHERMO 26    /* thermo quadrature passes spent on this point */
+#define PNJL_REC_T 27          /* echo: T_fm */
+#define PNJL_REC_MU 28         /* echo: mu_fm */
+#define PNJL_REC_XI 29         /* echo: xi */
+/* 30, 31 reserved (zero) */
+
+/* ---- status bits ---------------------------------------------------------------------------- */
+#define PNJL_ST_CONVERGED 1          /* SolverResult.converged  ImplicitSolver.jl:287 */
+#define PNJL_ST_USED_TR 2            /* returned candidate is the trust-region one  :72-101 */
+#define PNJL_ST_TR_ATTEMPTED 4       /* fallback solve ran  :130-150 */
+#define PNJL_ST_USED_MULTISEED 8     /* result came out of solve_multi  :532-559 */
+#define PNJL_ST_SEED_SHIFT 4         /* bits 4..6: index of the chosen MultiSeed candidate */
+#define PNJL_ST_SEED_MASK 0x70
+#define PNJL_ST_PHASE_SWITCH 128     /* PhaseAwareContinuitySeed re-seeded at a hadron<->quark flip  SeedStrategies.jl:818-826 */
+#define PNJL_ST_NONFINITE 256        /* seed residual not finite (NLsolve IsFiniteException) */
+#define PNJL_ST_ALL_SEEDS_FAILED 512 /* solve_multi found no converged candidate */
+
+/* ---- errors --------------------------------------------------------------------------------- */
+#define PNJL_OK 0
+#define PNJL_ERR_ARG (-1)
+#define PNJL_ERR_CUDA (-2)
+#define PNJL_ERR_NOMEM (-3)
+
+/* ---- seed modes of pnjl_solve_points_* (mirror of the reference's seed strategies) ---------- */
+#define PNJL_SEED_EXPLICIT 0 /* seeds[n][n_seeds][5]; n_seeds==1: DefaultSeed(seed,seed,:hadron) + auto-MultiSeed fallback per config;
+                                n_seeds>1: solve_multi over the given candidates  (ImplicitSolver.jl:539-546) */
+#define PNJL_SEED_AUTO 1     /* DefaultSeed(phase_hint=:auto)   SeedStrategies.jl:193-225 */
+#define PNJL_SEED_MULTI 2    /* MultiSeed(): the six built-in candidates  SeedStrategies.jl:251-284 */
+
+#define PNJL_MAX_TABLES 8
+#define PNJL_MAX_TABLE_ROWS 64
+
+typedef struct pnjl_handle pnjl_handle;
+
+/* Model constants in fm units (src/Constants_PNJL.jl:82-103), quadrature rule and solver options. */
+typedef struct pnjl_config {
+    double hbarc, Lambda, m_ud0, m_s0, G, K, T0, a0, a1, a2, b3, rho0;
+    int32_t Nc;
+    int32_t p_num, t_num;   /* Integrals.jl:87-96; p_num * t_num <= 2048 */
+    const double* p_nodes;  /* [p_num] gauleg(0, 10, p_num)   Integrals.jl:75-80   (NULL: library generates them) */
+    const double* p_w;      /* [p_num] */
+    const double* c_nodes;  /* [t_num] gauleg(0, 1, t_num)    Integrals.jl:67-73   (NULL: library generates them) */
+    const double* c_w;      /* [t_num] raw weights; the library doubles them like theta_nodes() does */
+    double xtol, ftol;              /* 1e-9, 1e-9     ImplicitSolver.jl:112 */
+    double residual_norm_max;       /* 1e-6           :221 */
+    double phi_tol;                 /* 1e-8           :50 */
+    int32_t max_iter;               /* NLsolve `iterations`: 1000 default, 40 in run_gap_transport_scan.jl:112 */
+    int32_t tr_fallback;            /* trust_region_fallback=true   :217 */
+    int32_t auto_multiseed_fallback;/* auto_multiseed_fallback=true :218 */
+    double omega_tie_rel;           /* MultiSeed argmin-Omega tie window (relative); ties -> lowest seed index. 1e-12 */
+    int32_t device;                 /* CUDA device ordinal; -1 = current device */
+    int32_t lanes_per_solve;        /* 0 = auto (8/16/32 by mesh size); else 8, 16 or 32 */
+} pnjl_config;
+
+/* First-order phase boundary mu_c(T) for one xi (data/reference/pnjl/boundary.csv + cep.csv;
+ * PhaseBoundaryData, SeedStrategies.jl:365-371).  n may be 0 and T_CEP NaN (no data for that xi). */
+typedef struct pnjl_boundary {
+    const double* T_MeV;    /* [n] ascending */
+    const double* mu_c_MeV; /* [n] */
+    int32_t n;              /* <= PNJL_MAX_TABLE_ROWS */
+    double T_CEP_MeV;       /* NaN if unknown */
+} pnjl_boundary;
+
+void pnjl_default_config(pnjl_config* cfg);  /* config/pnjl/default.toml values, 64x8 nodes, max_iter 1000 */
+int pnjl_abi_version(void);
+const char* pnjl_last_error(void);
+
+int pnjl_create(const pnjl_config* cfg, pnjl_handle** out);
+void pnjl_destroy(pnjl_handle* h);
+
+/* gauleg(a, b, n) (src/integration/GaussLegendre.jl:94-119): host-side helper so callers without
+ * FastGaussQuadrature can build the same rule the library would. */
+int pnjl_gauleg(double a, double b, int32_t n, double* nodes, double* weights);
+
+/* Independent points: PNJL.solve / solve_multi at n (T, mu, xi) triples.  records: [n][32]. */
+int pnjl_solve_points_host(pnjl_handle* h, int64_t n, const double* T_fm, const double* mu_fm, const double* xi,
+                           int32_t seed_mode, int32_t n_seeds, const double* seeds, double* records);
+int pnjl_solve_points_device(pnjl_handle* h, int64_t n, const double* d_T_fm, const double* d_mu_fm,
+                             const double* d_xi, int32_t seed_mode, int32_t n_seeds, const double* d_seeds,
+                             double* d_records, void* stream);
+
+/* Continuity lines in run_gap_transport_scan.jl order (:407-443): line l = (xi[l], muq_MeV[l]) marches
+ * T_MeV[0..n_T) ascending; MultiSeed while its tracker has no previous converged solution, then
+ * PhaseAwareContinuitySeed with table table_idx[l] (-1: no data).  records: [n_lines][n_T][32].
+ * muq_MeV, xi, table_idx are per line; T_MeV is shared by all lines. */
+int pnjl_set_boundaries(pnjl_handle* h, int32_t n_tables, const pnjl_boundary* tables);
+int pnjl_scan_lines_host(pnjl_handle* h, int64_t n_lines, const double* muq_MeV, const double* xi,
+                         const int32_t* table_idx, int32_t n_T, const double* T_MeV, double* records);
+int pnjl_scan_lines_device(pnjl_handle* h, int64_t n_lines, const double* d_muq_MeV, const double* d_xi,
+                           const int32_t* d_table_idx, int32_t n_T, const double* d_T_MeV, double* d_records,
+                           void* stream);
+
+/* Single Omega-gradient/Jacobian evaluation at given states (test hook for per-iterate parity):
+ * FJ: [n][30] = F[5] then J[5][5] row-major. */
+int pnjl_eval_fj_host(pnjl_handle* h, int64_t n, const double* T_fm, const double* mu_fm, const double* xi,
+                      const double* x /* [n][5] */, double* FJ);
+
+/* Measured launch statistics of the last *_device / *_host call on this handle. */
+typedef struct pnjl_stats {
+    int64_t kernel_launches;   /* kernels this library launched in the last call */
+    double kernel_ms;          /* device time of the solve kernel(s) of the last *_host call (CUDA events) */
+    int32_t lanes_per_solve;   /* lanes cooperating on one solve */
+    int32_t blocks, threads;   /* launch geometry of the solve kernel */
+    int32_t regs_per_thread;   /* cudaFuncGetAttributes */
+    int32_t smem_bytes;        /* dynamic shared memory per block */
+} pnjl_stats;
+int pnjl_get_stats(pnjl_handle* h, pnjl_stats* out);
+
+/* FP64 FMA peak of the device (register-resident DFMA chains; the roofline denominator the north
+ * star asks for, since MEASURED_PEAKS.json has no FP64 figure).  Returns TFLOP/s in *tflops. */
+int pnjl_measure_fp64_peak(pnjl_handle* h, double* tflops, double* sm_clock_mhz_est);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PNJL_B200_H */

@@ -1,0 +1,54 @@
+"""ctypes mirror of include/pnjl_b200.h (structs, record offsets, status bits)."""
+import ctypes as C
+
+import numpy as np
+
+ABI_VERSION = 1
+REC_DOUBLES = 32
+REC_X, REC_MASS, REC_OMEGA, REC_PRESSURE, REC_RHO_NORM, REC_ENTROPY, REC_ENERGY = 0, 5, 8, 9, 10, 11, 12
+REC_NQ, REC_NQBAR, REC_RESNORM, REC_ITER, REC_STATUS, REC_NEVAL, REC_RHO, REC_NTHERMO = 13, 16, 19, 20, 21, 22, 23, 26
+REC_T, REC_MU, REC_XI = 27, 28, 29
+
+ST_CONVERGED, ST_USED_TR, ST_TR_ATTEMPTED, ST_USED_MULTISEED = 1, 2, 4, 8
+ST_SEED_SHIFT, ST_SEED_MASK, ST_PHASE_SWITCH, ST_NONFINITE, ST_ALL_SEEDS_FAILED = 4, 0x70, 128, 256, 512
+
+SEED_EXPLICIT, SEED_AUTO, SEED_MULTI = 0, 1, 2
+MAX_TABLES, MAX_TABLE_ROWS = 8, 64
+
+c_double_p = C.POINTER(C.c_double)
+c_int32_p = C.POINTER(C.c_int32)
+
+
+class PnjlConfig(C.Structure):
+    _fields_ = [(n, C.c_double) for n in
+                ("hbarc", "Lambda", "m_ud0", "m_s0", "G", "K", "T0", "a0", "a1", "a2", "b3", "rho0")] + [
+        ("Nc", C.c_int32), ("p_num", C.c_int32), ("t_num", C.c_int32),
+        ("p_nodes", c_double_p), ("p_w", c_double_p), ("c_nodes", c_double_p), ("c_w", c_double_p),
+        ("xtol", C.c_double), ("ftol", C.c_double), ("residual_norm_max", C.c_double), ("phi_tol", C.c_double),
+        ("max_iter", C.c_int32), ("tr_fallback", C.c_int32), ("auto_multiseed_fallback", C.c_int32),
+        ("omega_tie_rel", C.c_double), ("device", C.c_int32), ("lanes_per_solve", C.c_int32)]
+
+
+class PnjlBoundary(C.Structure):
+    _fields_ = [("T_MeV", c_double_p), ("mu_c_MeV", c_double_p), ("n", C.c_int32), ("T_CEP_MeV", C.c_double)]
+
+
+class PnjlStats(C.Structure):
+    _fields_ = [("kernel_launches", C.c_int64), ("kernel_ms", C.c_double), ("lanes_per_solve", C.c_int32),
+                ("blocks", C.c_int32), ("threads", C.c_int32), ("regs_per_thread", C.c_int32),
+                ("smem_bytes", C.c_int32)]
+
+
+def dptr(a):
+    return a.ctypes.data_as(c_double_p)
+
+
+def iptr(a):
+    return a.ctypes.data_as(c_int32_p)
+
+
+def as_f64(a, n=None):
+    a = np.ascontiguousarray(np.atleast_1d(a), dtype=np.float64)
+    if n is not None and a.size != n:
+        a = np.ascontiguousarray(np.broadcast_to(a, (n,)), dtype=np.float64)
+    return a

@@ -1,0 +1,224 @@
+"""Build and load libpnjl_b200.so (csrc/pnjl_kernels.cu → sm_100a) and wrap its C ABI (include/pnjl_b200.h).
+
+There is no CPU path: if the shared library is missing, cannot be built, or no B200 is visible,
+the calls raise `PnjlError` — they never fall back to anything else.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from . import _abi
+from .constants import DEFAULT, PNJLConstants
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+BUILD_DIR = os.path.join(CSRC, "_build")
+LIB_PATH = os.path.join(BUILD_DIR, "libpnjl_b200.so")
+SOURCES = [os.path.join(CSRC, f) for f in ("pnjl_kernels.cu", "pnjl_math.cuh", "pnjl_solver.cuh")] + [
+    os.path.join(HERE, "..", "include", "pnjl_b200.h")]
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+class PnjlError(RuntimeError):
+    pass
+
+
+def build(force=False, verbose=False):
+    """nvcc → csrc/_build/libpnjl_b200.so (in-tree, so it travels to the GPU box)."""
+    if (not force and os.path.exists(LIB_PATH)
+            and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in SOURCES)):
+        return LIB_PATH
+    os.makedirs(BUILD_DIR, exist_ok=True)
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, SOURCES[0]]
+    try:
+        out = subprocess.run(cmd, check=True, capture_output=True, text=True)
+    except (OSError, subprocess.CalledProcessError) as e:
+        raise PnjlError("building libpnjl_b200.so failed: %s\n%s" % (e, getattr(e, "stderr", ""))) from e
+    if verbose:
+        print(out.stderr)
+    return LIB_PATH
+
+
+_LIB = None
+
+
+def load():
+    """dlopen the library (building it first when the sources are newer) and declare the prototypes."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = build()
+    try:
+        L = C.CDLL(path)
+    except OSError as e:
+        raise PnjlError("cannot load %s: %s" % (path, e)) from e
+    H = C.c_void_p
+    dp, ip = _abi.c_double_p, _abi.c_int32_p
+    L.pnjl_abi_version.restype = C.c_int
+    L.pnjl_last_error.restype = C.c_char_p
+    L.pnjl_default_config.argtypes = [C.POINTER(_abi.PnjlConfig)]
+    L.pnjl_default_config.restype = None
+    L.pnjl_create.argtypes = [C.POINTER(_abi.PnjlConfig), C.POINTER(H)]
+    L.pnjl_destroy.argtypes = [H]
+    L.pnjl_destroy.restype = None
+    L.pnjl_gauleg.argtypes = [C.c_double, C.c_double, C.c_int32, dp, dp]
+    L.pnjl_solve_points_host.argtypes = [H, C.c_int64, dp, dp, dp, C.c_int32, C.c_int32, dp, dp]
+    L.pnjl_solve_points_device.argtypes = [H, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                           C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pnjl_set_boundaries.argtypes = [H, C.c_int32, C.POINTER(_abi.PnjlBoundary)]
+    L.pnjl_scan_lines_host.argtypes = [H, C.c_int64, dp, dp, ip, C.c_int32, dp, dp]
+    L.pnjl_scan_lines_device.argtypes = [H, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                         C.c_void_p, C.c_void_p]
+    L.pnjl_eval_fj_host.argtypes = [H, C.c_int64, dp, dp, dp, dp, dp]
+    L.pnjl_get_stats.argtypes = [H, C.POINTER(_abi.PnjlStats)]
+    L.pnjl_measure_fp64_peak.argtypes = [H, dp, dp]
+    if L.pnjl_abi_version() != _abi.ABI_VERSION:
+        raise PnjlError("ABI version mismatch between _abi.py and libpnjl_b200.so")
+    _LIB = L
+    return L
+
+
+EXPORTED_SYMBOLS = [
+    "pnjl_default_config", "pnjl_abi_version", "pnjl_last_error", "pnjl_create", "pnjl_destroy", "pnjl_gauleg",
+    "pnjl_solve_points_host", "pnjl_solve_points_device", "pnjl_set_boundaries", "pnjl_scan_lines_host",
+    "pnjl_scan_lines_device", "pnjl_eval_fj_host", "pnjl_get_stats", "pnjl_measure_fp64_peak"]
+
+
+def gauleg(a, b, n):
+    """gauleg(a, b, n) of src/integration/GaussLegendre.jl:94-119 (host-side, no GPU needed)."""
+    L = load()
+    x = np.zeros(int(n))
+    w = np.zeros(int(n))
+    rc = L.pnjl_gauleg(float(a), float(b), int(n), _abi.dptr(x), _abi.dptr(w))
+    if rc != 0:
+        raise ValueError(L.pnjl_last_error().decode())   # ArgumentError in the reference
+    return x, w
+
+
+class Engine:
+    """One handle of the library: constants + quadrature rule + solver options on one GPU."""
+
+    def __init__(self, p_num=64, t_num=8, max_iter=1000, trust_region_fallback=True, auto_multiseed_fallback=True,
+                 residual_norm_max=1e-6, omega_tie_rel=1e-12, device=-1, lanes_per_solve=0, nodes=None,
+                 consts: PNJLConstants = DEFAULT):
+        self.L = load()
+        self.p_num, self.t_num = int(p_num), int(t_num)
+        self._keep = None
+        k = consts
+        cfg = _abi.PnjlConfig(
+            hbarc=k.hbarc, Lambda=k.Lambda_inv_fm, m_ud0=k.m_ud0_inv_fm, m_s0=k.m_s0_inv_fm, G=k.G_fm2, K=k.K_fm5,
+            T0=k.T0_inv_fm, a0=k.a0, a1=k.a1, a2=k.a2, b3=k.b3, rho0=k.rho0_fm3, Nc=k.N_color,
+            p_num=self.p_num, t_num=self.t_num, p_nodes=None, p_w=None, c_nodes=None, c_w=None,
+            xtol=1e-9, ftol=1e-9, residual_norm_max=residual_norm_max, phi_tol=1e-8, max_iter=int(max_iter),
+            tr_fallback=int(trust_region_fallback), auto_multiseed_fallback=int(auto_multiseed_fallback),
+            omega_tie_rel=omega_tie_rel, device=int(device), lanes_per_solve=int(lanes_per_solve))
+        if nodes is not None:
+            self._keep = [np.ascontiguousarray(a, dtype=np.float64) for a in nodes]
+            cfg.p_nodes, cfg.p_w, cfg.c_nodes, cfg.c_w = [_abi.dptr(a) for a in self._keep]
+        self.cfg = cfg
+        self.consts = consts
+        self.h = C.c_void_p()
+        rc = self.L.pnjl_create(C.byref(cfg), C.byref(self.h))
+        if rc != 0:
+            self.h = None
+            raise PnjlError("pnjl_create failed (%d): %s" % (rc, self.L.pnjl_last_error().decode()))
+        self._tables_key = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.pnjl_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise PnjlError("%s failed (%d): %s" % (what, rc, self.L.pnjl_last_error().decode()))
+
+    # ---- boundaries -------------------------------------------------------------------------------
+    def set_boundaries(self, tables):
+        """tables: list of (T_MeV[], mu_c_MeV[], T_CEP_MeV)."""
+        keep = []
+        arr = (_abi.PnjlBoundary * max(1, len(tables)))()
+        for i, (tt, mm, tcep) in enumerate(tables):
+            tt = _abi.as_f64(tt) if len(tt) else np.zeros(0)
+            mm = _abi.as_f64(mm) if len(mm) else np.zeros(0)
+            keep += [tt, mm]
+            arr[i] = _abi.PnjlBoundary(_abi.dptr(tt), _abi.dptr(mm), int(tt.size), float(tcep))
+        self._check(self.L.pnjl_set_boundaries(self.h, len(tables), arr), "pnjl_set_boundaries")
+
+    # ---- host-buffer entry points -------------------------------------------------------------------
+    def solve_points(self, T_fm, mu_fm, xi, seed_mode=_abi.SEED_MULTI, seeds=None, out=None):
+        T_fm = _abi.as_f64(T_fm)
+        n = T_fm.size
+        mu_fm = _abi.as_f64(mu_fm, n)
+        xi = _abi.as_f64(xi, n)
+        n_seeds, sp = 6, None
+        if seed_mode == _abi.SEED_EXPLICIT:
+            seeds = np.ascontiguousarray(seeds, dtype=np.float64).reshape(n, -1, 5)
+            n_seeds = seeds.shape[1]
+            sp = _abi.dptr(seeds)
+        rec = out if out is not None else np.empty((n, _abi.REC_DOUBLES))
+        self._check(self.L.pnjl_solve_points_host(self.h, n, _abi.dptr(T_fm), _abi.dptr(mu_fm), _abi.dptr(xi),
+                                                  int(seed_mode), int(n_seeds), sp, _abi.dptr(rec)),
+                    "pnjl_solve_points_host")
+        return rec
+
+    def scan_lines(self, muq_MeV, xi, T_MeV, table_idx=None, out=None):
+        muq_MeV = _abi.as_f64(muq_MeV)
+        n_lines = muq_MeV.size
+        xi = _abi.as_f64(xi, n_lines)
+        T_MeV = _abi.as_f64(T_MeV)
+        ti = None
+        if table_idx is not None:
+            table_idx = np.ascontiguousarray(table_idx, dtype=np.int32)
+            ti = _abi.iptr(table_idx)
+        rec = out if out is not None else np.empty((n_lines, T_MeV.size, _abi.REC_DOUBLES))
+        self._check(self.L.pnjl_scan_lines_host(self.h, n_lines, _abi.dptr(muq_MeV), _abi.dptr(xi), ti,
+                                                int(T_MeV.size), _abi.dptr(T_MeV), _abi.dptr(rec)),
+                    "pnjl_scan_lines_host")
+        return rec
+
+    def eval_fj(self, T_fm, mu_fm, xi, x):
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, 5)
+        n = x.shape[0]
+        T_fm, mu_fm, xi = _abi.as_f64(T_fm, n), _abi.as_f64(mu_fm, n), _abi.as_f64(xi, n)
+        FJ = np.empty((n, 30))
+        self._check(self.L.pnjl_eval_fj_host(self.h, n, _abi.dptr(T_fm), _abi.dptr(mu_fm), _abi.dptr(xi), _abi.dptr(x),
+                                             _abi.dptr(FJ)), "pnjl_eval_fj_host")
+        return FJ[:, :5].copy(), FJ[:, 5:].reshape(n, 5, 5).copy()
+
+    # ---- device-pointer entry points (torch tensors are only used for their data_ptr) --------------
+    def solve_points_device(self, d_T, d_mu, d_xi, d_records, seed_mode=_abi.SEED_MULTI, d_seeds=None, n_seeds=6,
+                            stream=0):
+        n = d_T.numel()
+        self._check(self.L.pnjl_solve_points_device(
+            self.h, n, d_T.data_ptr(), d_mu.data_ptr(), d_xi.data_ptr(), int(seed_mode), int(n_seeds),
+            d_seeds.data_ptr() if d_seeds is not None else None, d_records.data_ptr(), C.c_void_p(stream)),
+            "pnjl_solve_points_device")
+
+    def scan_lines_device(self, d_muq, d_xi, d_table_idx, d_T, d_records, stream=0):
+        self._check(self.L.pnjl_scan_lines_device(
+            self.h, d_muq.numel(), d_muq.data_ptr(), d_xi.data_ptr(),
+            d_table_idx.data_ptr() if d_table_idx is not None else None, d_T.numel(), d_T.data_ptr(),
+            d_records.data_ptr(), C.c_void_p(stream)), "pnjl_scan_lines_device")
+
+    def stats(self):
+        s = _abi.PnjlStats()
+        self._check(self.L.pnjl_get_stats(self.h, C.byref(s)), "pnjl_get_stats")
+        return {f[0]: getattr(s, f[0]) for f in _abi.PnjlStats._fields_}
+
+    def measure_fp64_peak(self):
+        tf = C.c_double()
+        mhz = C.c_double()
+        self._check(self.L.pnjl_measure_fp64_peak(self.h, C.byref(tf), C.byref(mhz)), "pnjl_measure_fp64_peak")
+        return tf.value, mhz.value

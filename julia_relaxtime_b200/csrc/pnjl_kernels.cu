@@ -1,0 +1,772 @@
+// pnjl_kernels.cu — sm_100a kernels and the C ABI (include/pnjl_b200.h) of libpnjl_b200.so.
+//
+// Kernel layout (one group of G lanes per solve; G = 8, 16 or 32 chosen from the mesh size):
+//   * the quadrature mesh (p^2, (p cos)^2, coefficient per node; 24 B/node) is staged once per CTA in
+//     shared memory; lanes of a group stride it, every node is reused for the three flavours
+//     (three independent dependency chains per lane);
+//   * each lane keeps 20 (FJ pass) or 8 (thermo pass) FP64 partial sums in registers; a group-wide
+//     xor-butterfly of __shfl_xor_sync leaves the bit-identical totals in every lane;
+//   * every lane of the group then runs the 5x5 Newton / dogleg / seed-cascade logic redundantly on
+//     identical registers (pnjl_solver.cuh), so control flow is group-uniform and no broadcast is needed;
+//   * groups pull work (points or whole continuity lines) from a global atomic counter, so slow points
+//     (fallback cascades) do not stall a static partition;
+//   * results leave as 256-byte records written cooperatively by the lanes of the group.
+// There is deliberately no tensor-core / TMA use: the path is FP64 transcendental-heavy quadrature with
+// ~7e3 FLOP per byte of HBM traffic, bounded by the FP64 pipe.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "pnjl_solver.cuh"
+
+namespace pnjl {
+
+struct DeviceConfig {
+    Model m;
+    SolverParams sp;
+    int n_nodes;
+    int pad;
+    PhaseTables pt;
+};
+
+// ---- group-collective evaluation policy ----------------------------------------------------------
+template <int G>
+struct GroupEval {
+    const Model* m;
+    const double* s_p2;
+    const double* s_pc2;
+    const double* s_coef;
+    int n;
+    int lane;        // lane within the group
+    unsigned mask;   // lanes of this group within the warp
+
+    __device__ __forceinline__ double gsum(double v) const {
+#pragma unroll
+        for (int off = G / 2; off > 0; off >>= 1) v += __shfl_xor_sync(mask, v, off);
+        return v;
+    }
+
+    __device__ __noinline__ void fj(double T, double mu, double xi, const double x[5], double F[5], double J[25]) {
+        PointCtx c;
+        make_ctx(*m, T, mu, xi, x, c);
+        double acc[kFJAcc];
+#pragma unroll
+        for (int i = 0; i < kFJAcc; ++i) acc[i] = 0.0;
+        for (int k = lane; k < n; k += G) {
+            const double k2 = fma(xi, s_pc2[k], s_p2[k]);
+            const double cf = s_coef[k];
+            fj_node<0>(c, k2, cf, acc);
+            fj_node<1>(c, k2, cf, acc);
+            fj_node<2>(c, k2, cf, acc);
+        }
+#pragma unroll
+        for (int i = 0; i < kFJAcc; ++i) acc[i] = gsum(acc[i]);
+        finish_fj(*m, c, x, acc, F, J);
+    }
+
+    __device__ __noinline__ void thermo(double T, double mu, double xi, const double x[5], Thermo& th) {
+        PointCtx c;
+        make_ctx(*m, T, mu, xi, x, c);
+        double acc[kThAcc];
+#pragma unroll
+        for (int i = 0; i < kThAcc; ++i) acc[i] = 0.0;
+        for (int k = lane; k < n; k += G) {
+            const double k2 = fma(xi, s_pc2[k], s_p2[k]);
+            const double cf = s_coef[k];
+            thermo_node<0>(c, k2, cf, acc);
+            thermo_node<1>(c, k2, cf, acc);
+            thermo_node<2>(c, k2, cf, acc);
+        }
+#pragma unroll
+        for (int i = 0; i < kThAcc; ++i) acc[i] = gsum(acc[i]);
+        finish_thermo(*m, c, x, acc, th);
+    }
+};
+
+template <int G>
+__device__ __forceinline__ void stage_mesh(const double* __restrict__ g_mesh, int n, double* s_mesh) {
+    for (int i = threadIdx.x; i < 3 * n; i += blockDim.x) s_mesh[i] = g_mesh[i];
+    __syncthreads();
+}
+
+template <int G>
+__device__ __forceinline__ GroupEval<G> make_eval(const DeviceConfig* cfg, const double* s_mesh) {
+    GroupEval<G> ev;
+    const int n = cfg->n_nodes;
+    ev.m = &cfg->m;
+    ev.s_p2 = s_mesh;
+    ev.s_pc2 = s_mesh + n;
+    ev.s_coef = s_mesh + 2 * n;
+    ev.n = n;
+    const int wl = threadIdx.x & 31;
+    ev.lane = wl % G;
+    ev.mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (wl - ev.lane));
+    return ev;
+}
+
+// Next work item for this group (leader pulls, group receives by shuffle).
+template <int G>
+__device__ __forceinline__ long long next_task(unsigned long long* counter, const GroupEval<G>& ev) {
+    unsigned long long t = 0;
+    if (ev.lane == 0) t = atomicAdd(counter, 1ULL);
+    const int leader = (threadIdx.x & 31) - ev.lane;
+    t = __shfl_sync(ev.mask, t, leader);
+    return (long long)t;
+}
+
+template <int G>
+__device__ __forceinline__ void store_record(const GroupEval<G>& ev, const double rec[PNJL_REC_DOUBLES], double* __restrict__ out) {
+#pragma unroll
+    for (int j = 0; j < PNJL_REC_DOUBLES / G; ++j) {
+        const int idx = j * G + ev.lane;
+        double v = rec[0];
+#pragma unroll
+        for (int q = 1; q < PNJL_REC_DOUBLES; ++q) v = (q == idx) ? rec[q] : v;
+        out[idx] = v;
+    }
+}
+
+// ---- independent points --------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(128, 4) k_solve_points(const DeviceConfig* __restrict__ cfg, const double* __restrict__ g_mesh,
+                                                      long long n_points, const double* __restrict__ T_fm,
+                                                      const double* __restrict__ mu_fm, const double* __restrict__ xi,
+                                                      int seed_mode, int n_seeds, const double* __restrict__ seeds,
+                                                      double* __restrict__ records, unsigned long long* counter) {
+    extern __shared__ double s_mesh[];
+    stage_mesh<G>(g_mesh, cfg->n_nodes, s_mesh);
+    GroupEval<G> ev = make_eval<G>(cfg, s_mesh);
+    Solver<GroupEval<G>> sv(cfg->m, cfg->sp, ev);
+    for (;;) {
+        const long long i = next_task<G>(counter, ev);
+        if (i >= n_points) break;
+        const double T = T_fm[i], mu = mu_fm[i], x_i = xi[i];
+        sv.set_point(T, mu, x_i);
+        sv.n_fj = 0;
+        sv.n_th = 0;
+        PointRes r;
+        if (seed_mode == PNJL_SEED_EXPLICIT && n_seeds == 1) {
+            double x0[5];
+            copy5(x0, seeds + 5 * i);
+            sv.solve_with_fallback(x0, r);
+        } else if (seed_mode == PNJL_SEED_EXPLICIT) {
+            sv.solve_multi(seeds + 5 * (long long)n_seeds * i, n_seeds, r);
+        } else if (seed_mode == PNJL_SEED_AUTO) {
+            double x0[5];
+            default_seed(2, T, mu, x0);
+            sv.solve_with_fallback(x0, r);
+        } else {
+            sv.solve_multi(nullptr, 6, r);
+        }
+        double rec[PNJL_REC_DOUBLES];
+        fill_record(r, T, mu, x_i, sv.n_fj, sv.n_th, rec);
+        store_record<G>(ev, rec, records + PNJL_REC_DOUBLES * i);
+    }
+}
+
+// ---- continuity lines ----------------------------------------------------------------------------
+template <int G>
+struct LineSink {
+    const GroupEval<G>* ev;
+    double* base;
+    double xi;
+    __device__ __forceinline__ void operator()(int it, const PointRes& r, double T_fm, double mu_fm, int n_fj, int n_th) {
+        double rec[PNJL_REC_DOUBLES];
+        fill_record(r, T_fm, mu_fm, xi, n_fj, n_th, rec);
+        store_record<G>(*ev, rec, base + (long long)PNJL_REC_DOUBLES * it);
+    }
+};
+
+template <int G>
+__global__ void __launch_bounds__(128, 4) k_scan_lines(const DeviceConfig* __restrict__ cfg, const double* __restrict__ g_mesh,
+                                                    long long n_lines, const double* __restrict__ muq_MeV,
+                                                    const double* __restrict__ xi, const int* __restrict__ table_idx,
+                                                    int n_T, const double* __restrict__ T_MeV, double* __restrict__ records,
+                                                    unsigned long long* counter) {
+    extern __shared__ double s_mesh[];
+    stage_mesh<G>(g_mesh, cfg->n_nodes, s_mesh);
+    GroupEval<G> ev = make_eval<G>(cfg, s_mesh);
+    Solver<GroupEval<G>> sv(cfg->m, cfg->sp, ev);
+    for (;;) {
+        const long long l = next_task<G>(counter, ev);
+        if (l >= n_lines) break;
+        LineSink<G> sink{&ev, records + (long long)PNJL_REC_DOUBLES * n_T * l, xi[l]};
+        scan_line(sv, &cfg->pt, table_idx ? table_idx[l] : -1, muq_MeV[l], xi[l], n_T, T_MeV, sink);
+    }
+}
+
+// ---- single FJ evaluation (test hook) ------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(128, 4) k_eval_fj(const DeviceConfig* __restrict__ cfg, const double* __restrict__ g_mesh,
+                                                 long long n, const double* __restrict__ T_fm, const double* __restrict__ mu_fm,
+                                                 const double* __restrict__ xi, const double* __restrict__ x,
+                                                 double* __restrict__ FJ, unsigned long long* counter) {
+    extern __shared__ double s_mesh[];
+    stage_mesh<G>(g_mesh, cfg->n_nodes, s_mesh);
+    GroupEval<G> ev = make_eval<G>(cfg, s_mesh);
+    for (;;) {
+        const long long i = next_task<G>(counter, ev);
+        if (i >= n) break;
+        double xs[5], F[5], J[25];
+        copy5(xs, x + 5 * i);
+        ev.fj(T_fm[i], mu_fm[i], xi[i], xs, F, J);
+        if (ev.lane == 0) {
+            for (int q = 0; q < 5; ++q) FJ[30 * i + q] = F[q];
+            for (int q = 0; q < 25; ++q) FJ[30 * i + 5 + q] = J[q];
+        }
+    }
+}
+
+// ---- FP64 FMA peak microbenchmark ----------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double seed) {
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double b = 0.999999, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+            a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+}  // namespace pnjl
+
+// =====================================================================================================
+// Host side: handle, buffers, C ABI
+// =====================================================================================================
+using namespace pnjl;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            return fail(PNJL_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));             \
+    } while (0)
+
+// Gauss-Legendre nodes on [-1, 1]: Newton on P_n with the three-term recurrence in long double,
+// Tricomi initial guess; symmetric fill.  (Stands in for FastGaussQuadrature.gausslegendre.)
+void gausslegendre_std(int n, std::vector<double>& x, std::vector<double>& w) {
+    x.assign(n, 0.0);
+    w.assign(n, 0.0);
+    const long double pi = 3.141592653589793238462643383279502884L;
+    const int half = (n + 1) / 2;
+    for (int i = 0; i < half; ++i) {
+        const long double th = pi * (4 * (i + 1) - 1) / (4 * n + 2);
+        long double z = (1 - (n - 1) / (8.0L * n * n * n)) * cosl(th);
+        long double dp = 1;
+        for (int iter = 0; iter < 64; ++iter) {
+            long double pm1 = 1, p = z;  // P_0, P_1
+            for (int k = 2; k <= n; ++k) {
+                const long double pk = ((2 * k - 1) * z * p - (k - 1) * pm1) / k;
+                pm1 = p;
+                p = pk;
+            }
+            if (n == 1) { p = z; pm1 = 1; }
+            dp = n * (pm1 - z * p) / (1 - z * z);
+            const long double dz = p / dp;
+            z -= dz;
+            if (fabsl(dz) < 1e-20L) break;
+        }
+        // re-evaluate derivative at the converged node
+        long double pm1 = 1, p = z;
+        for (int k = 2; k <= n; ++k) {
+            const long double pk = ((2 * k - 1) * z * p - (k - 1) * pm1) / k;
+            pm1 = p;
+            p = pk;
+        }
+        dp = n * (pm1 - z * p) / (1 - z * z);
+        const long double wt = 2 / ((1 - z * z) * dp * dp);
+        x[n - 1 - i] = (double)z;
+        x[i] = (double)(-z);
+        w[n - 1 - i] = (double)wt;
+        w[i] = (double)wt;
+    }
+    if (n % 2 == 1) x[n / 2] = 0.0;
+}
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+}  // namespace
+
+struct pnjl_handle {
+    int device = 0;
+    int sm_count = 0;
+    int n_nodes = 0;
+    int G = 32;
+    DeviceConfig host_cfg;
+    DeviceConfig* d_cfg = nullptr;
+    double* d_mesh = nullptr;
+    unsigned long long* d_counter = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    DevBuf in_T, in_mu, in_xi, in_seeds, in_idx, in_x, out_rec;
+    pnjl_stats stats;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+template <class K>
+int launch_geometry(pnjl_handle* h, K kernel, size_t smem, long long n_groups_needed, int G, int* blocks, int* threads) {
+    const int block = 128;
+    cudaFuncAttributes fa;
+    CUDA_TRY(cudaFuncGetAttributes(&fa, kernel));
+    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem));
+    if (per_sm < 1) return fail(PNJL_ERR_CUDA, "kernel does not fit on an SM");
+    const long long groups_per_block = block / G;
+    long long need = (n_groups_needed + groups_per_block - 1) / groups_per_block;
+    long long cap = (long long)per_sm * h->sm_count;
+    if (need < 1) need = 1;
+    *blocks = (int)(need < cap ? need : cap);
+    *threads = block;
+    h->stats.regs_per_thread = fa.numRegs;
+    h->stats.smem_bytes = (int)smem;
+    h->stats.blocks = *blocks;
+    h->stats.threads = block;
+    h->stats.lanes_per_solve = G;
+    return PNJL_OK;
+}
+
+template <int G>
+int launch_points(pnjl_handle* h, long long n, const double* T, const double* mu, const double* xi, int seed_mode,
+                  int n_seeds, const double* seeds, double* rec, cudaStream_t st) {
+    const size_t smem = sizeof(double) * 3 * h->n_nodes;
+    int blocks, threads;
+    int rc = launch_geometry(h, k_solve_points<G>, smem, n, G, &blocks, &threads);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned long long), st));
+    k_solve_points<G><<<blocks, threads, smem, st>>>(h->d_cfg, h->d_mesh, n, T, mu, xi, seed_mode, n_seeds, seeds, rec,
+                                                     h->d_counter);
+    CUDA_TRY(cudaGetLastError());
+    h->stats.kernel_launches += 1;
+    return PNJL_OK;
+}
+
+template <int G>
+int launch_lines(pnjl_handle* h, long long n_lines, const double* muq, const double* xi, const int* tidx, int n_T,
+                 const double* T, double* rec, cudaStream_t st) {
+    const size_t smem = sizeof(double) * 3 * h->n_nodes;
+    int blocks, threads;
+    int rc = launch_geometry(h, k_scan_lines<G>, smem, n_lines, G, &blocks, &threads);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned long long), st));
+    k_scan_lines<G><<<blocks, threads, smem, st>>>(h->d_cfg, h->d_mesh, n_lines, muq, xi, tidx, n_T, T, rec, h->d_counter);
+    CUDA_TRY(cudaGetLastError());
+    h->stats.kernel_launches += 1;
+    return PNJL_OK;
+}
+
+template <int G>
+int launch_fj(pnjl_handle* h, long long n, const double* T, const double* mu, const double* xi, const double* x,
+              double* FJ, cudaStream_t st) {
+    const size_t smem = sizeof(double) * 3 * h->n_nodes;
+    int blocks, threads;
+    int rc = launch_geometry(h, k_eval_fj<G>, smem, n, G, &blocks, &threads);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned long long), st));
+    k_eval_fj<G><<<blocks, threads, smem, st>>>(h->d_cfg, h->d_mesh, n, T, mu, xi, x, FJ, h->d_counter);
+    CUDA_TRY(cudaGetLastError());
+    h->stats.kernel_launches += 1;
+    return PNJL_OK;
+}
+
+#define DISPATCH_G(h, call)                      \
+    do {                                         \
+        switch ((h)->G) {                        \
+            case 8: return call<8>;              \
+            case 16: return call<16>;            \
+            default: return call<32>;            \
+        }                                        \
+    } while (0)
+
+int dispatch_points(pnjl_handle* h, long long n, const double* T, const double* mu, const double* xi, int seed_mode,
+                    int n_seeds, const double* seeds, double* rec, cudaStream_t st) {
+    switch (h->G) {
+        case 8: return launch_points<8>(h, n, T, mu, xi, seed_mode, n_seeds, seeds, rec, st);
+        case 16: return launch_points<16>(h, n, T, mu, xi, seed_mode, n_seeds, seeds, rec, st);
+        default: return launch_points<32>(h, n, T, mu, xi, seed_mode, n_seeds, seeds, rec, st);
+    }
+}
+int dispatch_lines(pnjl_handle* h, long long n_lines, const double* muq, const double* xi, const int* tidx, int n_T,
+                   const double* T, double* rec, cudaStream_t st) {
+    switch (h->G) {
+        case 8: return launch_lines<8>(h, n_lines, muq, xi, tidx, n_T, T, rec, st);
+        case 16: return launch_lines<16>(h, n_lines, muq, xi, tidx, n_T, T, rec, st);
+        default: return launch_lines<32>(h, n_lines, muq, xi, tidx, n_T, T, rec, st);
+    }
+}
+int dispatch_fj(pnjl_handle* h, long long n, const double* T, const double* mu, const double* xi, const double* x,
+                double* FJ, cudaStream_t st) {
+    switch (h->G) {
+        case 8: return launch_fj<8>(h, n, T, mu, xi, x, FJ, st);
+        case 16: return launch_fj<16>(h, n, T, mu, xi, x, FJ, st);
+        default: return launch_fj<32>(h, n, T, mu, xi, x, FJ, st);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int pnjl_abi_version(void) { return PNJL_ABI_VERSION; }
+
+const char* pnjl_last_error(void) { return g_last_error.c_str(); }
+
+void pnjl_default_config(pnjl_config* c) {
+    std::memset(c, 0, sizeof(*c));
+    c->hbarc = 197.327;
+    c->Lambda = 602.3 / c->hbarc;
+    c->m_ud0 = 5.5 / c->hbarc;
+    c->m_s0 = 140.7 / c->hbarc;
+    c->G = 1.835 / (c->Lambda * c->Lambda);
+    c->K = 12.36 / std::pow(c->Lambda, 5);
+    c->T0 = 210.0 / c->hbarc;
+    c->a0 = 3.51; c->a1 = -2.47; c->a2 = 15.2; c->b3 = -1.75;
+    c->rho0 = 0.16;
+    c->Nc = 3;
+    c->p_num = 64; c->t_num = 8;
+    c->xtol = 1e-9; c->ftol = 1e-9; c->residual_norm_max = 1e-6; c->phi_tol = 1e-8;
+    c->max_iter = 1000;
+    c->tr_fallback = 1; c->auto_multiseed_fallback = 1;
+    c->omega_tie_rel = 1e-12;
+    c->device = -1;
+    c->lanes_per_solve = 0;
+}
+
+int pnjl_gauleg(double a, double b, int32_t n, double* nodes, double* weights) {
+    if (n <= 0) return fail(PNJL_ERR_ARG, "gauleg: n must be > 0");        // GaussLegendre.jl:96-98
+    if (!(a < b)) return fail(PNJL_ERR_ARG, "gauleg: need a < b");          // GaussLegendre.jl:100-102
+    std::vector<double> x, w;
+    gausslegendre_std(n, x, w);
+    const double scale = (b - a) / 2.0, shift = (b + a) / 2.0;
+    for (int i = 0; i < n; ++i) {
+        nodes[i] = scale * x[i] + shift;
+        weights[i] = scale * w[i];
+    }
+    return PNJL_OK;
+}
+
+int pnjl_create(const pnjl_config* c, pnjl_handle** out) {
+    if (!c || !out) return fail(PNJL_ERR_ARG, "null argument");
+    if (c->p_num <= 0 || c->t_num <= 0 || (long long)c->p_num * c->t_num > 2048)
+        return fail(PNJL_ERR_ARG, "p_num * t_num must be in 1..2048");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(PNJL_ERR_CUDA, std::string("no CUDA device: this library has no CPU fallback (") +
+                                       cudaGetErrorString(e) + ")");
+    int dev = c->device;
+    if (dev < 0) CUDA_TRY(cudaGetDevice(&dev));
+    if (dev >= ndev) return fail(PNJL_ERR_ARG, "device ordinal out of range");
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10)
+        return fail(PNJL_ERR_CUDA, "device is not sm_100 (B200); the library is built for sm_100a only");
+    DeviceGuard guard(dev);
+
+    pnjl_handle* h = new pnjl_handle();
+    h->device = dev;
+    h->sm_count = prop.multiProcessorCount;
+    h->n_nodes = c->p_num * c->t_num;
+    std::memset(&h->stats, 0, sizeof(h->stats));
+    if (c->lanes_per_solve == 8 || c->lanes_per_solve == 16 || c->lanes_per_solve == 32) h->G = c->lanes_per_solve;
+    else if (c->lanes_per_solve == 0) h->G = h->n_nodes <= 96 ? 8 : (h->n_nodes <= 256 ? 16 : 32);
+    else { delete h; return fail(PNJL_ERR_ARG, "lanes_per_solve must be 0, 8, 16 or 32"); }
+
+    // quadrature rule: caller's nodes (Julia: FastGaussQuadrature) or the library's own
+    std::vector<double> pn(c->p_num), pw(c->p_num), cn(c->t_num), cw(c->t_num);
+    if (c->p_nodes && c->p_w) {
+        std::memcpy(pn.data(), c->p_nodes, sizeof(double) * c->p_num);
+        std::memcpy(pw.data(), c->p_w, sizeof(double) * c->p_num);
+    } else {
+        pnjl_gauleg(0.0, 10.0, c->p_num, pn.data(), pw.data());  // Integrals.jl:75-80
+    }
+    if (c->c_nodes && c->c_w) {
+        std::memcpy(cn.data(), c->c_nodes, sizeof(double) * c->t_num);
+        std::memcpy(cw.data(), c->c_w, sizeof(double) * c->t_num);
+    } else {
+        pnjl_gauleg(0.0, 1.0, c->t_num, cn.data(), cw.data());   // Integrals.jl:67-73
+    }
+    // mesh in build_nodes order (Integrals.jl:87-96): column-major (p_num, t_num), p fastest
+    std::vector<double> mesh(3 * (size_t)h->n_nodes);
+    const double two_pi = 2 * kPi;
+    for (int j = 0; j < c->t_num; ++j)
+        for (int i = 0; i < c->p_num; ++i) {
+            const int k = j * c->p_num + i;
+            const double p = pn[i], t = cn[j];
+            mesh[k] = p * p;
+            mesh[h->n_nodes + k] = (p * t) * (p * t);
+            mesh[2 * h->n_nodes + k] = (pw[i] * (cw[j] * 2.0)) * (p * p) / (two_pi * two_pi);
+        }
+
+    DeviceConfig& dc = h->host_cfg;
+    std::memset(&dc, 0, sizeof(dc));
+    dc.m.hbarc = c->hbarc; dc.m.Lambda = c->Lambda; dc.m.m_ud0 = c->m_ud0; dc.m.m_s0 = c->m_s0; dc.m.G = c->G; dc.m.K = c->K;
+    dc.m.T0 = c->T0; dc.m.a0 = c->a0; dc.m.a1 = c->a1; dc.m.a2 = c->a2; dc.m.b3 = c->b3; dc.m.rho0 = c->rho0; dc.m.Nc = c->Nc;
+    dc.sp.xtol = c->xtol; dc.sp.ftol = c->ftol; dc.sp.residual_norm_max = c->residual_norm_max; dc.sp.phi_tol = c->phi_tol;
+    dc.sp.omega_tie_rel = c->omega_tie_rel; dc.sp.max_iter = c->max_iter; dc.sp.tr_fallback = c->tr_fallback;
+    dc.sp.auto_multiseed_fallback = c->auto_multiseed_fallback;
+    dc.n_nodes = h->n_nodes;
+    dc.pt.n_tables = 0;
+
+#define CREATE_TRY(expr)                                                                              \
+    do {                                                                                              \
+        cudaError_t _e = (expr);                                                                      \
+        if (_e != cudaSuccess) {                                                                      \
+            pnjl_destroy(h);                                                                          \
+            return fail(PNJL_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));          \
+        }                                                                                             \
+    } while (0)
+    CREATE_TRY(cudaMalloc(&h->d_cfg, sizeof(DeviceConfig)));
+    CREATE_TRY(cudaMalloc(&h->d_mesh, sizeof(double) * mesh.size()));
+    CREATE_TRY(cudaMalloc(&h->d_counter, sizeof(unsigned long long)));
+    CREATE_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CREATE_TRY(cudaEventCreate(&h->ev0));
+    CREATE_TRY(cudaEventCreate(&h->ev1));
+    CREATE_TRY(cudaMemcpy(h->d_cfg, &dc, sizeof(dc), cudaMemcpyHostToDevice));
+    CREATE_TRY(cudaMemcpy(h->d_mesh, mesh.data(), sizeof(double) * mesh.size(), cudaMemcpyHostToDevice));
+#undef CREATE_TRY
+    *out = h;
+    return PNJL_OK;
+}
+
+void pnjl_destroy(pnjl_handle* h) {
+    if (!h) return;
+    DeviceGuard guard(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    h->in_T.release(); h->in_mu.release(); h->in_xi.release(); h->in_seeds.release(); h->in_idx.release();
+    h->in_x.release(); h->out_rec.release();
+    if (h->d_cfg) cudaFree(h->d_cfg);
+    if (h->d_mesh) cudaFree(h->d_mesh);
+    if (h->d_counter) cudaFree(h->d_counter);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int pnjl_set_boundaries(pnjl_handle* h, int32_t n_tables, const pnjl_boundary* tables) {
+    if (!h) return fail(PNJL_ERR_ARG, "null handle");
+    if (n_tables < 0 || n_tables > PNJL_MAX_TABLES) return fail(PNJL_ERR_ARG, "too many boundary tables");
+    DeviceGuard guard(h->device);
+    PhaseTables& pt = h->host_cfg.pt;
+    std::memset(&pt, 0, sizeof(pt));
+    pt.n_tables = n_tables;
+    for (int t = 0; t < n_tables; ++t) {
+        if (tables[t].n < 0 || tables[t].n > PNJL_MAX_TABLE_ROWS) return fail(PNJL_ERR_ARG, "boundary table too long");
+        pt.n[t] = tables[t].n;
+        pt.T_CEP[t] = tables[t].T_CEP_MeV;
+        for (int i = 0; i < tables[t].n; ++i) {
+            pt.T[t][i] = tables[t].T_MeV[i];
+            pt.mu[t][i] = tables[t].mu_c_MeV[i];
+            if (i > 0 && !(pt.T[t][i] >= pt.T[t][i - 1])) return fail(PNJL_ERR_ARG, "boundary table must be sorted by T");
+        }
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaMemcpy(h->d_cfg, &h->host_cfg, sizeof(DeviceConfig), cudaMemcpyHostToDevice));
+    return PNJL_OK;
+}
+
+int pnjl_solve_points_device(pnjl_handle* h, int64_t n, const double* d_T, const double* d_mu, const double* d_xi,
+                             int32_t seed_mode, int32_t n_seeds, const double* d_seeds, double* d_records, void* stream) {
+    if (!h) return fail(PNJL_ERR_ARG, "null handle");
+    if (n < 0) return fail(PNJL_ERR_ARG, "n < 0");
+    if (seed_mode < 0 || seed_mode > 2) return fail(PNJL_ERR_ARG, "bad seed_mode");
+    if (seed_mode == PNJL_SEED_EXPLICIT && (!d_seeds || n_seeds < 1 || n_seeds > 6))
+        return fail(PNJL_ERR_ARG, "explicit seeds need 1..6 seeds per point");
+    h->stats.kernel_launches = 0;
+    if (n == 0) return PNJL_OK;
+    if (!d_T || !d_mu || !d_xi || !d_records) return fail(PNJL_ERR_ARG, "null buffer");
+    DeviceGuard guard(h->device);
+    return dispatch_points(h, n, d_T, d_mu, d_xi, seed_mode, n_seeds, d_seeds, d_records, (cudaStream_t)stream);
+}
+
+int pnjl_scan_lines_device(pnjl_handle* h, int64_t n_lines, const double* d_muq, const double* d_xi,
+                           const int32_t* d_tidx, int32_t n_T, const double* d_T, double* d_records, void* stream) {
+    if (!h) return fail(PNJL_ERR_ARG, "null handle");
+    if (n_lines < 0 || n_T < 0) return fail(PNJL_ERR_ARG, "negative size");
+    h->stats.kernel_launches = 0;
+    if (n_lines == 0 || n_T == 0) return PNJL_OK;
+    if (!d_muq || !d_xi || !d_T || !d_records) return fail(PNJL_ERR_ARG, "null buffer");
+    DeviceGuard guard(h->device);
+    return dispatch_lines(h, n_lines, d_muq, d_xi, d_tidx, n_T, d_T, d_records, (cudaStream_t)stream);
+}
+
+int pnjl_solve_points_host(pnjl_handle* h, int64_t n, const double* T, const double* mu, const double* xi,
+                           int32_t seed_mode, int32_t n_seeds, const double* seeds, double* records) {
+    if (!h) return fail(PNJL_ERR_ARG, "null handle");
+    if (n < 0) return fail(PNJL_ERR_ARG, "n < 0");
+    if (n == 0) { h->stats.kernel_launches = 0; return PNJL_OK; }
+    if (!T || !mu || !xi || !records) return fail(PNJL_ERR_ARG, "null buffer");
+    DeviceGuard guard(h->device);
+    const size_t nb = sizeof(double) * (size_t)n;
+    CUDA_TRY(h->in_T.reserve(nb));
+    CUDA_TRY(h->in_mu.reserve(nb));
+    CUDA_TRY(h->in_xi.reserve(nb));
+    CUDA_TRY(h->out_rec.reserve(nb * PNJL_REC_DOUBLES));
+    cudaStream_t st = h->stream;
+    CUDA_TRY(cudaMemcpyAsync(h->in_T.p, T, nb, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(h->in_mu.p, mu, nb, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(h->in_xi.p, xi, nb, cudaMemcpyHostToDevice, st));
+    const double* d_seeds = nullptr;
+    if (seed_mode == PNJL_SEED_EXPLICIT) {
+        if (!seeds || n_seeds < 1 || n_seeds > 6) return fail(PNJL_ERR_ARG, "explicit seeds need 1..6 seeds per point");
+        CUDA_TRY(h->in_seeds.reserve(nb * 5 * n_seeds));
+        CUDA_TRY(cudaMemcpyAsync(h->in_seeds.p, seeds, nb * 5 * n_seeds, cudaMemcpyHostToDevice, st));
+        d_seeds = (const double*)h->in_seeds.p;
+    }
+    CUDA_TRY(cudaEventRecord(h->ev0, st));
+    int rc = pnjl_solve_points_device(h, n, (const double*)h->in_T.p, (const double*)h->in_mu.p, (const double*)h->in_xi.p,
+                                      seed_mode, n_seeds, d_seeds, (double*)h->out_rec.p, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(h->ev1, st));
+    CUDA_TRY(cudaMemcpyAsync(records, h->out_rec.p, nb * PNJL_REC_DOUBLES, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->stats.kernel_ms = ms;
+    return PNJL_OK;
+}
+
+int pnjl_scan_lines_host(pnjl_handle* h, int64_t n_lines, const double* muq, const double* xi, const int32_t* tidx,
+                         int32_t n_T, const double* T_MeV, double* records) {
+    if (!h) return fail(PNJL_ERR_ARG, "null handle");
+    if (n_lines < 0 || n_T < 0) return fail(PNJL_ERR_ARG, "negative size");
+    if (n_lines == 0 || n_T == 0) { h->stats.kernel_launches = 0; return PNJL_OK; }
+    if (!muq || !xi || !T_MeV || !records) return fail(PNJL_ERR_ARG, "null buffer");
+    DeviceGuard guard(h->device);
+    const size_t nl = sizeof(double) * (size_t)n_lines;
+    const size_t nrec = sizeof(double) * (size_t)n_lines * n_T * PNJL_REC_DOUBLES;
+    CUDA_TRY(h->in_mu.reserve(nl));
+    CUDA_TRY(h->in_xi.reserve(nl));
+    CUDA_TRY(h->in_T.reserve(sizeof(double) * n_T));
+    CUDA_TRY(h->in_idx.reserve(sizeof(int32_t) * (size_t)n_lines));
+    CUDA_TRY(h->out_rec.reserve(nrec));
+    cudaStream_t st = h->stream;
+    CUDA_TRY(cudaMemcpyAsync(h->in_mu.p, muq, nl, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(h->in_xi.p, xi, nl, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(h->in_T.p, T_MeV, sizeof(double) * n_T, cudaMemcpyHostToDevice, st));
+    const int32_t* d_idx = nullptr;
+    if (tidx) {
+        CUDA_TRY(cudaMemcpyAsync(h->in_idx.p, tidx, sizeof(int32_t) * (size_t)n_lines, cudaMemcpyHostToDevice, st));
+        d_idx = (const int32_t*)h->in_idx.p;
+    }
+    CUDA_TRY(cudaEventRecord(h->ev0, st));
+    int rc = pnjl_scan_lines_device(h, n_lines, (const double*)h->in_mu.p, (const double*)h->in_xi.p, d_idx, n_T,
+                                    (const double*)h->in_T.p, (double*)h->out_rec.p, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(h->ev1, st));
+    CUDA_TRY(cudaMemcpyAsync(records, h->out_rec.p, nrec, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->stats.kernel_ms = ms;
+    return PNJL_OK;
+}
+
+int pnjl_eval_fj_host(pnjl_handle* h, int64_t n, const double* T, const double* mu, const double* xi, const double* x,
+                      double* FJ) {
+    if (!h) return fail(PNJL_ERR_ARG, "null handle");
+    if (n <= 0) return n == 0 ? PNJL_OK : fail(PNJL_ERR_ARG, "n < 0");
+    if (!T || !mu || !xi || !x || !FJ) return fail(PNJL_ERR_ARG, "null buffer");
+    DeviceGuard guard(h->device);
+    const size_t nb = sizeof(double) * (size_t)n;
+    CUDA_TRY(h->in_T.reserve(nb));
+    CUDA_TRY(h->in_mu.reserve(nb));
+    CUDA_TRY(h->in_xi.reserve(nb));
+    CUDA_TRY(h->in_x.reserve(nb * 5));
+    CUDA_TRY(h->out_rec.reserve(nb * 30));
+    cudaStream_t st = h->stream;
+    CUDA_TRY(cudaMemcpyAsync(h->in_T.p, T, nb, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(h->in_mu.p, mu, nb, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(h->in_xi.p, xi, nb, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(h->in_x.p, x, nb * 5, cudaMemcpyHostToDevice, st));
+    h->stats.kernel_launches = 0;
+    int rc = dispatch_fj(h, n, (const double*)h->in_T.p, (const double*)h->in_mu.p, (const double*)h->in_xi.p,
+                         (const double*)h->in_x.p, (double*)h->out_rec.p, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(FJ, h->out_rec.p, nb * 30, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return PNJL_OK;
+}
+
+int pnjl_get_stats(pnjl_handle* h, pnjl_stats* out) {
+    if (!h || !out) return fail(PNJL_ERR_ARG, "null argument");
+    *out = h->stats;
+    return PNJL_OK;
+}
+
+int pnjl_measure_fp64_peak(pnjl_handle* h, double* tflops, double* sm_clock_mhz_est) {
+    if (!h || !tflops) return fail(PNJL_ERR_ARG, "null argument");
+    DeviceGuard guard(h->device);
+    const int threads = 256, blocks = h->sm_count * 8, iters = 4096;
+    double* d_out = nullptr;
+    CUDA_TRY(cudaMalloc(&d_out, sizeof(double) * threads * blocks));
+    cudaStream_t st = h->stream;
+    double best_ms = 1e30;
+    for (int rep = 0; rep < 6; ++rep) {
+        CUDA_TRY(cudaEventRecord(h->ev0, st));
+        k_dfma_peak<<<blocks, threads, 0, st>>>(d_out, iters, 1.0 + rep);
+        CUDA_TRY(cudaEventRecord(h->ev1, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        if (rep >= 1 && ms < best_ms) best_ms = ms;
+    }
+    cudaFree(d_out);
+    const double fmas = (double)threads * blocks * (double)iters * 16.0 * 8.0;
+    *tflops = 2.0 * fmas / (best_ms * 1e-3) / 1e12;
+    if (sm_clock_mhz_est) {
+        // 64 FP64 FMA lanes per SM per clock (assumed; reported for cross-checking against nvidia-smi)
+        *sm_clock_mhz_est = fmas / (best_ms * 1e-3) / (64.0 * h->sm_count) / 1e6;
+    }
+    return PNJL_OK;
+}
+
+}  // extern "C"

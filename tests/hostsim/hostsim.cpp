@@ -1,0 +1,151 @@
+// hostsim.cpp — TEST-ONLY host build of the product's math/solver headers.
+//
+// Compiles julia_relaxtime_b200/csrc/pnjl_math.cuh + pnjl_solver.cuh with g++ (no CUDA) and a
+// sequential evaluation policy, so the analytic derivatives and the solve cascade that the CUDA
+// kernels run can be checked against the oracle on a machine without a GPU.  It is NOT part of
+// libpnjl_b200.so and nothing in the product package loads it: the product has no CPU path.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../julia_relaxtime_b200/csrc/pnjl_solver.cuh"
+
+using namespace pnjl;
+
+namespace {
+
+struct HostMesh {
+    int n;
+    std::vector<double> p2, pc2, coef;
+};
+
+struct HostEval {
+    const Model* m;
+    const HostMesh* mesh;
+    void fj(double T, double mu, double xi, const double x[5], double F[5], double J[25]) {
+        PointCtx c;
+        make_ctx(*m, T, mu, xi, x, c);
+        double acc[kFJAcc] = {0};
+        for (int k = 0; k < mesh->n; ++k) {
+            const double k2 = mesh->p2[k] + xi * mesh->pc2[k];
+            fj_node<0>(c, k2, mesh->coef[k], acc);
+            fj_node<1>(c, k2, mesh->coef[k], acc);
+            fj_node<2>(c, k2, mesh->coef[k], acc);
+        }
+        finish_fj(*m, c, x, acc, F, J);
+    }
+    void thermo(double T, double mu, double xi, const double x[5], Thermo& th) {
+        PointCtx c;
+        make_ctx(*m, T, mu, xi, x, c);
+        double acc[kThAcc] = {0};
+        for (int k = 0; k < mesh->n; ++k) {
+            const double k2 = mesh->p2[k] + xi * mesh->pc2[k];
+            thermo_node<0>(c, k2, mesh->coef[k], acc);
+            thermo_node<1>(c, k2, mesh->coef[k], acc);
+            thermo_node<2>(c, k2, mesh->coef[k], acc);
+        }
+        finish_thermo(*m, c, x, acc, th);
+    }
+};
+
+Model model_of(const pnjl_config* c) {
+    Model m;
+    m.hbarc = c->hbarc; m.Lambda = c->Lambda; m.m_ud0 = c->m_ud0; m.m_s0 = c->m_s0; m.G = c->G; m.K = c->K;
+    m.T0 = c->T0; m.a0 = c->a0; m.a1 = c->a1; m.a2 = c->a2; m.b3 = c->b3; m.rho0 = c->rho0; m.Nc = c->Nc;
+    return m;
+}
+SolverParams params_of(const pnjl_config* c) {
+    SolverParams s;
+    s.xtol = c->xtol; s.ftol = c->ftol; s.residual_norm_max = c->residual_norm_max; s.phi_tol = c->phi_tol;
+    s.omega_tie_rel = c->omega_tie_rel; s.max_iter = c->max_iter; s.tr_fallback = c->tr_fallback;
+    s.auto_multiseed_fallback = c->auto_multiseed_fallback; s.pad = 0;
+    return s;
+}
+HostMesh mesh_of(const pnjl_config* c) {
+    HostMesh h;
+    h.n = c->p_num * c->t_num;
+    h.p2.resize(h.n); h.pc2.resize(h.n); h.coef.resize(h.n);
+    const double two_pi = 2 * kPi;
+    for (int j = 0; j < c->t_num; ++j)
+        for (int i = 0; i < c->p_num; ++i) {
+            const int k = j * c->p_num + i;
+            const double p = c->p_nodes[i], t = c->c_nodes[j];
+            h.p2[k] = p * p;
+            h.pc2[k] = (p * t) * (p * t);
+            h.coef[k] = (c->p_w[i] * (c->c_w[j] * 2.0)) * (p * p) / (two_pi * two_pi);
+        }
+    return h;
+}
+
+}  // namespace
+
+extern "C" {
+
+void hostsim_fj(const pnjl_config* c, const double* x, double T, double mu, double xi, double* F, double* J) {
+    Model m = model_of(c);
+    HostMesh mesh = mesh_of(c);
+    HostEval ev{&m, &mesh};
+    ev.fj(T, mu, xi, x, F, J);
+}
+
+void hostsim_thermo(const pnjl_config* c, const double* x, double T, double mu, double xi, double* out17) {
+    Model m = model_of(c);
+    HostMesh mesh = mesh_of(c);
+    HostEval ev{&m, &mesh};
+    Thermo th;
+    ev.thermo(T, mu, xi, x, th);
+    out17[0] = th.omega; out17[1] = th.pressure; out17[2] = th.rho_norm; out17[3] = th.entropy; out17[4] = th.energy;
+    for (int i = 0; i < 3; ++i) { out17[5 + i] = th.rho[i]; out17[8 + i] = th.M[i]; out17[11 + i] = th.nq[i]; out17[14 + i] = th.nqb[i]; }
+}
+
+void hostsim_solve_points(const pnjl_config* c, int64_t n, const double* T, const double* mu, const double* xi,
+                          int32_t seed_mode, int32_t n_seeds, const double* seeds, double* records) {
+    Model m = model_of(c);
+    SolverParams sp = params_of(c);
+    HostMesh mesh = mesh_of(c);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t i = 0; i < n; ++i) {
+        HostEval ev{&m, &mesh};
+        Solver<HostEval> sv(m, sp, ev);
+        sv.set_point(T[i], mu[i], xi[i]);
+        PointRes r;
+        if (seed_mode == PNJL_SEED_EXPLICIT && n_seeds == 1) sv.solve_with_fallback(seeds + 5 * i, r);
+        else if (seed_mode == PNJL_SEED_EXPLICIT) sv.solve_multi(seeds + 5 * n_seeds * i, n_seeds, r);
+        else if (seed_mode == PNJL_SEED_AUTO) { double x0[5]; default_seed(2, T[i], mu[i], x0); sv.solve_with_fallback(x0, r); }
+        else sv.solve_multi(nullptr, 6, r);
+        fill_record(r, T[i], mu[i], xi[i], sv.n_fj, sv.n_th, records + PNJL_REC_DOUBLES * i);
+    }
+}
+
+struct Sink {
+    double* base;
+    double xi;
+    void operator()(int it, const PointRes& r, double T_fm, double mu_fm, int n_fj, int n_th) {
+        fill_record(r, T_fm, mu_fm, xi, n_fj, n_th, base + PNJL_REC_DOUBLES * it);
+    }
+};
+
+void hostsim_scan_lines(const pnjl_config* c, int64_t n_lines, const double* muq_MeV, const double* xi,
+                        const int32_t* table_idx, int32_t n_T, const double* T_MeV, int32_t n_tables,
+                        const pnjl_boundary* tables, double* records) {
+    Model m = model_of(c);
+    SolverParams sp = params_of(c);
+    HostMesh mesh = mesh_of(c);
+    PhaseTables* pt = new PhaseTables();
+    pt->n_tables = n_tables;
+    for (int t = 0; t < n_tables; ++t) {
+        pt->n[t] = tables[t].n;
+        pt->T_CEP[t] = tables[t].T_CEP_MeV;
+        for (int i = 0; i < tables[t].n; ++i) { pt->T[t][i] = tables[t].T_MeV[i]; pt->mu[t][i] = tables[t].mu_c_MeV[i]; }
+    }
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t l = 0; l < n_lines; ++l) {
+        HostEval ev{&m, &mesh};
+        Solver<HostEval> sv(m, sp, ev);
+        Sink sink{records + PNJL_REC_DOUBLES * n_T * l, xi[l]};
+        scan_line(sv, pt, table_idx ? table_idx[l] : -1, muq_MeV[l], xi[l], n_T, T_MeV, sink);
+    }
+    delete pt;
+}
+
+}  // extern "C"

@@ -1,0 +1,92 @@
+"""Loader of the TEST-ONLY host build of the product's math/solver headers (see hostsim.cpp)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from julia_relaxtime_b200 import _abi
+from julia_relaxtime_b200.constants import DEFAULT
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "hostsim.cpp")
+LIB = os.path.join(HERE, "_hostsim.so")
+CSRC = os.path.join(HERE, "..", "..", "julia_relaxtime_b200", "csrc")
+
+
+def build():
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("pnjl_math.cuh", "pnjl_solver.cuh")]
+    if os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps):
+        return LIB
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-fno-fast-math", "-fopenmp", "-fPIC", "-shared",
+                           "-Wno-unknown-pragmas", "-o", LIB, SRC])
+    return LIB
+
+
+class HostSim:
+    def __init__(self, p_nodes, p_w, c_nodes, c_w, max_iter=1000, tr_fallback=True, auto_multiseed_fallback=True,
+                 omega_tie_rel=1e-12, consts=DEFAULT):
+        self.lib = C.CDLL(build())
+        self.keep = [np.ascontiguousarray(a, dtype=np.float64) for a in (p_nodes, p_w, c_nodes, c_w)]
+        k = consts
+        self.cfg = _abi.PnjlConfig(
+            hbarc=k.hbarc, Lambda=k.Lambda_inv_fm, m_ud0=k.m_ud0_inv_fm, m_s0=k.m_s0_inv_fm, G=k.G_fm2, K=k.K_fm5,
+            T0=k.T0_inv_fm, a0=k.a0, a1=k.a1, a2=k.a2, b3=k.b3, rho0=k.rho0_fm3, Nc=k.N_color,
+            p_num=len(self.keep[0]), t_num=len(self.keep[2]), p_nodes=_abi.dptr(self.keep[0]),
+            p_w=_abi.dptr(self.keep[1]), c_nodes=_abi.dptr(self.keep[2]), c_w=_abi.dptr(self.keep[3]),
+            xtol=1e-9, ftol=1e-9, residual_norm_max=1e-6, phi_tol=1e-8, max_iter=max_iter,
+            tr_fallback=int(tr_fallback), auto_multiseed_fallback=int(auto_multiseed_fallback),
+            omega_tie_rel=omega_tie_rel, device=-1, lanes_per_solve=0)
+
+    def fj(self, x, T, mu, xi):
+        x = _abi.as_f64(x)
+        F = np.zeros(5)
+        J = np.zeros((5, 5))
+        self.lib.hostsim_fj(C.byref(self.cfg), _abi.dptr(x), C.c_double(T), C.c_double(mu), C.c_double(xi),
+                            _abi.dptr(F), _abi.dptr(J))
+        return F, J
+
+    def thermo(self, x, T, mu, xi):
+        x = _abi.as_f64(x)
+        o = np.zeros(17)
+        self.lib.hostsim_thermo(C.byref(self.cfg), _abi.dptr(x), C.c_double(T), C.c_double(mu), C.c_double(xi),
+                                _abi.dptr(o))
+        return dict(omega=o[0], pressure=o[1], rho_norm=o[2], entropy=o[3], energy=o[4], rho=o[5:8].copy(),
+                    masses=o[8:11].copy(), n_q=o[11:14].copy(), n_qbar=o[14:17].copy())
+
+    def solve_points(self, T, mu, xi, seed_mode=_abi.SEED_MULTI, seeds=None):
+        T = _abi.as_f64(T)
+        n = T.size
+        mu = _abi.as_f64(mu, n)
+        xi = _abi.as_f64(xi, n)
+        n_seeds = 6
+        sp = None
+        if seed_mode == _abi.SEED_EXPLICIT:
+            seeds = np.ascontiguousarray(seeds, dtype=np.float64).reshape(n, -1, 5)
+            n_seeds = seeds.shape[1]
+            sp = _abi.dptr(seeds)
+        rec = np.zeros((n, _abi.REC_DOUBLES))
+        self.lib.hostsim_solve_points(C.byref(self.cfg), C.c_int64(n), _abi.dptr(T), _abi.dptr(mu), _abi.dptr(xi),
+                                      C.c_int32(seed_mode), C.c_int32(n_seeds), sp, _abi.dptr(rec))
+        return rec
+
+    def scan_lines(self, muq_MeV, xi, T_MeV, tables=(), table_idx=None):
+        muq_MeV = _abi.as_f64(muq_MeV)
+        n_lines = muq_MeV.size
+        xi = _abi.as_f64(xi, n_lines)
+        T_MeV = _abi.as_f64(T_MeV)
+        keep = []
+        ctabs = (_abi.PnjlBoundary * max(1, len(tables)))()
+        for i, (tt, mm, tcep) in enumerate(tables):
+            tt = _abi.as_f64(tt)
+            mm = _abi.as_f64(mm)
+            keep += [tt, mm]
+            ctabs[i] = _abi.PnjlBoundary(_abi.dptr(tt), _abi.dptr(mm), tt.size, tcep)
+        if table_idx is None:
+            table_idx = np.full(n_lines, -1, dtype=np.int32)
+        table_idx = np.ascontiguousarray(table_idx, dtype=np.int32)
+        rec = np.zeros((n_lines, T_MeV.size, _abi.REC_DOUBLES))
+        self.lib.hostsim_scan_lines(C.byref(self.cfg), C.c_int64(n_lines), _abi.dptr(muq_MeV), _abi.dptr(xi),
+                                    _abi.iptr(table_idx), C.c_int32(T_MeV.size), _abi.dptr(T_MeV),
+                                    C.c_int32(len(tables)), ctabs, _abi.dptr(rec))
+        return rec

@@ -1,0 +1,218 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the reference's golden CSV.
+
+Tolerance (BASELINE.json north_star): |Δ|/|x| ≤ 1e-9 on φ, Φ, Φ̄ and masses, same converged branch.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from julia_relaxtime_b200 import _abi as A
+from oracle.oracle import HBARC, Oracle, load_phase_tables
+from tests.golden_io import GOLDEN, golden_lines, read_scan_csv, rel
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9
+
+
+def engine(**kw):
+    from julia_relaxtime_b200._lib import Engine
+    return Engine(**kw)
+
+
+def state_errors(rec, res):
+    """Per-point worst relative error over (φ_u, φ_d, φ_s, Φ, Φ̄, M_u, M_d, M_s); Φ, Φ̄ below 1e-3 are
+    compared on the 1e-3 scale (they are exponentially small in the confined phase)."""
+    rec = rec.reshape(-1, A.REC_DOUBLES)
+    worst = np.zeros(rec.shape[0])
+    for q in range(5):
+        scale = np.maximum(np.abs(res.x[q]), 1e-3 if q >= 3 else 1e-300)
+        worst = np.maximum(worst, np.abs(rec[:, A.REC_X + q] - res.x[q]) / scale)
+    for q in range(3):
+        worst = np.maximum(worst, rel(rec[:, A.REC_MASS + q], res.mass[q]))
+    return worst
+
+
+def assert_state_parity(rec, res, tol=TOL, label=""):
+    rec = rec.reshape(-1, A.REC_DOUBLES)
+    st = rec[:, A.REC_STATUS].astype(np.int64)
+    conv_g = (st & A.ST_CONVERGED) != 0
+    assert (conv_g == res.converged).all(), (label, np.nonzero(conv_g != res.converged)[0][:10])
+    w = state_errors(rec, res)[conv_g]
+    assert w.max() <= tol, (label, w.max(), np.nonzero(w > tol)[0][:10])
+    return w.max()
+
+
+def test_fp64_peak_and_stats():
+    e = engine(p_num=12, t_num=6)
+    tf, mhz = e.measure_fp64_peak()
+    print("FP64 DFMA peak: %.2f TFLOP/s (implied SM clock %.0f MHz at 64 lanes/SM)" % (tf, mhz))
+    assert 10.0 < tf < 60.0
+
+
+@pytest.mark.parametrize("p_num,t_num", [(12, 6), (64, 8), (64, 16)])
+def test_fj_pass_matches_oracle_ad(p_num, t_num):
+    """One Ω-gradient/Jacobian pass: analytic derivatives + warp reduction vs nested-dual AD on the CPU."""
+    o = Oracle(p_num=p_num, t_num=t_num)
+    e = engine(p_num=p_num, t_num=t_num, nodes=(o.p_nodes, o.p_w, o.c_nodes, o.c_w))
+    rng = np.random.default_rng(0)
+    n = 48
+    T = rng.uniform(30, 400, n) / HBARC
+    mu = rng.uniform(0, 400, n) / HBARC
+    xi = rng.uniform(-0.6, 0.8, n)
+    x = np.stack([rng.uniform(-2.2, 0.3, n), rng.uniform(-2.2, 0.3, n), rng.uniform(-2.4, -0.3, n),
+                  rng.uniform(-0.05, 1.02, n), rng.uniform(-0.05, 1.02, n)], axis=1)
+    F, J = e.eval_fj(T, mu, xi, x)
+    for i in range(n):
+        F0, J0 = o.FJ(x[i], T[i], mu[i], xi[i])
+        assert np.abs(F[i] - F0).max() <= 1e-11 * (np.abs(F0).max() + 1e-3)
+        assert np.abs(J[i] - J0).max() <= 1e-11 * np.abs(J0).max()
+
+
+def test_library_nodes_match_oracle_nodes():
+    from julia_relaxtime_b200._lib import gauleg
+    o = Oracle(p_num=64, t_num=16)
+    x, w = gauleg(0.0, 10.0, 64)
+    assert np.abs(x - o.p_nodes).max() < 2e-15 and np.abs(w - o.p_w).max() < 2e-15
+
+
+@pytest.mark.parametrize("lanes", [8, 16, 32])
+def test_golden_scan_lines(lanes):
+    """The reference's committed scan (406 rows) reproduced on the GPU through pnjl_scan_lines_host."""
+    cols = read_scan_csv(os.path.join(GOLDEN, "gap_transport_scan_xi-0p6to0p6.csv"))
+    lines = golden_lines(cols)
+    xis = sorted(set(cols["xi"]))
+    tables, index = load_phase_tables(os.path.join(GOLDEN, "boundary.csv"), os.path.join(GOLDEN, "cep.csv"), xis)
+    e = engine(p_num=12, t_num=6, max_iter=40, lanes_per_solve=lanes)
+    e.set_boundaries(tables)
+    T = cols["T_MeV"][lines[0][2]]
+    muq = np.array([l[1] / 3.0 for l in lines])
+    lxi = np.array([l[0] for l in lines])
+    tidx = np.array([index[l[0]] for l in lines], dtype=np.int32)
+    rec = e.scan_lines(muq, lxi, T, tidx).reshape(-1, A.REC_DOUBLES)
+    order = np.concatenate([l[2] for l in lines])
+    first = np.zeros(len(order), bool)
+    first[::29] = True
+    st = rec[:, A.REC_STATUS].astype(int)
+    assert ((st & A.ST_CONVERGED) != 0).all()
+    for name, off in [("Phi", 3), ("Phibar", 4), ("m_u", 5), ("m_d", 6), ("m_s", 7), ("omega_fm4inv", 8),
+                      ("P_fm4inv", 9), ("epsilon_fm4inv", 12), ("s_fm3inv", 11), ("n_u", 13), ("n_s", 15),
+                      ("n_ubar", 16), ("n_sbar", 18)]:
+        r = rel(rec[:, off], cols[name][order])
+        assert r[~first].max() <= TOL, (name, r[~first].max())
+        assert r[first].max() <= 1e-8, (name, r[first].max())   # MultiSeed tie-break rows
+    np.testing.assert_array_equal(rec[~first, A.REC_ITER].astype(int), cols["iterations"][order][~first].astype(int))
+    print("golden continuity rows (lanes=%d): max rel Phi %.2e, m_u %.2e" % (
+        lanes, rel(rec[:, 3], cols["Phi"][order])[~first].max(), rel(rec[:, 5], cols["m_u"][order])[~first].max()))
+
+
+def test_points_multiseed_vs_oracle():
+    o = Oracle(p_num=12, t_num=6, max_iter=40)
+    e = engine(p_num=12, t_num=6, max_iter=40, nodes=(o.p_nodes, o.p_w, o.c_nodes, o.c_w))
+    rng = np.random.default_rng(1)
+    n = 600
+    T = rng.uniform(20, 400, n) / HBARC
+    mu = rng.uniform(0, 450, n) / HBARC
+    xi = rng.uniform(-0.8, 0.8, n)
+    res = o.solve_points(T, mu, xi, "multi")
+    rec = e.solve_points(T, mu, xi, A.SEED_MULTI)
+    w = assert_state_parity(rec, res, label="multi")
+    st = rec[:, A.REC_STATUS].astype(int)
+    same_seed = ((st >> 4) & 7) == ((res.status >> 4) & 7)
+    print("multiseed: worst rel %.2e; same chosen seed %d/%d" % (w, same_seed.sum(), n))
+    assert same_seed.mean() > 0.99
+    assert rel(rec[:, A.REC_OMEGA], res.omega).max() < 1e-11
+
+
+def test_points_auto_seed_and_reference_regression_points():
+    """DefaultSeed(:auto) + fallbacks, incl. the two regression points of
+    tests/unit/pnjl/test_solver_random_physical_smoke.jl:33-54 (p=12, t=4)."""
+    o = Oracle(p_num=12, t_num=4)
+    e = engine(p_num=12, t_num=4, nodes=(o.p_nodes, o.p_w, o.c_nodes, o.c_w))
+    T = np.array([48.269077, 288.453662]) / HBARC
+    mu = np.array([972.640900, 563.275131]) / 3.0 / HBARC
+    xi = np.array([0.479315, -0.652469])
+    rng = np.random.default_rng(2)
+    n = 200
+    T = np.concatenate([T, rng.uniform(1, 350, n) / HBARC])
+    mu = np.concatenate([mu, rng.uniform(0, 600, n) / HBARC])
+    xi = np.concatenate([xi, rng.uniform(-0.8, 0.8, n)])
+    res = o.solve_points(T, mu, xi, "auto")
+    rec = e.solve_points(T, mu, xi, A.SEED_AUTO)
+    assert_state_parity(rec, res, label="auto")
+    st = rec[:, A.REC_STATUS].astype(int)
+    assert (st[:2] & A.ST_CONVERGED).all()
+    assert (rec[:2, 3:5] >= -1e-8).all() and (rec[:2, 3:5] <= 1 + 1e-8).all() and (rec[:2, 5:8] > 0).all()
+
+
+def test_config1_single_point_default_nodes():
+    """BASELINE config 1: T=150 MeV, mu=0, xi=0, 64x8 nodes, DefaultSeed and MultiSeed."""
+    o = Oracle(p_num=64, t_num=8)
+    e = engine(p_num=64, t_num=8, nodes=(o.p_nodes, o.p_w, o.c_nodes, o.c_w))
+    T = np.array([150.0 / HBARC])
+    for mode, omode in ((A.SEED_AUTO, "auto"), (A.SEED_MULTI, "multi")):
+        res = o.solve_points(T, [0.0], [0.0], omode)
+        rec = e.solve_points(T, [0.0], [0.0], mode)
+        assert_state_parity(rec, res, label="cfg1")
+        assert int(rec[0, A.REC_ITER]) == int(res.iterations[0])
+    rec = e.solve_points(T, [0.0], [0.0], A.SEED_AUTO)
+    assert abs(rec[0, A.REC_MASS] - 1.84419432518967) < 1e-9      # SURVEY §8c item 4 probe value
+    assert abs(rec[0, A.REC_OMEGA] - (-21.6179127301546)) < 1e-9
+
+
+def test_lines_cross_first_order_region_vs_oracle():
+    """Config-2-like slab: 24 mu-lines x 96 T at 12x6 nodes, through the first-order region and the CEP."""
+    o = Oracle(p_num=12, t_num=6, max_iter=40)
+    tables, index = load_phase_tables(os.path.join(GOLDEN, "boundary.csv"), os.path.join(GOLDEN, "cep.csv"), [0.0, 0.2])
+    e = engine(p_num=12, t_num=6, max_iter=40, nodes=(o.p_nodes, o.p_w, o.c_nodes, o.c_w))
+    e.set_boundaries(tables)
+    T = np.linspace(50, 300, 96)
+    muq = np.concatenate([np.linspace(0, 400, 16), np.linspace(300, 370, 8)])
+    xi = np.concatenate([np.zeros(16), np.full(8, 0.2)])
+    tidx = np.array([index[x] for x in xi], dtype=np.int32)
+    res = o.scan_lines(muq, xi, T, tables, tidx)
+    rec = e.scan_lines(muq, xi, T, tidx)
+    assert_state_parity(rec, res, label="lines")
+    r = rec.reshape(-1, A.REC_DOUBLES)
+    assert (r[:, A.REC_ITER].astype(int) == res.iterations).mean() > 0.995
+    assert ((r[:, A.REC_STATUS].astype(int) & A.ST_PHASE_SWITCH) != 0).sum() == ((res.status & A.ST_PHASE_SWITCH) != 0).sum()
+    for off, arr in ((A.REC_ENTROPY, res.entropy), (A.REC_ENERGY, res.energy), (A.REC_PRESSURE, res.pressure)):
+        assert (np.abs(r[:, off] - arr) <= 1e-9 * np.maximum(np.abs(arr), 1e-2)).all()
+    for q in range(3):
+        assert (np.abs(r[:, A.REC_NQ + q] - res.n_q[q]) <= 1e-9 * np.maximum(np.abs(res.n_q[q]), 1e-6)).all()
+        assert (np.abs(r[:, A.REC_NQBAR + q] - res.n_qbar[q]) <= 1e-9 * np.maximum(np.abs(res.n_qbar[q]), 1e-6)).all()
+
+
+def test_fine_mesh_lines_vs_oracle():
+    """64x16 mesh (configs 3-5), a few anisotropic lines."""
+    o = Oracle(p_num=64, t_num=16, max_iter=40)
+    tables, index = load_phase_tables(os.path.join(GOLDEN, "boundary.csv"), os.path.join(GOLDEN, "cep.csv"), [0.0, 0.4])
+    e = engine(p_num=64, t_num=16, max_iter=40, nodes=(o.p_nodes, o.p_w, o.c_nodes, o.c_w))
+    e.set_boundaries(tables)
+    T = np.linspace(50, 300, 24)
+    muq = np.array([0.0, 150.0, 320.0, 345.0, 400.0, 100.0, 330.0, 250.0])
+    xi = np.array([0.0, 0.0, 0.0, 0.0, 0.0, 0.4, 0.4, -0.6])
+    tidx = np.array([index.get(x, -1) for x in xi], dtype=np.int32)
+    res = o.scan_lines(muq, xi, T, tables, tidx)
+    rec = e.scan_lines(muq, xi, T, tidx)
+    assert_state_parity(rec, res, label="fine")
+
+
+def test_edge_cases():
+    e = engine(p_num=12, t_num=6, max_iter=40)
+    # empty inputs
+    assert e.solve_points(np.zeros(0), np.zeros(0), np.zeros(0)).shape == (0, A.REC_DOUBLES)
+    assert e.scan_lines(np.zeros(0), np.zeros(0), np.array([100.0])).shape == (0, 1, A.REC_DOUBLES)
+    # a non-finite seed residual is a status, not a crash (NLsolve IsFiniteException)
+    seeds = np.array([[np.nan, -1.8, -2.2, 0.1, 0.1]])
+    rec = e.solve_points([150.0 / HBARC], [0.0], [0.0], A.SEED_EXPLICIT, seeds)
+    assert int(rec[0, A.REC_STATUS]) & A.ST_NONFINITE
+    assert not int(rec[0, A.REC_STATUS]) & A.ST_CONVERGED
+    # ragged: one line, one T
+    rec = e.scan_lines([100.0], [0.0], [150.0])
+    assert int(rec[0, 0, A.REC_STATUS]) & A.ST_CONVERGED
+    # explicit seed list goes through solve_multi and reports the chosen index
+    seeds = np.array([[[-0.3, -0.3, -0.9, 0.9, 0.9], [-1.84329, -1.84329, -2.22701, 1e-5, 4e-5]]])
+    rec = e.solve_points([100.0 / HBARC], [0.0], [0.0], A.SEED_EXPLICIT, seeds)
+    assert int(rec[0, A.REC_STATUS]) & A.ST_USED_MULTISEED
