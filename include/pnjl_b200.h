@@ -160,8 +160,9 @@ typedef struct pnjl_stats {
 int pnjl_get_stats(pnjl_handle* h, pnjl_stats* out);
 
 /* FP64 FMA peak of the device (register-resident DFMA chains; the roofline denominator the north
- * star asks for, since MEASURED_PEAKS.json has no FP64 figure).  Returns TFLOP/s in *tflops. */
-int pnjl_measure_fp64_peak(pnjl_handle* h, double* tflops, double* sm_clock_mhz_est);
+ * star asks for, since MEASURED_PEAKS.json has no FP64 figure).  *tflops_burst = best single launch;
+ * *tflops_sustained (may be NULL) = average over back-to-back launches lasting `seconds`. */
+int pnjl_measure_fp64_peak(pnjl_handle* h, double seconds, double* tflops_burst, double* tflops_sustained);
 
 #ifdef __cplusplus
 }

@@ -76,7 +76,7 @@ def load():
                                          C.c_void_p, C.c_void_p]
     L.pnjl_eval_fj_host.argtypes = [H, C.c_int64, dp, dp, dp, dp, dp]
     L.pnjl_get_stats.argtypes = [H, C.POINTER(_abi.PnjlStats)]
-    L.pnjl_measure_fp64_peak.argtypes = [H, dp, dp]
+    L.pnjl_measure_fp64_peak.argtypes = [H, C.c_double, dp, dp]
     if L.pnjl_abi_version() != _abi.ABI_VERSION:
         raise PnjlError("ABI version mismatch between _abi.py and libpnjl_b200.so")
     _LIB = L
@@ -217,8 +217,10 @@ class Engine:
         self._check(self.L.pnjl_get_stats(self.h, C.byref(s)), "pnjl_get_stats")
         return {f[0]: getattr(s, f[0]) for f in _abi.PnjlStats._fields_}
 
-    def measure_fp64_peak(self):
-        tf = C.c_double()
-        mhz = C.c_double()
-        self._check(self.L.pnjl_measure_fp64_peak(self.h, C.byref(tf), C.byref(mhz)), "pnjl_measure_fp64_peak")
-        return tf.value, mhz.value
+    def measure_fp64_peak(self, seconds=1.0):
+        """(burst, sustained) FP64 FMA throughput in TFLOP/s of a register-resident DFMA kernel."""
+        burst = C.c_double()
+        sus = C.c_double()
+        self._check(self.L.pnjl_measure_fp64_peak(self.h, float(seconds), C.byref(burst), C.byref(sus)),
+                    "pnjl_measure_fp64_peak")
+        return burst.value, sus.value

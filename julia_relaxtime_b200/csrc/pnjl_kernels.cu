@@ -742,13 +742,14 @@ int pnjl_get_stats(pnjl_handle* h, pnjl_stats* out) {
     return PNJL_OK;
 }
 
-int pnjl_measure_fp64_peak(pnjl_handle* h, double* tflops, double* sm_clock_mhz_est) {
-    if (!h || !tflops) return fail(PNJL_ERR_ARG, "null argument");
+int pnjl_measure_fp64_peak(pnjl_handle* h, double seconds, double* tflops_burst, double* tflops_sustained) {
+    if (!h || !tflops_burst) return fail(PNJL_ERR_ARG, "null argument");
     DeviceGuard guard(h->device);
     const int threads = 256, blocks = h->sm_count * 8, iters = 4096;
     double* d_out = nullptr;
     CUDA_TRY(cudaMalloc(&d_out, sizeof(double) * threads * blocks));
     cudaStream_t st = h->stream;
+    const double fmas = (double)threads * blocks * (double)iters * 16.0 * 8.0;
     double best_ms = 1e30;
     for (int rep = 0; rep < 6; ++rep) {
         CUDA_TRY(cudaEventRecord(h->ev0, st));
@@ -759,13 +760,20 @@ int pnjl_measure_fp64_peak(pnjl_handle* h, double* tflops, double* sm_clock_mhz_
         CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
         if (rep >= 1 && ms < best_ms) best_ms = ms;
     }
-    cudaFree(d_out);
-    const double fmas = (double)threads * blocks * (double)iters * 16.0 * 8.0;
-    *tflops = 2.0 * fmas / (best_ms * 1e-3) / 1e12;
-    if (sm_clock_mhz_est) {
-        // 64 FP64 FMA lanes per SM per clock (assumed; reported for cross-checking against nvidia-smi)
-        *sm_clock_mhz_est = fmas / (best_ms * 1e-3) / (64.0 * h->sm_count) / 1e6;
+    *tflops_burst = 2.0 * fmas / (best_ms * 1e-3) / 1e12;
+    if (tflops_sustained) {
+        // back-to-back launches for `seconds` (power-capped clocks), one event pair around the whole train
+        int reps = (int)(seconds * 1e3 / best_ms) + 1;
+        if (reps > 100000) reps = 100000;
+        CUDA_TRY(cudaEventRecord(h->ev0, st));
+        for (int rep = 0; rep < reps; ++rep) k_dfma_peak<<<blocks, threads, 0, st>>>(d_out, iters, 2.0 + rep);
+        CUDA_TRY(cudaEventRecord(h->ev1, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        *tflops_sustained = 2.0 * fmas * reps / (ms * 1e-3) / 1e12;
     }
+    cudaFree(d_out);
     return PNJL_OK;
 }
 

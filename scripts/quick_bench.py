@@ -60,7 +60,7 @@ def run_points(p, t, n, mode=A.SEED_MULTI, lanes=0):
 
 if __name__ == "__main__":
     e = Engine(p_num=12, t_num=6)
-    print("fp64 peak TFLOP/s, implied MHz:", e.measure_fp64_peak())
+    print("fp64 peak TFLOP/s (burst, sustained):", e.measure_fp64_peak())
     del e
     run_lines(12, 6, 128, 128, [0.0])
     run_lines(64, 16, 256, 64, [0.0, 0.2])
