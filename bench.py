@@ -208,7 +208,13 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--n-mu", type=int, default=0, help="override the mu density (profiling runs only; recorded in config)")
+    ap.add_argument("--n-t", type=int, default=0, help="override the T density (profiling runs only; recorded in config)")
     args = ap.parse_args()
+    if args.n_mu or args.n_t:
+        k, xs, nm, mr, nt, tr, pp, tt = WORKLOADS[args.workload]
+        WORKLOADS[args.workload] = (k, xs, args.n_mu or nm, mr, args.n_t or nt, tr, pp, tt)
+        DESCR[args.workload] += " [REDUCED GRID for profiling: n_mu=%d n_T=%d]" % (args.n_mu or nm, args.n_t or nt)
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
     if args.impl == "reference":
