@@ -46,9 +46,11 @@ MAX_ITER = 40
 HBARC = 197.327
 
 
-def alg_flops(n_nodes, n_fj, n_th):
-    """123 FLOP per node x flavour of an Omega-gradient/Jacobian pass, 54 per thermo-pass unit."""
-    return n_nodes * 3 * (123.0 * n_fj + 54.0 * n_th)
+def alg_flops(n_nodes, n_fj, n_th, n_flav=3):
+    """123 FLOP per node x flavour of an Omega-gradient/Jacobian pass, 54 per thermo-pass unit.
+    n_flav = flavours actually evaluated per node: 2 when the kernel uses M_u == M_d (isospin_symmetric, the
+    default: every state on these grids has phi_u == phi_d), 3 for the reference's loop."""
+    return n_nodes * n_flav * (123.0 * n_fj + 54.0 * n_th)
 
 
 class ClockSampler:
@@ -335,7 +337,8 @@ def main():
     total_ms, kernel_ms = float(tot[0]), float(tot[1])
     n_conv, n_fj, n_th = (float(v) for v in cnt)
     value = n_conv * args.steps / (total_ms * 1e-3)
-    fl = alg_flops(n_nodes, n_fj, n_th)               # whole job, one step
+    fl = alg_flops(n_nodes, n_fj, n_th, 2)            # whole job, one step, flavours actually evaluated (u == d)
+    fl_ref = alg_flops(n_nodes, n_fj, n_th, 3)        # same passes counted the way the reference loops (3 flavours)
     st = eng.stats()
 
     # ---- e2e: the reference-facing call with HOST buffers (pnjl_scan_lines_host / pnjl_solve_points_host):
@@ -406,7 +409,9 @@ def main():
                               "frac": achieved / (peak_sus * world), "traffic": traffic,
                               "peak_source": "DFMA microbenchmark run in this process (pnjl_measure_fp64_peak): sustained %.2f, "
                                              "burst %.2f TFLOP/s per GPU; MEASURED_PEAKS.json has no FP64 figure" % (peak_sus, peak_burst),
-                              "algorithmic_flop_per_step": fl, "fj_passes_per_point": n_fj / max(1.0, float(n_total)),
+                              "algorithmic_flop_per_step": fl, "flavours_evaluated": 2,
+                              "reference_equivalent_tflops": fl_ref * args.steps / (kernel_ms * 1e-3) / 1e12,
+                              "fj_passes_per_point": n_fj / max(1.0, float(n_total)),
                               "thermo_passes_per_point": n_th / max(1.0, float(n_total)),
                               "kernel_ms_per_step": kernel_ms / args.steps}, **extra),
             "gpu_launches": int(args.steps) * world,

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define PNJL_ABI_VERSION 1
+#define PNJL_ABI_VERSION 2
 
 /* ---- result record layout (doubles) --------------------------------------------------------- */
 #define PNJL_REC_DOUBLES 32
@@ -103,6 +103,10 @@ typedef struct pnjl_config {
     double omega_tie_rel;           /* MultiSeed argmin-Omega tie window (relative); ties -> lowest seed index. 1e-12 */
     int32_t device;                 /* CUDA device ordinal; -1 = current device */
     int32_t lanes_per_solve;        /* 0 = auto (8/16/32 by mesh size); else 8, 16 or 32 */
+    int32_t isospin_symmetric;      /* 1 (default): when phi_u == phi_d bitwise (always true from the built-in seeds, since
+                                       mu_u = mu_d and m_u0 = m_d0 on this path) evaluate the d flavour as the u flavour and
+                                       keep Newton/dogleg steps u<->d symmetric (a <= 1 ulp change of the step).  0: three
+                                       independent flavours everywhere, like the reference's loop (Integrals.jl:250-257). */
 } pnjl_config;
 
 /* First-order phase boundary mu_c(T) for one xi (data/reference/pnjl/boundary.csv + cep.csv;
@@ -147,6 +151,10 @@ int pnjl_scan_lines_device(pnjl_handle* h, int64_t n_lines, const double* d_muq_
  * FJ: [n][30] = F[5] then J[5][5] row-major. */
 int pnjl_eval_fj_host(pnjl_handle* h, int64_t n, const double* T_fm, const double* mu_fm, const double* xi,
                       const double* x /* [n][5] */, double* FJ);
+
+/* Accuracy self-test of the kernels' branch-free FP64 primitives (test hook):
+ * which = 0: exp(x) for x in [-708, 0];  1: 1/x;  2: 1/sqrt(x)  (x normal, positive for 1 and 2). */
+int pnjl_selftest_math(pnjl_handle* h, int64_t n, const double* x, int32_t which, double* out);
 
 /* Measured launch statistics of the last *_device / *_host call on this handle. */
 typedef struct pnjl_stats {

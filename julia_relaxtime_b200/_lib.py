@@ -75,6 +75,7 @@ def load():
     L.pnjl_scan_lines_device.argtypes = [H, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                          C.c_void_p, C.c_void_p]
     L.pnjl_eval_fj_host.argtypes = [H, C.c_int64, dp, dp, dp, dp, dp]
+    L.pnjl_selftest_math.argtypes = [H, C.c_int64, dp, C.c_int32, dp]
     L.pnjl_get_stats.argtypes = [H, C.POINTER(_abi.PnjlStats)]
     L.pnjl_measure_fp64_peak.argtypes = [H, C.c_double, dp, dp]
     if L.pnjl_abi_version() != _abi.ABI_VERSION:
@@ -86,7 +87,7 @@ def load():
 EXPORTED_SYMBOLS = [
     "pnjl_default_config", "pnjl_abi_version", "pnjl_last_error", "pnjl_create", "pnjl_destroy", "pnjl_gauleg",
     "pnjl_solve_points_host", "pnjl_solve_points_device", "pnjl_set_boundaries", "pnjl_scan_lines_host",
-    "pnjl_scan_lines_device", "pnjl_eval_fj_host", "pnjl_get_stats", "pnjl_measure_fp64_peak"]
+    "pnjl_scan_lines_device", "pnjl_eval_fj_host", "pnjl_selftest_math", "pnjl_get_stats", "pnjl_measure_fp64_peak"]
 
 
 def gauleg(a, b, n):
@@ -105,7 +106,7 @@ class Engine:
 
     def __init__(self, p_num=64, t_num=8, max_iter=1000, trust_region_fallback=True, auto_multiseed_fallback=True,
                  residual_norm_max=1e-6, omega_tie_rel=1e-12, device=-1, lanes_per_solve=0, nodes=None,
-                 consts: PNJLConstants = DEFAULT):
+                 isospin_symmetric=True, consts: PNJLConstants = DEFAULT):
         self.L = load()
         self.p_num, self.t_num = int(p_num), int(t_num)
         self._keep = None
@@ -116,7 +117,8 @@ class Engine:
             p_num=self.p_num, t_num=self.t_num, p_nodes=None, p_w=None, c_nodes=None, c_w=None,
             xtol=1e-9, ftol=1e-9, residual_norm_max=residual_norm_max, phi_tol=1e-8, max_iter=int(max_iter),
             tr_fallback=int(trust_region_fallback), auto_multiseed_fallback=int(auto_multiseed_fallback),
-            omega_tie_rel=omega_tie_rel, device=int(device), lanes_per_solve=int(lanes_per_solve))
+            omega_tie_rel=omega_tie_rel, device=int(device), lanes_per_solve=int(lanes_per_solve),
+            isospin_symmetric=int(isospin_symmetric))
         if nodes is not None:
             self._keep = [np.ascontiguousarray(a, dtype=np.float64) for a in nodes]
             cfg.p_nodes, cfg.p_w, cfg.c_nodes, cfg.c_w = [_abi.dptr(a) for a in self._keep]
@@ -211,6 +213,14 @@ class Engine:
             self.h, d_muq.numel(), d_muq.data_ptr(), d_xi.data_ptr(),
             d_table_idx.data_ptr() if d_table_idx is not None else None, d_T.numel(), d_T.data_ptr(),
             d_records.data_ptr(), C.c_void_p(stream)), "pnjl_scan_lines_device")
+
+    def selftest_math(self, x, which):
+        """which: 'exp' (x in [-708, 0]), 'rcp', 'rsqrt' — the kernels' branch-free primitives evaluated on the GPU."""
+        x = _abi.as_f64(x)
+        out = np.empty_like(x)
+        self._check(self.L.pnjl_selftest_math(self.h, x.size, _abi.dptr(x), {"exp": 0, "rcp": 1, "rsqrt": 2}[which],
+                                              _abi.dptr(out)), "pnjl_selftest_math")
+        return out
 
     def stats(self):
         s = _abi.PnjlStats()

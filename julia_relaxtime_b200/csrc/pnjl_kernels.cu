@@ -15,9 +15,11 @@
 // ~7e3 FLOP per byte of HBM traffic, bounded by the FP64 pipe.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -30,7 +32,9 @@ struct DeviceConfig {
     Model m;
     SolverParams sp;
     int n_nodes;
-    int pad;
+    int lockstep;
+    double p2max, pc2max;   // mesh maxima (bound on E for the fast-path test)
+    unsigned long long* dbg;   // phase-profiling counters (PNJL_PROFILE_PHASES builds only)
     PhaseTables pt;
 };
 
@@ -38,16 +42,81 @@ struct DeviceConfig {
 template <int G>
 struct GroupEval {
     const Model* m;
-    const double* s_p2;
-    const double* s_pc2;
-    const double* s_coef;
-    int n;
+    MeshView mv;     // mesh in shared memory
+    int isospin;
     int lane;        // lane within the group
     unsigned mask;   // lanes of this group within the warp
+    int lockstep;    // CTA-wide phase alignment (G == 32 only), see bar_enter()
+    int* s_done;     // shared counter of warps that ran out of work
+#ifdef PNJL_PROFILE_PHASES
+    unsigned long long* dbg;
+    long long t_last, t0, t1;
+#endif
 
+    // Phase alignment.  The warps of a CTA alternate between the quadrature loops (a few KB of straight-line FP64
+    // code) and ~40 KB of scalar Newton / finishing code.  Left alone they drift apart, the SM's instruction cache
+    // then has to hold everything at once, misses on a third of its requests (ncu: sm__icc_requests_lookup_miss)
+    // and the FP64 pipe starves.  A named barrier in front of every quadrature loop keeps the warps of the CTA in
+    // the same phase, so the loop is fetched once and stays resident while it runs.
+    //   barrier 1 ("enter"): bar.sync by everybody;
+    //   barrier 2 ("leave"): bar.arrive (non-blocking, lockstep == 1) or bar.sync (lockstep == 3) by working warps.
+    // Warps that ran out of work keep both barriers going from drain() until every warp of the CTA is there, so
+    // the arrival count is always the full CTA and nothing relies on how exited warps are counted.
+    __device__ __forceinline__ bool aligned() const { return G == 32 && lockstep != 0; }
+    __device__ __forceinline__ void bar_enter() const {
+        asm volatile("bar.sync 1, %0;" ::"r"((int)blockDim.x) : "memory");
+    }
+    __device__ __forceinline__ void bar_leave(bool blocking) const {
+        if (blocking) asm volatile("bar.sync 2, %0;" ::"r"((int)blockDim.x) : "memory");
+        else asm volatile("bar.arrive 2, %0;" ::"r"((int)blockDim.x) : "memory");
+    }
+
+    __device__ __forceinline__ void pass_begin() {
+#ifdef PNJL_PROFILE_PHASES
+        t0 = clock64();
+        if (aligned()) bar_enter();
+        t1 = clock64();
+#else
+        if (aligned()) bar_enter();
+#endif
+    }
+    __device__ __forceinline__ void pass_end() {
+#ifdef PNJL_PROFILE_PHASES
+        const long long t2 = clock64();
+        if (aligned()) bar_leave(lockstep == 3);
+        const long long t3 = clock64();
+        if (lane == 0 && dbg) {
+            atomicAdd(dbg + 0, (unsigned long long)(t2 - t1));                 // loop cycles
+            atomicAdd(dbg + 1, (unsigned long long)((t1 - t0) + (t3 - t2)));   // barrier waits
+            atomicAdd(dbg + 2, 1ULL);                                          // passes
+            if (t_last) atomicAdd(dbg + 3, (unsigned long long)(t0 - t_last)); // scalar phase since the last pass
+        }
+        t_last = t3;
+#else
+        if (aligned()) bar_leave(lockstep == 3);
+#endif
+    }
+
+    // Out of work: count this warp in (between the two barriers, so that the value every drained warp reads after
+    // barrier 2 is the same) and keep the barriers going until all warps of the CTA have drained.
+    __device__ __forceinline__ void drain() const {
+        if (!aligned()) return;
+        const int n_warps = blockDim.x >> 5;
+        bool counted = false;
+        for (;;) {
+            bar_enter();
+            if (!counted && (threadIdx.x & 31) == 0) atomicAdd(s_done, 1);
+            counted = true;
+            bar_leave(true);
+            if (*((volatile int*)s_done) >= n_warps) break;
+        }
+    }
+
+    // Group-wide sum, bit-identical in every lane.  For G == 32 the mask is a compile-time constant, which
+    // keeps each step at SHFL.BFLY x2 + DADD (a runtime mask costs ~15 instructions per shuffle).
     __device__ __forceinline__ double gsum(double v) const {
 #pragma unroll
-        for (int off = G / 2; off > 0; off >>= 1) v += __shfl_xor_sync(mask, v, off);
+        for (int off = G / 2; off > 0; off >>= 1) v += __shfl_xor_sync(G == 32 ? 0xffffffffu : mask, v, off);
         return v;
     }
 
@@ -55,33 +124,41 @@ struct GroupEval {
         PointCtx c;
         make_ctx(*m, T, mu, xi, x, c);
         double acc[kFJAcc];
-#pragma unroll
-        for (int i = 0; i < kFJAcc; ++i) acc[i] = 0.0;
-        for (int k = lane; k < n; k += G) {
-            const double k2 = fma(xi, s_pc2[k], s_p2[k]);
-            const double cf = s_coef[k];
-            fj_node<0>(c, k2, cf, acc);
-            fj_node<1>(c, k2, cf, acc);
-            fj_node<2>(c, k2, cf, acc);
-        }
+        pass_begin();
+        const bool fast = fj_partial(*m, isospin != 0, c, x, mv, lane, G, acc);
+        pass_end();
 #pragma unroll
         for (int i = 0; i < kFJAcc; ++i) acc[i] = gsum(acc[i]);
-        finish_fj(*m, c, x, acc, F, J);
+        finish_fj(*m, c, x, acc, F, J, fast);
+    }
+
+    // Fused pass: F(x) and the Newton direction p = -J^{-1} F, with J and the 5x5 elimination in registers.
+    __device__ __noinline__ bool fj_step(double T, double mu, double xi, const double x[5], double F[5], double p[5]) {
+        PointCtx c;
+        make_ctx(*m, T, mu, xi, x, c);
+        double acc[kFJAcc];
+        pass_begin();
+        const bool fast = fj_partial(*m, isospin != 0, c, x, mv, lane, G, acc);
+        pass_end();
+#pragma unroll
+        for (int i = 0; i < kFJAcc; ++i) acc[i] = gsum(acc[i]);
+        double J[25], b[5];
+        finish_fj(*m, c, x, acc, F, J, fast);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) b[i] = F[i];
+        const bool ok = lu_solve5_regs(J, b, p);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) p[i] = -p[i];
+        return ok;
     }
 
     __device__ __noinline__ void thermo(double T, double mu, double xi, const double x[5], Thermo& th) {
         PointCtx c;
         make_ctx(*m, T, mu, xi, x, c);
         double acc[kThAcc];
-#pragma unroll
-        for (int i = 0; i < kThAcc; ++i) acc[i] = 0.0;
-        for (int k = lane; k < n; k += G) {
-            const double k2 = fma(xi, s_pc2[k], s_p2[k]);
-            const double cf = s_coef[k];
-            thermo_node<0>(c, k2, cf, acc);
-            thermo_node<1>(c, k2, cf, acc);
-            thermo_node<2>(c, k2, cf, acc);
-        }
+        pass_begin();
+        thermo_partial(*m, isospin != 0, c, x, mv, lane, G, acc);
+        pass_end();
 #pragma unroll
         for (int i = 0; i < kThAcc; ++i) acc[i] = gsum(acc[i]);
         finish_thermo(*m, c, x, acc, th);
@@ -89,20 +166,30 @@ struct GroupEval {
 };
 
 template <int G>
-__device__ __forceinline__ void stage_mesh(const double* __restrict__ g_mesh, int n, double* s_mesh) {
+__device__ __forceinline__ void stage_mesh(const double* __restrict__ g_mesh, int n, double* s_mesh, int* s_done) {
     for (int i = threadIdx.x; i < 3 * n; i += blockDim.x) s_mesh[i] = g_mesh[i];
+    if (threadIdx.x == 0) *s_done = 0;
     __syncthreads();
 }
 
 template <int G>
-__device__ __forceinline__ GroupEval<G> make_eval(const DeviceConfig* cfg, const double* s_mesh) {
+__device__ __forceinline__ GroupEval<G> make_eval(const DeviceConfig* cfg, const double* s_mesh, int* s_done) {
     GroupEval<G> ev;
     const int n = cfg->n_nodes;
     ev.m = &cfg->m;
-    ev.s_p2 = s_mesh;
-    ev.s_pc2 = s_mesh + n;
-    ev.s_coef = s_mesh + 2 * n;
-    ev.n = n;
+    ev.mv.p2 = s_mesh;
+    ev.mv.pc2 = s_mesh + n;
+    ev.mv.coef = s_mesh + 2 * n;
+    ev.mv.n = n;
+    ev.mv.p2max = cfg->p2max;
+    ev.mv.pc2max = cfg->pc2max;
+    ev.isospin = cfg->sp.isospin;
+    ev.lockstep = cfg->lockstep;
+    ev.s_done = s_done;
+#ifdef PNJL_PROFILE_PHASES
+    ev.dbg = cfg->dbg;
+    ev.t_last = 0;
+#endif
     const int wl = threadIdx.x & 31;
     ev.lane = wl % G;
     ev.mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (wl - ev.lane));
@@ -133,14 +220,15 @@ __device__ __forceinline__ void store_record(const GroupEval<G>& ev, const doubl
 
 // ---- independent points --------------------------------------------------------------------------
 template <int G>
-__global__ void __launch_bounds__(128, 4) k_solve_points(const DeviceConfig* __restrict__ cfg, const double* __restrict__ g_mesh,
+__global__ void __launch_bounds__(512, 1) k_solve_points(const DeviceConfig* __restrict__ cfg, const double* __restrict__ g_mesh,
                                                       long long n_points, const double* __restrict__ T_fm,
                                                       const double* __restrict__ mu_fm, const double* __restrict__ xi,
                                                       int seed_mode, int n_seeds, const double* __restrict__ seeds,
                                                       double* __restrict__ records, unsigned long long* counter) {
     extern __shared__ double s_mesh[];
-    stage_mesh<G>(g_mesh, cfg->n_nodes, s_mesh);
-    GroupEval<G> ev = make_eval<G>(cfg, s_mesh);
+    __shared__ int s_done;
+    stage_mesh<G>(g_mesh, cfg->n_nodes, s_mesh, &s_done);
+    GroupEval<G> ev = make_eval<G>(cfg, s_mesh, &s_done);
     Solver<GroupEval<G>> sv(cfg->m, cfg->sp, ev);
     for (;;) {
         const long long i = next_task<G>(counter, ev);
@@ -167,6 +255,7 @@ __global__ void __launch_bounds__(128, 4) k_solve_points(const DeviceConfig* __r
         fill_record(r, T, mu, x_i, sv.n_fj, sv.n_th, rec);
         store_record<G>(ev, rec, records + PNJL_REC_DOUBLES * i);
     }
+    ev.drain();
 }
 
 // ---- continuity lines ----------------------------------------------------------------------------
@@ -183,14 +272,15 @@ struct LineSink {
 };
 
 template <int G>
-__global__ void __launch_bounds__(128, 4) k_scan_lines(const DeviceConfig* __restrict__ cfg, const double* __restrict__ g_mesh,
+__global__ void __launch_bounds__(512, 1) k_scan_lines(const DeviceConfig* __restrict__ cfg, const double* __restrict__ g_mesh,
                                                     long long n_lines, const double* __restrict__ muq_MeV,
                                                     const double* __restrict__ xi, const int* __restrict__ table_idx,
                                                     int n_T, const double* __restrict__ T_MeV, double* __restrict__ records,
                                                     unsigned long long* counter) {
     extern __shared__ double s_mesh[];
-    stage_mesh<G>(g_mesh, cfg->n_nodes, s_mesh);
-    GroupEval<G> ev = make_eval<G>(cfg, s_mesh);
+    __shared__ int s_done;
+    stage_mesh<G>(g_mesh, cfg->n_nodes, s_mesh, &s_done);
+    GroupEval<G> ev = make_eval<G>(cfg, s_mesh, &s_done);
     Solver<GroupEval<G>> sv(cfg->m, cfg->sp, ev);
     for (;;) {
         const long long l = next_task<G>(counter, ev);
@@ -198,17 +288,19 @@ __global__ void __launch_bounds__(128, 4) k_scan_lines(const DeviceConfig* __res
         LineSink<G> sink{&ev, records + (long long)PNJL_REC_DOUBLES * n_T * l, xi[l]};
         scan_line(sv, &cfg->pt, table_idx ? table_idx[l] : -1, muq_MeV[l], xi[l], n_T, T_MeV, sink);
     }
+    ev.drain();
 }
 
 // ---- single FJ evaluation (test hook) ------------------------------------------------------------
 template <int G>
-__global__ void __launch_bounds__(128, 4) k_eval_fj(const DeviceConfig* __restrict__ cfg, const double* __restrict__ g_mesh,
+__global__ void __launch_bounds__(512, 1) k_eval_fj(const DeviceConfig* __restrict__ cfg, const double* __restrict__ g_mesh,
                                                  long long n, const double* __restrict__ T_fm, const double* __restrict__ mu_fm,
                                                  const double* __restrict__ xi, const double* __restrict__ x,
                                                  double* __restrict__ FJ, unsigned long long* counter) {
     extern __shared__ double s_mesh[];
-    stage_mesh<G>(g_mesh, cfg->n_nodes, s_mesh);
-    GroupEval<G> ev = make_eval<G>(cfg, s_mesh);
+    __shared__ int s_done;
+    stage_mesh<G>(g_mesh, cfg->n_nodes, s_mesh, &s_done);
+    GroupEval<G> ev = make_eval<G>(cfg, s_mesh, &s_done);
     for (;;) {
         const long long i = next_task<G>(counter, ev);
         if (i >= n) break;
@@ -220,6 +312,7 @@ __global__ void __launch_bounds__(128, 4) k_eval_fj(const DeviceConfig* __restri
             for (int q = 0; q < 25; ++q) FJ[30 * i + 5 + q] = J[q];
         }
     }
+    ev.drain();
 }
 
 // ---- FP64 FMA peak microbenchmark ----------------------------------------------------------------
@@ -234,6 +327,14 @@ __global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, doubl
         }
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+// ---- accuracy self-test of the branch-free primitives (test hook) ---------------------------------
+__global__ void k_selftest_math(long long n, const double* __restrict__ x, int which, double* __restrict__ out) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double v = x[i];
+    out[i] = which == 0 ? fast_exp_nonpos(v) : (which == 1 ? fast_rcp(v) : fast_rsqrt(v));
 }
 
 }  // namespace pnjl
@@ -326,6 +427,7 @@ struct pnjl_handle {
     int sm_count = 0;
     int n_nodes = 0;
     int G = 32;
+    int block_threads = 128;
     DeviceConfig host_cfg;
     DeviceConfig* d_cfg = nullptr;
     double* d_mesh = nullptr;
@@ -352,7 +454,7 @@ struct DeviceGuard {
 
 template <class K>
 int launch_geometry(pnjl_handle* h, K kernel, size_t smem, long long n_groups_needed, int G, int* blocks, int* threads) {
-    const int block = 128;
+    const int block = h->block_threads;
     cudaFuncAttributes fa;
     CUDA_TRY(cudaFuncGetAttributes(&fa, kernel));
     if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -477,6 +579,7 @@ void pnjl_default_config(pnjl_config* c) {
     c->omega_tie_rel = 1e-12;
     c->device = -1;
     c->lanes_per_solve = 0;
+    c->isospin_symmetric = 1;
 }
 
 int pnjl_gauleg(double a, double b, int32_t n, double* nodes, double* weights) {
@@ -552,7 +655,23 @@ int pnjl_create(const pnjl_config* c, pnjl_handle** out) {
     dc.sp.xtol = c->xtol; dc.sp.ftol = c->ftol; dc.sp.residual_norm_max = c->residual_norm_max; dc.sp.phi_tol = c->phi_tol;
     dc.sp.omega_tie_rel = c->omega_tie_rel; dc.sp.max_iter = c->max_iter; dc.sp.tr_fallback = c->tr_fallback;
     dc.sp.auto_multiseed_fallback = c->auto_multiseed_fallback;
+    dc.sp.isospin = c->isospin_symmetric;
+    {
+        // launch shape: lock-stepped 512-thread CTAs (one per SM) for the 32-lane layout, small CTAs otherwise;
+        // PNJL_BLOCK_THREADS / PNJL_LOCKSTEP override for experiments
+        const char* eb = getenv("PNJL_BLOCK_THREADS");
+        const char* el = getenv("PNJL_LOCKSTEP");
+        dc.lockstep = el ? atoi(el) : (h->G == 32 ? 1 : 0);   // 0 off, 1 align loop entry, 3 align entry and exit
+        h->block_threads = eb ? atoi(eb) : (h->G == 32 ? 512 : 128);
+        if (h->block_threads < 32 || h->block_threads > 512 || (h->block_threads & 31)) h->block_threads = 128;
+    }
     dc.n_nodes = h->n_nodes;
+    dc.p2max = 0.0;
+    dc.pc2max = 0.0;
+    for (int k = 0; k < h->n_nodes; ++k) {
+        dc.p2max = std::max(dc.p2max, mesh[k]);
+        dc.pc2max = std::max(dc.pc2max, mesh[h->n_nodes + k]);
+    }
     dc.pt.n_tables = 0;
 
 #define CREATE_TRY(expr)                                                                              \
@@ -563,6 +682,10 @@ int pnjl_create(const pnjl_config* c, pnjl_handle** out) {
             return fail(PNJL_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));          \
         }                                                                                             \
     } while (0)
+#ifdef PNJL_PROFILE_PHASES
+    CREATE_TRY(cudaMalloc(&dc.dbg, 8 * sizeof(unsigned long long)));
+    CREATE_TRY(cudaMemset(dc.dbg, 0, 8 * sizeof(unsigned long long)));
+#endif
     CREATE_TRY(cudaMalloc(&h->d_cfg, sizeof(DeviceConfig)));
     CREATE_TRY(cudaMalloc(&h->d_mesh, sizeof(double) * mesh.size()));
     CREATE_TRY(cudaMalloc(&h->d_counter, sizeof(unsigned long long)));
@@ -580,6 +703,17 @@ void pnjl_destroy(pnjl_handle* h) {
     if (!h) return;
     DeviceGuard guard(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+#ifdef PNJL_PROFILE_PHASES
+    if (h->host_cfg.dbg) {
+        unsigned long long d[8];
+        cudaDeviceSynchronize();
+        cudaMemcpy(d, h->host_cfg.dbg, sizeof(d), cudaMemcpyDeviceToHost);
+        if (d[2])
+            fprintf(stderr, "[phases] passes %llu: loop %.0f cyc/pass; barrier wait %.0f cyc/pass; scalar phase %.0f cyc/pass\n", d[2],
+                    (double)d[0] / d[2], (double)d[1] / d[2], (double)d[3] / d[2]);
+        cudaFree(h->host_cfg.dbg);
+    }
+#endif
     h->in_T.release(); h->in_mu.release(); h->in_xi.release(); h->in_seeds.release(); h->in_idx.release();
     h->in_x.release(); h->out_rec.release();
     if (h->d_cfg) cudaFree(h->d_cfg);
@@ -728,10 +862,30 @@ int pnjl_eval_fj_host(pnjl_handle* h, int64_t n, const double* T, const double* 
     CUDA_TRY(cudaMemcpyAsync(h->in_xi.p, xi, nb, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(h->in_x.p, x, nb * 5, cudaMemcpyHostToDevice, st));
     h->stats.kernel_launches = 0;
+    CUDA_TRY(cudaEventRecord(h->ev0, st));
     int rc = dispatch_fj(h, n, (const double*)h->in_T.p, (const double*)h->in_mu.p, (const double*)h->in_xi.p,
                          (const double*)h->in_x.p, (double*)h->out_rec.p, st);
     if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(h->ev1, st));
     CUDA_TRY(cudaMemcpyAsync(FJ, h->out_rec.p, nb * 30, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->stats.kernel_ms = ms;
+    return PNJL_OK;
+}
+
+int pnjl_selftest_math(pnjl_handle* h, int64_t n, const double* x, int32_t which, double* out) {
+    if (!h || !x || !out || n <= 0 || which < 0 || which > 2) return fail(PNJL_ERR_ARG, "bad argument");
+    DeviceGuard guard(h->device);
+    const size_t nb = sizeof(double) * (size_t)n;
+    CUDA_TRY(h->in_T.reserve(nb));
+    CUDA_TRY(h->out_rec.reserve(nb));
+    cudaStream_t st = h->stream;
+    CUDA_TRY(cudaMemcpyAsync(h->in_T.p, x, nb, cudaMemcpyHostToDevice, st));
+    k_selftest_math<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, (const double*)h->in_T.p, which, (double*)h->out_rec.p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out, h->out_rec.p, nb, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return PNJL_OK;
 }

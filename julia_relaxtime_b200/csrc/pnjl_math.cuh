@@ -40,7 +40,8 @@ struct Model {
 
 struct SolverParams {
     double xtol, ftol, residual_norm_max, phi_tol, omega_tie_rel;
-    int max_iter, tr_fallback, auto_multiseed_fallback, pad;
+    int max_iter, tr_fallback, auto_multiseed_fallback;
+    int isospin;   // exploit M_u == M_d when phi_u == phi_d bitwise (mu_u = mu_d on this path)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -67,6 +68,91 @@ PNJL_HD double f_fma(double a, double b, double c) {
     return fma(a, b, c);
 #else
     return a * b + c;
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------
+// Branch-free FP64 primitives for the fast path (device: MUFU seed + Newton-Raphson in DFMA, a
+// degree-11 polynomial exp; host build: libm).  Domain restrictions are guaranteed by the
+// group-uniform fast-path test (fast_path_ok below): arguments are normal, positive where needed,
+// and exp arguments lie in [-708, 0].  Keeping them branch-free lets ptxas interleave the independent
+// flavour/node chains, which is what keeps the FP64 pipe fed.
+// ------------------------------------------------------------------------------------------------
+PNJL_HD double fast_rcp(double x) {
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+#else
+    return 1.0 / x;
+#endif
+}
+
+PNJL_HD double fast_rsqrt(double x) {
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double h = 0.5 * x;
+    double e = fma(-(h * y), y, 0.5);
+    y = fma(y, e, y);
+    e = fma(-(h * y), y, 0.5);
+    return fma(y, e, y);
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
+
+// exp(t) for t in [-708, 0]: t = k ln2 + r, |r| <= ln2/2, degree-11 interpolant at Chebyshev nodes
+// (max relative error 4.3e-18 before rounding), scaling by an integer add into the exponent field.
+PNJL_HD double fast_exp_nonpos(double t) {
+#if defined(__CUDA_ARCH__)
+    const double kShift = 6755399441055744.0;  // 1.5 * 2^52
+    double kd = fma(t, 1.4426950408889634, kShift);
+    const int k = __double2loint(kd);
+    kd -= kShift;
+    double r = fma(kd, -6.93147180369123816490e-01, t);
+    r = fma(kd, -1.90821492927058770002e-10, r);
+    double p = 0x1.af635e4f6b5eep-26;
+    p = fma(p, r, 0x1.28b43a93fe57ap-22);
+    p = fma(p, r, 0x1.71ddf5514be0cp-19);
+    p = fma(p, r, 0x1.a01991731e6fap-16);
+    p = fma(p, r, 0x1.a01a01b150ad2p-13);
+    p = fma(p, r, 0x1.6c16c1881156bp-10);
+    p = fma(p, r, 0x1.111111110f205p-7);
+    p = fma(p, r, 0x1.555555554f067p-5);
+    p = fma(p, r, 0x1.555555555555ap-3);
+    p = fma(p, r, 0x1.0000000000011p-1);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+#else
+    return exp(t);
+#endif
+}
+
+// ln(x) for positive, normal, finite x: exponent/mantissa split with integer ops, m in [sqrt(1/2), sqrt(2)),
+// s = f/(2+f), odd series in s (the classic fdlibm e_log.c scheme).  No special cases, no branches.
+PNJL_HD double fast_log_pos(double x) {
+#if defined(__CUDA_ARCH__)
+    const int hi = __double2hiint(x);
+    const int hx = hi & 0x000fffff;
+    const int i = (hx + 0x95f64) & 0x100000;
+    const double dk = (double)(((hi >> 20) - 1023) + (i >> 20));
+    const double f = __hiloint2double(hx | (i ^ 0x3ff00000), __double2loint(x)) - 1.0;
+    const double s = f * fast_rcp(2.0 + f);
+    const double z = s * s;
+    const double w = z * z;
+    const double t1 = w * fma(w, fma(w, 1.531383769920937332e-01, 2.222219843214978396e-01), 3.999999999940941908e-01);
+    const double t2 = z * fma(w, fma(w, fma(w, 1.479819860511658591e-01, 1.818357216161805012e-01), 2.857142874366239149e-01),
+                              6.666666666666735130e-01);
+    const double R = t2 + t1;
+    const double hfsq = 0.5 * f * f;
+    return fma(dk, 6.93147180369123816490e-01, -((hfsq - fma(s, hfsq + R, dk * 1.90821492927058770002e-10)) - f));
+#else
+    return log(x);
 #endif
 }
 
@@ -135,7 +221,8 @@ PNJL_HD void masses_of(const Model& m, const double x[5], double M[3]) {
 }
 
 PNJL_HD void make_ctx(const Model& m, double T, double mu, double xi, const double x[5], PointCtx& c) {
-    c.T = T; c.mu = mu; c.xi = xi; c.invT = 1.0 / T;
+    c.T = T; c.mu = mu; c.xi = xi;
+    c.invT = (T > 1e-300 && T < 1e300) ? fast_rcp(T) : 1.0 / T;
     c.Phi = x[3]; c.Phib = x[4]; c.Phi3 = 3.0 * x[3]; c.Phib3 = 3.0 * x[4];
     masses_of(m, x, c.M);
     for (int i = 0; i < 3; ++i) c.M2[i] = c.M[i] * c.M[i];
@@ -174,6 +261,173 @@ PNJL_HD void fj_node(const PointCtx& c, double k2, double coef, double acc[kFJAc
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fast path of the quadrature passes.  Valid (and selected group-uniformly per evaluation) when
+//   Phi >= 0 and Phibar >= 0        -> f+- >= 1, so the reference's max(., 1e-16) floors cannot be active,
+//   (E_max + |mu|) / T <= 200       -> y^3 = e^{3a} <= e^{600} stays finite, so the reference's a>0 rescaling
+//                                      (Integrals.jl:203-218), which only guards against overflow, is the identity.
+// Then with e1 = exp(-E/T):  y = e^{-(E-mu)/T} = e1 * e^{mu/T},  z = e^{-(E+mu)/T} = e1 * e^{-mu/T}  (ONE exp per
+// node x flavour), f+ = 1 + y (3 Phi + y (3 Phibar + y)), f- likewise with z and Phi <-> Phibar.
+// Every other evaluation (non-physical iterates, T -> 0) takes the general path above.
+// ------------------------------------------------------------------------------------------------
+struct FastCtx {
+    double nInvT;         // -1/T
+    double kapP, kapM;    // e^{+mu/T}, e^{-mu/T}
+    double Phi, Phib, Phi3, Phib3, Phi2, Phib2, Phi4, Phib4;
+};
+
+PNJL_HD bool fast_path_ok(double T, double mu, double Phi, double Phib, double k2max, const double M2[3]) {
+    double m2 = M2[0] > M2[1] ? M2[0] : M2[1];
+    m2 = m2 > M2[2] ? m2 : M2[2];
+    const double r = 200.0 * T - fabs(mu);          // E_max <= r  <=>  (E_max + |mu|) / T <= 200
+    return (Phi >= 0.0) && (Phib >= 0.0) && (T > 1e-300) && (r > 0.0) && (k2max + m2 <= r * r);
+}
+
+PNJL_HD void make_fast_ctx(const PointCtx& c, FastCtx& f) {
+    f.nInvT = -c.invT;
+    // |mu|/T <= 200 here, so e^{-|mu|/T} is a normal number and its reciprocal is safe
+    const double km = fast_exp_nonpos(-fabs(c.mu) * c.invT);
+    const double kp = fast_rcp(km);
+    f.kapP = c.mu >= 0.0 ? kp : km;
+    f.kapM = c.mu >= 0.0 ? km : kp;
+    f.Phi = c.Phi; f.Phib = c.Phib;
+    f.Phi3 = c.Phi3; f.Phib3 = c.Phib3;
+    f.Phi2 = 2.0 * c.Phi; f.Phib2 = 2.0 * c.Phib;
+    f.Phi4 = 4.0 * c.Phi; f.Phib4 = 4.0 * c.Phib;
+}
+
+// One species on the fast path: y = e^a; outputs n = g/f, qf = q/f, r1 = y/f, r2 = y^2/f.
+//   f = 1 + y (3 P1 + y (3 P2 + y)),  g = y (P1 + y (2 P2 + y)),  q = y (P1 + y (4 P2 + 3 y))
+PNJL_HD void species_fast(double y, double P1, double P1x3, double P2x2, double P2x3, double P2x4, double& n, double& qf,
+                          double& r1, double& r2, double& fval) {
+    const double f = f_fma(y, f_fma(y, y + P2x3, P1x3), 1.0);
+    const double g = f_fma(y, y + P2x2, P1);
+    const double q = f_fma(y, f_fma(3.0, y, P2x4), P1);
+    const double inv = fast_rcp(f);
+    r1 = y * inv;
+    r2 = r1 * y;
+    n = g * r1;
+    qf = q * r1;
+    fval = f;
+}
+
+// One node x one flavour of the FJ pass on the fast path.
+//   fl[5] = per-flavour sums {S1, S2A, S2B', S3, S4} with S2B' = sum c (n+ + n-)/E^3
+//           (k^2/E^3 = 1/E - M^2/E^3 is folded in finish_fj, flag `fast`)
+//   sh[5] = flavour-summed sums {GP, GPB, HPP, HPPB, HPBPB}
+PNJL_HD void fj_node_fast(const FastCtx& fc, double M2, double k2, double coef, double fl[5], double sh[5]) {
+    const double E2 = k2 + M2;
+    const double rE = fast_rsqrt(E2);
+    const double E = E2 * rE;
+    const double e1 = fast_exp_nonpos(E * fc.nInvT);
+    const double y = e1 * fc.kapP;
+    const double z = e1 * fc.kapM;
+    double np, qp, r1p, r2p, fp, nm, qm, r1m, r2m, fm;
+    species_fast(y, fc.Phi, fc.Phi3, fc.Phib2, fc.Phib3, fc.Phib4, np, qp, r1p, r2p, fp);
+    species_fast(z, fc.Phib, fc.Phib3, fc.Phi2, fc.Phi3, fc.Phi4, nm, qm, r1m, r2m, fm);
+    const double nsum = np + nm;
+    const double m3p = -3.0 * np, m3m = -3.0 * nm;
+    const double Q = f_fma(m3p, np, qp) + f_fma(m3m, nm, qm);
+    const double crE = coef * rE;
+    const double crE2 = crE * rE;
+    fl[0] = f_fma(crE, nsum, fl[0]);
+    fl[1] = f_fma(crE2, Q, fl[1]);
+    fl[2] = f_fma(crE2 * rE, nsum, fl[2]);
+    fl[3] = f_fma(crE, f_fma(r1p, 1.0 + m3p, r2m * (2.0 + m3m)), fl[3]);
+    fl[4] = f_fma(crE, f_fma(r2p, 2.0 + m3p, r1m * (1.0 + m3m)), fl[4]);
+    sh[0] = f_fma(coef, r1p + r2m, sh[0]);
+    sh[1] = f_fma(coef, r2p + r1m, sh[1]);
+    sh[2] = f_fma(coef, f_fma(r1p, r1p, r2m * r2m), sh[2]);
+    sh[3] = f_fma(coef, f_fma(r1p, r2p, r2m * r1m), sh[3]);
+    sh[4] = f_fma(coef, f_fma(r2p, r2p, r1m * r1m), sh[4]);
+}
+
+// Thermo pass, fast path: th[4] = {sum c n+, sum c n-, sum c (L+ + L-), sum c [n+ (E-mu) + n- (E+mu)]} of one flavour.
+PNJL_HD void thermo_node_fast(const FastCtx& fc, double mu, double M2, double k2, double coef, double th[4]) {
+    const double E2 = k2 + M2;
+    const double rE = fast_rsqrt(E2);
+    const double E = E2 * rE;
+    const double e1 = fast_exp_nonpos(E * fc.nInvT);
+    const double y = e1 * fc.kapP;
+    const double z = e1 * fc.kapM;
+    double np, qp, r1p, r2p, fp, nm, qm, r1m, r2m, fm;
+    species_fast(y, fc.Phi, fc.Phi3, fc.Phib2, fc.Phib3, fc.Phib4, np, qp, r1p, r2p, fp);
+    species_fast(z, fc.Phib, fc.Phib3, fc.Phi2, fc.Phi3, fc.Phi4, nm, qm, r1m, r2m, fm);
+    const double L = fast_log_pos(fp * fm);
+    th[0] = f_fma(coef, np, th[0]);
+    th[1] = f_fma(coef, nm, th[1]);
+    th[2] = f_fma(coef, L, th[2]);
+    th[3] = f_fma(coef, f_fma(np, E - mu, nm * (E + mu)), th[3]);
+}
+
+// Mesh slice seen by one lane: nodes lane, lane+stride, ...   (host build: lane 0, stride 1)
+struct MeshView {
+    const double* p2;     // p^2
+    const double* pc2;    // (p cos)^2
+    const double* coef;   // w_p * 2 w_c * p^2 / (2 pi)^2
+    int n;
+    double p2max, pc2max;
+};
+
+// Per-lane partial sums of one FJ pass in the canonical 20-slot layout (to be summed over the lanes of
+// the group, then finish_fj).  Chooses, uniformly for the whole group, between
+//   fast + isospin (x[0] == x[1] bitwise -> M_u == M_d bitwise: the d flavour is the u flavour, 2 flavours evaluated),
+//   fast, three flavours,
+//   general path (floors / rescaling live).
+// Returns true when the fast-path slot convention (S2B') is in use.
+PNJL_HD bool fj_partial(const Model& m, bool isospin, const PointCtx& c, const double x[5], const MeshView& mv, int lane,
+                        int stride, double acc[kFJAcc]) {
+    const double k2max = mv.p2max + (c.xi > 0.0 ? c.xi * mv.pc2max : 0.0);
+    if (fast_path_ok(c.T, c.mu, c.Phi, c.Phib, k2max, c.M2)) {
+        FastCtx fc;
+        make_fast_ctx(c, fc);
+        if (isospin && x[0] == x[1]) {
+            double fu[5] = {0, 0, 0, 0, 0}, fs[5] = {0, 0, 0, 0, 0}, su[5] = {0, 0, 0, 0, 0}, ss[5] = {0, 0, 0, 0, 0};
+#pragma unroll 2
+            for (int k = lane; k < mv.n; k += stride) {
+                const double k2 = f_fma(c.xi, mv.pc2[k], mv.p2[k]);
+                const double cf = mv.coef[k];
+                fj_node_fast(fc, c.M2[0], k2, cf, fu, su);
+                fj_node_fast(fc, c.M2[2], k2, cf, fs, ss);
+            }
+#pragma unroll
+            for (int q = 0; q < 5; ++q) {
+                acc[3 * q + 0] = fu[q];
+                acc[3 * q + 1] = fu[q];
+                acc[3 * q + 2] = fs[q];
+                acc[15 + q] = f_fma(2.0, su[q], ss[q]);
+            }
+        } else {
+            double f0[5] = {0, 0, 0, 0, 0}, f1[5] = {0, 0, 0, 0, 0}, f2[5] = {0, 0, 0, 0, 0}, sh[5] = {0, 0, 0, 0, 0};
+            for (int k = lane; k < mv.n; k += stride) {
+                const double k2 = f_fma(c.xi, mv.pc2[k], mv.p2[k]);
+                const double cf = mv.coef[k];
+                fj_node_fast(fc, c.M2[0], k2, cf, f0, sh);
+                fj_node_fast(fc, c.M2[1], k2, cf, f1, sh);
+                fj_node_fast(fc, c.M2[2], k2, cf, f2, sh);
+            }
+#pragma unroll
+            for (int q = 0; q < 5; ++q) {
+                acc[3 * q + 0] = f0[q];
+                acc[3 * q + 1] = f1[q];
+                acc[3 * q + 2] = f2[q];
+                acc[15 + q] = sh[q];
+            }
+        }
+        return true;
+    }
+#pragma unroll
+    for (int i = 0; i < kFJAcc; ++i) acc[i] = 0.0;
+    for (int k = lane; k < mv.n; k += stride) {
+        const double k2 = f_fma(c.xi, mv.pc2[k], mv.p2[k]);
+        const double cf = mv.coef[k];
+        fj_node<0>(c, k2, cf, acc);
+        fj_node<1>(c, k2, cf, acc);
+        fj_node<2>(c, k2, cf, acc);
+    }
+    return false;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Closed-form pieces
 // ------------------------------------------------------------------------------------------------
 // Vacuum integral I(Lambda, m) and its first two derivatives in m = |M| + 1e-12.
@@ -183,12 +437,15 @@ PNJL_HD void fj_node(const PointCtx& c, double k2, double coef, double acc[kFJAc
 PNJL_HD void vacuum_terms(double Lam, double M, double& I0, double& I1, double& I2) {
     const double m = fabs(M) + 1e-12;
     const double m2 = m * m;
-    const double s = sqrt(Lam * Lam + m2);
-    const double lg = log((Lam + s) / m);
-    I0 = (Lam * s * (2 * (Lam * Lam) + m2) - (m2 * m2) * lg) / (16 * (kPi * kPi));
+    const double s2 = Lam * Lam + m2;
+    const bool tame = (m < 1e100) && (Lam > 1e-100) && (Lam < 1e100);   // everything below is a positive normal number
+    const double rs = tame ? fast_rsqrt(s2) : 1.0 / sqrt(s2);
+    const double s = s2 * rs;
+    const double lg = tame ? fast_log_pos((Lam + s) * fast_rcp(m)) : log((Lam + s) / m);
+    I0 = (Lam * s * (2 * (Lam * Lam) + m2) - (m2 * m2) * lg) * (1.0 / (16 * (kPi * kPi)));
     const double sgn = (M > 0.0) ? 1.0 : ((M < 0.0) ? -1.0 : 0.0);
-    I1 = sgn * (Lam * m * s - m2 * m * lg) / (4 * (kPi * kPi));
-    I2 = (Lam * s + 2 * Lam * m2 / s - 3 * m2 * lg) / (4 * (kPi * kPi));
+    I1 = sgn * (Lam * m * s - m2 * m * lg) * (1.0 / (4 * (kPi * kPi)));
+    I2 = (Lam * s + 2 * Lam * m2 * rs - 3 * m2 * lg) * (1.0 / (4 * (kPi * kPi)));
 }
 
 struct UTerms {
@@ -197,17 +454,17 @@ struct UTerms {
 
 // U = T^4 [ -1/2 A(T) Phi Phibar + B(T) ln v ],  v = 1 - 6 Phi Phibar + 4 (Phi^3 + Phibar^3) - 3 (Phi Phibar)^2,
 // A = a0 + a1 t + a2 t^2, B = b3 t^3, t = T0/T;  ln v is floored at ln 1e-16 (safe_log) -> zero derivative.
-PNJL_HD UTerms polyakov_U(const Model& m, double T, double P, double Pb) {
-    UTerms u;
-    const double t = m.T0 / T;
+PNJL_HD void polyakov_U(const Model& m, double T, double iT, double P, double Pb, UTerms& u) {
+    const double t = m.T0 * iT;
     const double A = m.a0 + m.a1 * t + m.a2 * (t * t);
     const double B = m.b3 * (t * t * t);
     const double T2 = T * T, T4 = T2 * T2;
     const double PPb = Pb * P;
     const double v = 1 - 6 * PPb + 4 * (Pb * Pb * Pb + P * P * P) - 3 * (PPb * PPb);
     const bool live = !(v <= 0.0) && !(v < kPolyakovEps);
-    const double lv = live ? log(v) : log(kPolyakovEps);
-    const double iv = live ? 1.0 / v : 0.0;
+    const bool tame = live && (v < 1e100);
+    const double lv = tame ? fast_log_pos(v) : (live ? log(v) : log(kPolyakovEps));
+    const double iv = tame ? fast_rcp(v) : (live ? 1.0 / v : 0.0);
     const double vP = -6 * Pb + 12 * P * P - 6 * P * Pb * Pb;
     const double vPb = -6 * P + 12 * Pb * Pb - 6 * P * P * Pb;
     const double vPP = 24 * P - 6 * Pb * Pb;
@@ -220,24 +477,26 @@ PNJL_HD UTerms polyakov_U(const Model& m, double T, double P, double Pb) {
     u.U_PbPb = T4 * B * (vPbPb * iv - (vPb * iv) * (vPb * iv));
     u.U_PPb = T4 * (-0.5 * A + B * (vPPb * iv - (vP * iv) * (vPb * iv)));
     // dU/dT at fixed Phi: Thermodynamics.jl:147-165
-    const double dA = -m.a1 * m.T0 / T2 - 2 * m.a2 * (m.T0 * m.T0) / (T2 * T);
-    const double dB = -3 * m.b3 * (m.T0 * m.T0 * m.T0) / T4;
+    const double iT2 = iT * iT;
+    const double dA = -m.a1 * m.T0 * iT2 - 2 * m.a2 * (m.T0 * m.T0) * (iT2 * iT);
+    const double dB = -3 * m.b3 * (m.T0 * m.T0 * m.T0) * (iT2 * iT2);
     u.U_T = 4 * (T2 * T) * (-0.5 * A * PPb + B * lv) + T4 * (dA * (-0.5 * PPb) + dB * lv);
-    return u;
 }
 
 // Assemble F = grad_x P (5) and J = Hess_x P (5x5 row-major) from the reduced accumulators.
 PNJL_HD void finish_fj(const Model& m, const PointCtx& c, const double x[5], const double acc[kFJAcc], double F[5],
-                       double J[25]) {
+                       double J[25], bool fast = false) {
     const double T = c.T, invT = c.invT;
     const double twoT = 2.0 * T;
     // dP/dM_i, d2P/dM_i^2, d2P/dM_i dPhi, d2P/dM_i dPhibar  (thermal + vacuum)
     double PM[3], PMM[3], PMP[3], PMPb[3];
+    double I0 = 0, I1 = 0, I2 = 0;
     for (int i = 0; i < 3; ++i) {
-        double I0, I1, I2;
-        vacuum_terms(m.Lambda, c.M[i], I0, I1, I2);
+        if (!(i == 1 && c.M[1] == c.M[0])) vacuum_terms(m.Lambda, c.M[i], I0, I1, I2);   // M_d == M_u: reuse
         const double S1 = -3.0 * invT * c.M[i] * acc[ACC_S1 + i];
-        const double S2 = 3.0 * invT * invT * c.M2[i] * acc[ACC_S2A + i] - 3.0 * invT * acc[ACC_S2B + i];
+        // general path: S2B = sum c n k^2/E^3;  fast path: S2B = sum c n/E^3 and k^2/E^3 = 1/E - M^2/E^3
+        const double s2b = fast ? (acc[ACC_S1 + i] - c.M2[i] * acc[ACC_S2B + i]) : acc[ACC_S2B + i];
+        const double S2 = 3.0 * invT * invT * c.M2[i] * acc[ACC_S2A + i] - 3.0 * invT * s2b;
         const double S3 = -3.0 * invT * c.M[i] * acc[ACC_S3 + i];
         const double S4 = -3.0 * invT * c.M[i] * acc[ACC_S4 + i];
         PM[i] = twoT * S1 + 2.0 * m.Nc * I1;
@@ -251,7 +510,8 @@ PNJL_HD void finish_fj(const Model& m, const PointCtx& c, const double x[5], con
     D[0][0] = g4;        D[0][1] = k2 * x[2]; D[0][2] = k2 * x[1];
     D[1][0] = k2 * x[2]; D[1][1] = g4;        D[1][2] = k2 * x[0];
     D[2][0] = k2 * x[1]; D[2][1] = k2 * x[0]; D[2][2] = g4;
-    const UTerms u = polyakov_U(m, T, x[3], x[4]);
+    UTerms u;
+    polyakov_U(m, T, c.invT, x[3], x[4], u);
     // -chi: d/dphi_j = -4G phi_j + 4K phi_k phi_l
     const double chi1[3] = {-4 * m.G * x[0] + 4 * m.K * x[1] * x[2], -4 * m.G * x[1] + 4 * m.K * x[0] * x[2],
                             -4 * m.G * x[2] + 4 * m.K * x[0] * x[1]};
@@ -308,6 +568,51 @@ PNJL_HD void thermo_node(const PointCtx& c, double k2, double coef, double acc[k
     acc[TH_T] = f_fma(coef, f_fma(np, E - c.mu, nm * (E + c.mu)), acc[TH_T]);
 }
 
+// Per-lane partial sums of one thermo pass in the canonical 8-slot layout.
+PNJL_HD void thermo_partial(const Model& m, bool isospin, const PointCtx& c, const double x[5], const MeshView& mv, int lane,
+                            int stride, double acc[kThAcc]) {
+    const double k2max = mv.p2max + (c.xi > 0.0 ? c.xi * mv.pc2max : 0.0);
+    if (fast_path_ok(c.T, c.mu, c.Phi, c.Phib, k2max, c.M2)) {
+        FastCtx fc;
+        make_fast_ctx(c, fc);
+        double t0[4] = {0, 0, 0, 0}, t1[4] = {0, 0, 0, 0}, t2[4] = {0, 0, 0, 0};
+        const bool iso = isospin && x[0] == x[1];
+        if (iso) {
+#pragma unroll 2
+            for (int k = lane; k < mv.n; k += stride) {
+                const double k2 = f_fma(c.xi, mv.pc2[k], mv.p2[k]);
+                const double cf = mv.coef[k];
+                thermo_node_fast(fc, c.mu, c.M2[0], k2, cf, t0);
+                thermo_node_fast(fc, c.mu, c.M2[2], k2, cf, t2);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) t1[q] = t0[q];
+        } else {
+            for (int k = lane; k < mv.n; k += stride) {
+                const double k2 = f_fma(c.xi, mv.pc2[k], mv.p2[k]);
+                const double cf = mv.coef[k];
+                thermo_node_fast(fc, c.mu, c.M2[0], k2, cf, t0);
+                thermo_node_fast(fc, c.mu, c.M2[1], k2, cf, t1);
+                thermo_node_fast(fc, c.mu, c.M2[2], k2, cf, t2);
+            }
+        }
+        acc[TH_NP + 0] = t0[0]; acc[TH_NP + 1] = t1[0]; acc[TH_NP + 2] = t2[0];
+        acc[TH_NM + 0] = t0[1]; acc[TH_NM + 1] = t1[1]; acc[TH_NM + 2] = t2[1];
+        acc[TH_L] = (t0[2] + t1[2]) + t2[2];
+        acc[TH_T] = (t0[3] + t1[3]) + t2[3];
+        return;
+    }
+#pragma unroll
+    for (int i = 0; i < kThAcc; ++i) acc[i] = 0.0;
+    for (int k = lane; k < mv.n; k += stride) {
+        const double k2 = f_fma(c.xi, mv.pc2[k], mv.p2[k]);
+        const double cf = mv.coef[k];
+        thermo_node<0>(c, k2, cf, acc);
+        thermo_node<1>(c, k2, cf, acc);
+        thermo_node<2>(c, k2, cf, acc);
+    }
+}
+
 struct Thermo {
     double omega, pressure, rho_norm, entropy, energy;
     double rho[3], nq[3], nqb[3], M[3];
@@ -315,12 +620,13 @@ struct Thermo {
 
 PNJL_HD void finish_thermo(const Model& m, const PointCtx& c, const double x[5], const double acc[kThAcc], Thermo& th) {
     const double T = c.T;
-    const UTerms u = polyakov_U(m, T, x[3], x[4]);
+    UTerms u;
+    polyakov_U(m, T, c.invT, x[3], x[4], u);
     const double chi = 2 * m.G * ((x[0] * x[0] + x[1] * x[1]) + x[2] * x[2]) - 4 * m.K * ((x[0] * x[1]) * x[2]);
     double vac = 0.0;
+    double I0 = 0, I1 = 0, I2 = 0;
     for (int i = 0; i < 3; ++i) {
-        double I0, I1, I2;
-        vacuum_terms(m.Lambda, c.M[i], I0, I1, I2);
+        if (!(i == 1 && c.M[1] == c.M[0])) vacuum_terms(m.Lambda, c.M[i], I0, I1, I2);
         vac += I0;
         th.M[i] = c.M[i];
     }
@@ -345,14 +651,58 @@ PNJL_HD void finish_thermo(const Model& m, const PointCtx& c, const double x[5],
 // ------------------------------------------------------------------------------------------------
 // 5x5 dense algebra
 // ------------------------------------------------------------------------------------------------
-// Solve A y = b by LU with partial pivoting.  false on an exactly-zero pivot.
+// Solve A y = b by LU with partial pivoting.  false on an exactly-zero pivot.  Deliberately compact
+// (rolled loops, local arrays): it runs once per quadrature pass and must not crowd the instruction cache.
 PNJL_HD_NOINL bool lu_solve5(const double A_in[25], const double b_in[5], double y[5]) {
     double A[25], b[5];
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < 25; ++i) A[i] = A_in[i];
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < 5; ++i) b[i] = b_in[i];
     bool ok = true;
+#pragma unroll 1
+    for (int k = 0; k < 5; ++k) {
+        int piv = k;
+        double best = fabs(A[k * 5 + k]);
+#pragma unroll 1
+        for (int i = k + 1; i < 5; ++i) {
+            const double v = fabs(A[i * 5 + k]);
+            if (v > best) { best = v; piv = i; }
+        }
+        if (best == 0.0) ok = false;
+        if (piv != k) {
+#pragma unroll 1
+            for (int j = 0; j < 5; ++j) { const double t = A[k * 5 + j]; A[k * 5 + j] = A[piv * 5 + j]; A[piv * 5 + j] = t; }
+            const double t = b[k]; b[k] = b[piv]; b[piv] = t;
+        }
+        const double inv = 1.0 / A[k * 5 + k];
+#pragma unroll 1
+        for (int i = k + 1; i < 5; ++i) {
+            const double l = A[i * 5 + k] * inv;
+#pragma unroll 1
+            for (int j = k + 1; j < 5; ++j) A[i * 5 + j] -= l * A[k * 5 + j];
+            b[i] -= l * b[k];
+        }
+    }
+#pragma unroll 1
+    for (int i = 4; i >= 0; --i) {
+        double sacc = b[i];
+#pragma unroll 1
+        for (int j = i + 1; j < 5; ++j) sacc -= A[i * 5 + j] * y[j];
+        y[i] = sacc / A[i * 5 + i];
+    }
+    return ok;
+}
+
+// Same elimination order as lu_solve5, fully unrolled with select-based row swaps so that A, b and y live in
+// registers (used in the fused quadrature-pass epilogue; A and b are destroyed).
+PNJL_HD double guarded_rcp(double v) {
+    const double a = fabs(v);
+    return (a > 1e-280 && a < 1e280) ? fast_rcp(v) : 1.0 / v;
+}
+PNJL_HD bool lu_solve5_regs(double A[25], double b[5], double y[5]) {
+    bool ok = true;
+    double inv[5];
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
         int piv = k;
@@ -360,32 +710,39 @@ PNJL_HD_NOINL bool lu_solve5(const double A_in[25], const double b_in[5], double
 #pragma unroll
         for (int i = k + 1; i < 5; ++i) {
             const double v = fabs(A[i * 5 + k]);
-            if (v > best) { best = v; piv = i; }
+            const bool g = v > best;
+            best = g ? v : best;
+            piv = g ? i : piv;
         }
-        if (best == 0.0) ok = false;
+        ok = ok && (best != 0.0);
 #pragma unroll
         for (int i = k + 1; i < 5; ++i) {
-            if (i == piv) {
+            const bool sw = (piv == i);
 #pragma unroll
-                for (int j = 0; j < 5; ++j) { const double t = A[k * 5 + j]; A[k * 5 + j] = A[i * 5 + j]; A[i * 5 + j] = t; }
-                const double t = b[k]; b[k] = b[i]; b[i] = t;
+            for (int j = k; j < 5; ++j) {
+                const double a = A[k * 5 + j], c = A[i * 5 + j];
+                A[k * 5 + j] = sw ? c : a;
+                A[i * 5 + j] = sw ? a : c;
             }
+            const double a = b[k], c = b[i];
+            b[k] = sw ? c : a;
+            b[i] = sw ? a : c;
         }
-        const double inv = 1.0 / A[k * 5 + k];
+        inv[k] = guarded_rcp(A[k * 5 + k]);
 #pragma unroll
         for (int i = k + 1; i < 5; ++i) {
-            const double l = A[i * 5 + k] * inv;
+            const double l = A[i * 5 + k] * inv[k];
 #pragma unroll
-            for (int j = k + 1; j < 5; ++j) A[i * 5 + j] -= l * A[k * 5 + j];
-            b[i] -= l * b[k];
+            for (int j = k + 1; j < 5; ++j) A[i * 5 + j] = f_fma(-l, A[k * 5 + j], A[i * 5 + j]);
+            b[i] = f_fma(-l, b[k], b[i]);
         }
     }
 #pragma unroll
     for (int i = 4; i >= 0; --i) {
-        double s = b[i];
+        double sacc = b[i];
 #pragma unroll
-        for (int j = i + 1; j < 5; ++j) s -= A[i * 5 + j] * y[j];
-        y[i] = s / A[i * 5 + i];
+        for (int j = i + 1; j < 5; ++j) sacc = f_fma(-A[i * 5 + j], y[j], sacc);
+        y[i] = sacc * inv[i];
     }
     return ok;
 }

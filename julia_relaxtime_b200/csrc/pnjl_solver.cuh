@@ -135,11 +135,18 @@ struct Solver {
 
     PNJL_HD void FJ(const double x[5], double F[5], double J[25]) { ev.fj(T, mu, xi, x, F, J); ++n_fj; }
 
+    // One quadrature pass at x fused with the Newton direction: F(x) and p = -J(x)^{-1} F(x); J never leaves the
+    // evaluator's registers.  Returns false when J(x) is exactly singular (p is then unusable).
+    PNJL_HD bool FJ_step(const double x[5], double F[5], double p[5]) {
+        ++n_fj;
+        return ev.fj_step(T, mu, xi, x, F, p);
+    }
+
     // NLsolve newton_: full steps, stop on ||F||inf <= ftol or ||dx||inf <= xtol, NaN guard, iteration cap.
     PNJL_HD_NOINL void newton(const double x0[5], NLRes& r) {
-        double x[5], xold[5], f[5], J[25], p[5];
+        double x[5], xold[5], f[5], p[5];
         copy5(x, x0);
-        FJ(x, f, J);
+        bool nonsing = FJ_step(x, f, p);   // F(x0) and the first Newton direction from J(x0)
         r.threw = !all_finite5(f);
         int it = 0;
         bool xc = false;
@@ -148,16 +155,18 @@ struct Solver {
         if (!r.threw) {
             while (!stopped && !(xc || fc) && it < sp.max_iter) {
                 ++it;
-                if (lu_solve5(J, f, p)) {
-#pragma unroll
-                    for (int i = 0; i < 5; ++i) p[i] = -p[i];
-                } else {
+                if (!nonsing) {
+                    // exactly singular J: NLsolve's regularised step needs J itself (rare; one extra pass, not
+                    // counted as a reference-side evaluation)
+                    double J[25], f2[5];
+                    ev.fj(T, mu, xi, x, f2, J);
                     singular_step(J, f, p);
                 }
+                if (sp.isospin && x[0] == x[1]) p[1] = p[0];   // keep the exact u<->d symmetry of the equations
                 copy5(xold, x);
 #pragma unroll
                 for (int i = 0; i < 5; ++i) x[i] = x[i] + p[i];
-                FJ(x, f, J);  // F for the test, J for the next step (one fused pass)
+                nonsing = FJ_step(x, f, p);  // F for the test, and the next direction from J (one fused pass)
                 double dx = 0.0;
 #pragma unroll
                 for (int i = 0; i < 5; ++i) {
@@ -269,6 +278,7 @@ struct Solver {
             while (!stopped && !converged && it < sp.max_iter) {
                 ++it;
                 dogleg(p, r, d, J, delta);
+                if (sp.isospin && x[0] == x[1]) p[1] = p[0];
                 copy5(xold, x);
                 for (int i = 0; i < 5; ++i) x[i] += p[i];
                 FJ(x, fv, Jn);  // trial residual; Jn is kept only if the step is accepted

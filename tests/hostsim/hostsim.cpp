@@ -22,28 +22,37 @@ struct HostMesh {
 struct HostEval {
     const Model* m;
     const HostMesh* mesh;
+    int isospin;
+    MeshView view() const {
+        MeshView mv;
+        mv.p2 = mesh->p2.data(); mv.pc2 = mesh->pc2.data(); mv.coef = mesh->coef.data(); mv.n = mesh->n;
+        mv.p2max = 0; mv.pc2max = 0;
+        for (int k = 0; k < mesh->n; ++k) {
+            mv.p2max = mesh->p2[k] > mv.p2max ? mesh->p2[k] : mv.p2max;
+            mv.pc2max = mesh->pc2[k] > mv.pc2max ? mesh->pc2[k] : mv.pc2max;
+        }
+        return mv;
+    }
     void fj(double T, double mu, double xi, const double x[5], double F[5], double J[25]) {
         PointCtx c;
         make_ctx(*m, T, mu, xi, x, c);
-        double acc[kFJAcc] = {0};
-        for (int k = 0; k < mesh->n; ++k) {
-            const double k2 = mesh->p2[k] + xi * mesh->pc2[k];
-            fj_node<0>(c, k2, mesh->coef[k], acc);
-            fj_node<1>(c, k2, mesh->coef[k], acc);
-            fj_node<2>(c, k2, mesh->coef[k], acc);
-        }
-        finish_fj(*m, c, x, acc, F, J);
+        double acc[kFJAcc];
+        const bool fast = fj_partial(*m, isospin != 0, c, x, view(), 0, 1, acc);
+        finish_fj(*m, c, x, acc, F, J, fast);
+    }
+    bool fj_step(double T, double mu, double xi, const double x[5], double F[5], double p[5]) {
+        double J[25], b[5];
+        fj(T, mu, xi, x, F, J);
+        for (int i = 0; i < 5; ++i) b[i] = F[i];
+        const bool ok = lu_solve5_regs(J, b, p);
+        for (int i = 0; i < 5; ++i) p[i] = -p[i];
+        return ok;
     }
     void thermo(double T, double mu, double xi, const double x[5], Thermo& th) {
         PointCtx c;
         make_ctx(*m, T, mu, xi, x, c);
-        double acc[kThAcc] = {0};
-        for (int k = 0; k < mesh->n; ++k) {
-            const double k2 = mesh->p2[k] + xi * mesh->pc2[k];
-            thermo_node<0>(c, k2, mesh->coef[k], acc);
-            thermo_node<1>(c, k2, mesh->coef[k], acc);
-            thermo_node<2>(c, k2, mesh->coef[k], acc);
-        }
+        double acc[kThAcc];
+        thermo_partial(*m, isospin != 0, c, x, view(), 0, 1, acc);
         finish_thermo(*m, c, x, acc, th);
     }
 };
@@ -58,7 +67,7 @@ SolverParams params_of(const pnjl_config* c) {
     SolverParams s;
     s.xtol = c->xtol; s.ftol = c->ftol; s.residual_norm_max = c->residual_norm_max; s.phi_tol = c->phi_tol;
     s.omega_tie_rel = c->omega_tie_rel; s.max_iter = c->max_iter; s.tr_fallback = c->tr_fallback;
-    s.auto_multiseed_fallback = c->auto_multiseed_fallback; s.pad = 0;
+    s.auto_multiseed_fallback = c->auto_multiseed_fallback; s.isospin = c->isospin_symmetric;
     return s;
 }
 HostMesh mesh_of(const pnjl_config* c) {
@@ -84,14 +93,14 @@ extern "C" {
 void hostsim_fj(const pnjl_config* c, const double* x, double T, double mu, double xi, double* F, double* J) {
     Model m = model_of(c);
     HostMesh mesh = mesh_of(c);
-    HostEval ev{&m, &mesh};
+    HostEval ev{&m, &mesh, c->isospin_symmetric};
     ev.fj(T, mu, xi, x, F, J);
 }
 
 void hostsim_thermo(const pnjl_config* c, const double* x, double T, double mu, double xi, double* out17) {
     Model m = model_of(c);
     HostMesh mesh = mesh_of(c);
-    HostEval ev{&m, &mesh};
+    HostEval ev{&m, &mesh, c->isospin_symmetric};
     Thermo th;
     ev.thermo(T, mu, xi, x, th);
     out17[0] = th.omega; out17[1] = th.pressure; out17[2] = th.rho_norm; out17[3] = th.entropy; out17[4] = th.energy;
@@ -105,7 +114,7 @@ void hostsim_solve_points(const pnjl_config* c, int64_t n, const double* T, cons
     HostMesh mesh = mesh_of(c);
 #pragma omp parallel for schedule(dynamic, 1)
     for (int64_t i = 0; i < n; ++i) {
-        HostEval ev{&m, &mesh};
+        HostEval ev{&m, &mesh, c->isospin_symmetric};
         Solver<HostEval> sv(m, sp, ev);
         sv.set_point(T[i], mu[i], xi[i]);
         PointRes r;
@@ -140,7 +149,7 @@ void hostsim_scan_lines(const pnjl_config* c, int64_t n_lines, const double* muq
     }
 #pragma omp parallel for schedule(dynamic, 1)
     for (int64_t l = 0; l < n_lines; ++l) {
-        HostEval ev{&m, &mesh};
+        HostEval ev{&m, &mesh, c->isospin_symmetric};
         Solver<HostEval> sv(m, sp, ev);
         Sink sink{records + PNJL_REC_DOUBLES * n_T * l, xi[l]};
         scan_line(sv, pt, table_idx ? table_idx[l] : -1, muq_MeV[l], xi[l], n_T, T_MeV, sink);
