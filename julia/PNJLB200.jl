@@ -1,0 +1,152 @@
+# PNJLB200.jl — Julia binding of libpnjl_b200.so (include/pnjl_b200.h) for Julia_RelaxTime.
+#
+# NOT EXECUTED IN THE BUILD IMAGE: there is no Julia toolchain in this container or on the GPU box, so this file is
+# the binding a maintainer adds to the reference (see INTEGRATION.md); its Python twin
+# (julia_relaxtime_b200/_lib.py + solver.py + scan.py) is what the tests drive.  Every `ccall` below matches one
+# prototype of include/pnjl_b200.h; struct layouts match `pnjl_config` / `pnjl_boundary` field by field.
+#
+# Drop-in points in the reference:
+#   * PNJL.solve(::FixedMu, T_fm, μ_fm; ...)            src/pnjl/solver/ImplicitSolver.jl:211  → PNJLB200.solve
+#   * PNJL.solve_multi(::FixedMu, ...)                   src/pnjl/solver/ImplicitSolver.jl:532  → PNJLB200.solve (MultiSeed)
+#   * the (xi, muB, T) loop of run_gap_transport_scan.jl scripts/relaxtime/run_gap_transport_scan.jl:407-443
+#                                                                                                → PNJLB200.scan_lines
+module PNJLB200
+
+using StaticArrays
+
+const LIB = get(ENV, "PNJL_B200_LIB", joinpath(@__DIR__, "..", "julia_relaxtime_b200", "csrc", "_build", "libpnjl_b200.so"))
+
+const REC = 32                       # doubles per result record (PNJL_REC_DOUBLES)
+const ST_CONVERGED = 1
+const ST_ALL_SEEDS_FAILED = 512
+const SEED_EXPLICIT, SEED_AUTO, SEED_MULTI = Int32(0), Int32(1), Int32(2)
+
+# struct pnjl_config (field order and types as in the header)
+struct Config
+    hbarc::Cdouble; Lambda::Cdouble; m_ud0::Cdouble; m_s0::Cdouble; G::Cdouble; K::Cdouble
+    T0::Cdouble; a0::Cdouble; a1::Cdouble; a2::Cdouble; b3::Cdouble; rho0::Cdouble
+    Nc::Int32; p_num::Int32; t_num::Int32
+    p_nodes::Ptr{Cdouble}; p_w::Ptr{Cdouble}; c_nodes::Ptr{Cdouble}; c_w::Ptr{Cdouble}
+    xtol::Cdouble; ftol::Cdouble; residual_norm_max::Cdouble; phi_tol::Cdouble
+    max_iter::Int32; tr_fallback::Int32; auto_multiseed_fallback::Int32
+    omega_tie_rel::Cdouble
+    device::Int32; lanes_per_solve::Int32; isospin_symmetric::Int32
+end
+
+struct Boundary                      # struct pnjl_boundary
+    T_MeV::Ptr{Cdouble}; mu_c_MeV::Ptr{Cdouble}; n::Int32; T_CEP_MeV::Cdouble
+end
+
+mutable struct Engine
+    handle::Ptr{Cvoid}
+    keep::Vector{Any}                # node vectors must outlive pnjl_create only; kept for clarity
+end
+
+last_error() = unsafe_string(ccall((:pnjl_last_error, LIB), Cstring, ()))
+check(rc, what) = rc == 0 ? nothing : error("$what failed ($rc): $(last_error())")
+
+"""
+    Engine(; p_num=64, t_num=8, iterations=1000, trust_region_fallback=true, auto_multiseed_fallback=true,
+             residual_norm_max=1e-6, device=-1, constants=Main.Constants_PNJL)
+
+One library handle = one GPU + model constants + quadrature rule.  Nodes come from the reference's own
+`GaussLegendre.gauleg` (FastGaussQuadrature) so that both paths integrate on bit-identical rules
+(Integrals.jl:67-96).
+"""
+function Engine(; p_num::Int=64, t_num::Int=8, iterations::Int=1000, trust_region_fallback::Bool=true,
+                auto_multiseed_fallback::Bool=true, residual_norm_max::Float64=1e-6, device::Int=-1,
+                C=Main.Constants_PNJL, gauleg=Main.GaussLegendre.gauleg)
+    pn, pw = gauleg(0.0, 10.0, p_num)
+    cn, cw = gauleg(0.0, 1.0, t_num)
+    cfg = Config(C.ħc_MeV_fm, C.Λ_inv_fm, C.m_ud0_inv_fm, C.m_s0_inv_fm, C.G_fm2, C.K_fm5, C.T0_inv_fm,
+                 C.a0, C.a1, C.a2, C.b3, C.ρ0_inv_fm3, Int32(C.N_color), Int32(p_num), Int32(t_num),
+                 pointer(pn), pointer(pw), pointer(cn), pointer(cw),
+                 1e-9, 1e-9, residual_norm_max, 1e-8, Int32(iterations), Int32(trust_region_fallback),
+                 Int32(auto_multiseed_fallback), 1e-12, Int32(device), Int32(0), Int32(1))
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve pn pw cn cw begin
+        check(ccall((:pnjl_create, LIB), Cint, (Ref{Config}, Ref{Ptr{Cvoid}}), cfg, h), "pnjl_create")
+    end
+    e = Engine(h[], Any[pn, pw, cn, cw])
+    finalizer(x -> ccall((:pnjl_destroy, LIB), Cvoid, (Ptr{Cvoid},), x.handle), e)
+    return e
+end
+
+"""Upload PhaseBoundaryData tables (SeedStrategies.jl:365-371), one per distinct xi."""
+function set_boundaries!(e::Engine, tables::Vector)   # tables: Vector of PNJL.PhaseBoundaryData
+    bs = [Boundary(pointer(t.T_values), pointer(t.mu_values), Int32(length(t.T_values)), t.T_CEP) for t in tables]
+    GC.@preserve tables begin
+        check(ccall((:pnjl_set_boundaries, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Boundary}), e.handle,
+                    Int32(length(bs)), bs), "pnjl_set_boundaries")
+    end
+end
+
+"""Independent points.  Returns a `Matrix{Float64}(32, n)`: column i is the record of point i."""
+function solve_points(e::Engine, T_fm::Vector{Float64}, mu_fm::Vector{Float64}, xi::Vector{Float64};
+                      seed_mode::Int32=SEED_MULTI, seeds::Union{Nothing,Array{Float64,3}}=nothing)
+    n = length(T_fm)
+    rec = Matrix{Float64}(undef, REC, n)
+    n_seeds = seeds === nothing ? Int32(6) : Int32(size(seeds, 2))      # seeds[5, n_seeds, n]
+    sp = seeds === nothing ? Ptr{Cdouble}(C_NULL) : pointer(seeds)
+    GC.@preserve seeds begin
+        check(ccall((:pnjl_solve_points_host, LIB), Cint,
+                    (Ptr{Cvoid}, Int64, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Int32, Int32, Ptr{Cdouble}, Ptr{Cdouble}),
+                    e.handle, n, T_fm, mu_fm, xi, seed_mode, n_seeds, sp, rec), "pnjl_solve_points_host")
+    end
+    return rec
+end
+
+"""Continuity lines in run_gap_transport_scan.jl order.  Returns `Array{Float64}(32, n_T, n_lines)`."""
+function scan_lines(e::Engine, muq_MeV::Vector{Float64}, xi::Vector{Float64}, table_idx::Vector{Int32},
+                    T_MeV::Vector{Float64})
+    nl, nT = length(muq_MeV), length(T_MeV)
+    rec = Array{Float64}(undef, REC, nT, nl)
+    check(ccall((:pnjl_scan_lines_host, LIB), Cint,
+                (Ptr{Cvoid}, Int64, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Int32}, Int32, Ptr{Cdouble}, Ptr{Cdouble}),
+                e.handle, nl, muq_MeV, xi, table_idx, Int32(nT), T_MeV, rec), "pnjl_scan_lines_host")
+    return rec
+end
+
+"""Rebuild the reference's `SolverResult` (ImplicitSolver.jl:178-193) from one record."""
+function solver_result(r::AbstractVector{Float64}; PNJL=Main.PNJL)
+    st = Int(r[22])
+    x = SVector{5}(r[1], r[2], r[3], r[4], r[5])
+    mu = r[29]
+    PNJL.SolverResult(PNJL.FixedMu(), (st & ST_CONVERGED) != 0, collect(x), x, SVector{3}(mu, mu, mu),
+                      r[9], r[10], r[11], r[12], r[13], SVector{3}(r[6], r[7], r[8]), Int(r[21]), r[20], r[30])
+end
+
+const _ENGINES = Dict{Tuple,Engine}()
+engine(p_num, t_num, iterations, tr, ams, rmax) =
+    get!(() -> Engine(; p_num, t_num, iterations, trust_region_fallback=tr, auto_multiseed_fallback=ams,
+                      residual_norm_max=rmax), _ENGINES, (p_num, t_num, iterations, tr, ams, rmax))
+
+"""
+    solve(PNJL.FixedMu(), T_fm, μ_fm; xi, seed_strategy, p_num, t_num, iterations, ...) -> PNJL.SolverResult
+
+Same signature and seed semantics as `PNJL.solve` (ImplicitSolver.jl:211-328): the seed is obtained with the
+reference's own `get_seed`, the solve (Newton → trust-region fallback → auto MultiSeed) runs on the GPU.
+`error("All seeds failed …")` is raised exactly where the reference raises it (:553,:556).
+"""
+function solve(mode, T_fm::Real, mu_fm::Real; xi::Real=0.0, seed_strategy=Main.PNJL.DefaultSeed(), p_num::Int=64,
+               t_num::Int=8, trust_region_fallback::Bool=true, auto_multiseed_fallback::Bool=true,
+               residual_norm_max::Real=1e-6, iterations::Int=1000, PNJL=Main.PNJL)
+    e = engine(p_num, t_num, iterations, trust_region_fallback, auto_multiseed_fallback, Float64(residual_norm_max))
+    T, mu, x = [Float64(T_fm)], [Float64(mu_fm)], [Float64(xi)]
+    multi = seed_strategy isa PNJL.MultiSeed ||
+            (seed_strategy isa PNJL.PhaseAwareContinuitySeed && seed_strategy.bootstrap_multiseed &&
+             seed_strategy.previous_solution === nothing)
+    if multi
+        ms = seed_strategy isa PNJL.MultiSeed ? seed_strategy : seed_strategy.bootstrap_strategy
+        cand = PNJL.get_all_seeds(ms, [T[1], mu[1]], mode)
+        seeds = reshape(reduce(hcat, cand), 5, length(cand), 1)
+        rec = solve_points(e, T, mu, x; seed_mode=SEED_EXPLICIT, seeds=seeds)
+        (Int(rec[22, 1]) & ST_ALL_SEEDS_FAILED) != 0 && error("All seeds failed to converge to a physical solution")
+        return solver_result(view(rec, :, 1); PNJL)
+    end
+    x0 = Float64.(PNJL.get_seed(seed_strategy, [T[1], mu[1]], mode))
+    rec = solve_points(e, T, mu, x; seed_mode=SEED_EXPLICIT, seeds=reshape(x0, 5, 1, 1))
+    return solver_result(view(rec, :, 1); PNJL)
+end
+
+end # module

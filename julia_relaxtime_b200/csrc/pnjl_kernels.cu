@@ -454,7 +454,15 @@ struct DeviceGuard {
 
 template <class K>
 int launch_geometry(pnjl_handle* h, K kernel, size_t smem, long long n_groups_needed, int G, int* blocks, int* threads) {
-    const int block = h->block_threads;
+    // CTA size: h->block_threads when there is enough work to fill every SM with such CTAs, otherwise the
+    // largest warp count per CTA that still gives every SM a CTA (few lines per GPU in multi-GPU runs).
+    int block = h->block_threads;
+    {
+        const long long warps_needed = (n_groups_needed * G + 31) / 32;
+        long long per_sm = (warps_needed + h->sm_count - 1) / h->sm_count;
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm * 32 < block) block = (int)per_sm * 32;
+    }
     cudaFuncAttributes fa;
     CUDA_TRY(cudaFuncGetAttributes(&fa, kernel));
     if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -1,0 +1,106 @@
+"""GPU tests of the reference-facing host API (`solve`, `solve_multi`, seed strategies, `run_scan`), modelled on the
+reference's own unit tests: tests/unit/pnjl/test_solver_implicit.jl, test_solver_random_physical_smoke.jl,
+test_aniso_gap_solver.jl, and on its committed scan CSV."""
+import os
+
+import numpy as np
+import pytest
+
+from julia_relaxtime_b200 import _abi as A
+from tests.golden_io import GOLDEN, read_scan_csv, rel
+
+pytestmark = pytest.mark.gpu
+
+HBARC = 197.327
+
+
+def test_solve_fixedmu_basic_properties():
+    """test_solver_implicit.jl:56-69, 248-269: P = -Omega, xi = 0 / 0.2 converge, M_s > M_u, M_u ≈ M_d, sweeps."""
+    from julia_relaxtime_b200.solver import FixedMu, solve
+    r = solve(FixedMu(), 150.0 / HBARC, 100.0 / HBARC, p_num=24, t_num=8)
+    assert r.converged and abs(r.pressure + r.omega) < 1e-10
+    assert r.masses[2] > r.masses[0] and abs(r.masses[0] - r.masses[1]) < 1e-12
+    assert len(r.solution) == 5 and r.mu_vec == (100.0 / HBARC,) * 3 and r.xi == 0.0
+    r2 = solve(FixedMu(), 150.0 / HBARC, 100.0 / HBARC, xi=0.2, p_num=24, t_num=8)
+    assert r2.converged and r2.xi == 0.2 and r2.masses[0] != r.masses[0]
+    for T in (80.0, 120.0, 160.0, 200.0, 250.0):
+        assert solve(FixedMu(), T / HBARC, 50.0 / HBARC, p_num=24, t_num=8).converged
+    for mu in (0.0, 100.0, 200.0, 300.0, 350.0):
+        assert solve(FixedMu(), 100.0 / HBARC, mu / HBARC, p_num=24, t_num=8).converged
+
+
+def test_solve_seed_strategies_and_multi():
+    from julia_relaxtime_b200.seeds import (ContinuitySeed, DefaultSeed, MultiSeed, PhaseAwareContinuitySeed,
+                                            update_)
+    from julia_relaxtime_b200.solver import FixedMu, solve, solve_multi
+    T, mu = 100.0 / HBARC, 300.0 / HBARC
+    rm = solve(FixedMu(), T, mu, xi=0.2, seed_strategy=MultiSeed(), p_num=64, t_num=16, iterations=40)
+    assert rm.converged and rm.status & A.ST_USED_MULTISEED
+    assert abs(rm.omega - (-21.6156727997846)) < 1e-9 and abs(rm.masses[0] - 1.81848848689695) < 1e-9
+    rm2 = solve_multi(FixedMu(), T, mu, xi=0.2, p_num=64, t_num=16, iterations=40)
+    assert rm2.solution == rm.solution
+    # continuity: previous solution as the seed converges in very few iterations
+    c = ContinuitySeed()
+    update_(c, rm.solution)
+    rc = solve(FixedMu(), 101.0 / HBARC, mu, xi=0.2, seed_strategy=c, p_num=64, t_num=16, iterations=40)
+    assert rc.converged and rc.iterations <= 4
+    # phase-aware tracker: bootstrap_multiseed on the first point, then its own seeds
+    t = PhaseAwareContinuitySeed(0.0, bootstrap_multiseed=True)
+    r0 = solve(FixedMu(), 100.0 / HBARC, 330.0 / HBARC, seed_strategy=t, p_num=24, t_num=8, iterations=40)
+    assert r0.converged and r0.status & A.ST_USED_MULTISEED
+    update_(t, r0.solution, 100.0, 330.0)
+    assert t.previous_phase == "hadron"
+    r1 = solve(FixedMu(), 100.0 / HBARC, 345.0 / HBARC, seed_strategy=t, p_num=24, t_num=8, iterations=40)
+    assert r1.converged and r1.masses[0] < 0.5 * r0.masses[0]       # flipped to the quark seed → chirally restored branch
+    rd = solve(FixedMu(), 150.0 / HBARC, 0.0, seed_strategy=DefaultSeed(phase_hint="hadron"))
+    assert rd.converged and rd.iterations == 4 and abs(rd.masses[0] - 1.84419432518967) < 1e-9
+
+
+def test_random_physical_smoke():
+    """test_solver_random_physical_smoke.jl:55-89 (p=12, t=4; T∈[0,350], muB∈[0,1800], xi∈[-0.8,0.8])."""
+    from julia_relaxtime_b200.solver import solve_batch
+    rng = np.random.default_rng(2)
+    n = 400
+    T = rng.uniform(1.0, 350.0, n) / HBARC
+    mu = rng.uniform(0.0, 1800.0, n) / 3.0 / HBARC
+    xi = rng.uniform(-0.8, 0.8, n)
+    rec = solve_batch(T, mu, xi, seed_strategy="auto", p_num=12, t_num=4)
+    conv = (rec[:, A.REC_STATUS].astype(int) & A.ST_CONVERGED) != 0
+    assert conv.mean() > 0.98
+    g = rec[conv]
+    assert ((g[:, 3:5] >= -1e-8) & (g[:, 3:5] <= 1 + 1e-8)).all() and (g[:, 5:8] > 0).all() and np.isfinite(g[:, :20]).all()
+
+
+def test_run_scan_reproduces_reference_csv(tmp_path):
+    """The script's golden configuration end to end: xi -0.6..0.6, muB {0, 800}, T 120..400 step 10, p=12, t=6,
+    iterations=40 → 47-column CSV equal to the reference's committed file on columns 1-30 (continuity rows 1e-9,
+    first-of-line MultiSeed rows 1e-8), then resume semantics."""
+    from julia_relaxtime_b200.scan import HEADER, ScanOptions, run_scan
+    out = str(tmp_path / "scan.csv")
+    opts = ScanOptions(output=out, xi_values=[-0.6, -0.4, -0.2, 0.0, 0.2, 0.4, 0.6], tmin=120.0, tmax=400.0,
+                       tstep=10.0, muB_values=[0.0, 800.0], p_num=12, t_num=6, max_iter=40)
+    assert run_scan(opts) == 406
+    got = read_scan_csv(out)
+    gold = read_scan_csv(os.path.join(GOLDEN, "gap_transport_scan_xi-0p6to0p6.csv"))
+    head = [l for l in open(out) if not l.startswith("#")][0].strip().split(",")
+    assert head == HEADER and any(l.startswith("# schema: scan_csv_v1") for l in open(out))
+    for k in ("T_MeV", "muq_MeV", "muB_MeV", "xi", "T_fm", "muq_fm"):
+        np.testing.assert_array_equal(got[k], gold[k])
+    assert got["converged"].all()
+    first = np.zeros(406, bool)
+    first[::29] = True
+    np.testing.assert_array_equal(got["iterations"][~first], gold["iterations"][~first])
+    for k in HEADER[9:30]:
+        d = np.abs(got[k] - gold[k]) / np.maximum(np.abs(gold[k]), 1e-6)
+        assert d[~first].max() <= 1e-9, (k, d[~first].max())
+        assert d[first].max() <= 2e-8, (k, d[first].max())
+    assert np.isnan(got["eta"]).all()                      # relaxtime columns stay with the Julia chain
+    # resume: nothing to do; after dropping the tail of the file only the missing rows come back
+    assert run_scan(opts) == 0
+    lines = open(out).read().splitlines(keepends=True)
+    open(out, "w").writelines(lines[:-40])
+    assert run_scan(opts) == 40
+    again = read_scan_csv(out)
+    assert len(again["T_MeV"]) == 406
+    opts.overwrite = True
+    assert run_scan(opts) == 406
