@@ -46,11 +46,15 @@ MAX_ITER = 40
 HBARC = 197.327
 
 
-def alg_flops(n_nodes, n_fj, n_th, n_flav=3):
+FUSED_FLOP = 90.0   # fused final pass: residual F without second derivatives (≈ 61) + the thermo sums that do not
+                    # share work with it (≈ 29); DESIGN.md §5
+
+
+def alg_flops(n_nodes, n_fj, n_th, n_flav=3, n_ft=0.0):
     """123 FLOP per node x flavour of an Omega-gradient/Jacobian pass, 54 per thermo-pass unit.
     n_flav = flavours actually evaluated per node: 2 when the kernel uses M_u == M_d (isospin_symmetric, the
     default: every state on these grids has phi_u == phi_d), 3 for the reference's loop."""
-    return n_nodes * n_flav * (123.0 * n_fj + 54.0 * n_th)
+    return n_nodes * n_flav * (123.0 * n_fj + 54.0 * n_th + FUSED_FLOP * n_ft)
 
 
 class ClockSampler:
@@ -330,15 +334,15 @@ def main():
     # converged points / evaluation counts of this rank's slab (identical every step; counted once)
     r2 = d_rec.reshape(-1, A.REC_DOUBLES)
     conv = ((r2[:, A.REC_STATUS].to(torch.int64) & 1) != 0).sum().to(torch.float64)
-    cnt = torch.stack([conv, r2[:, A.REC_NEVAL].sum(), r2[:, A.REC_NTHERMO].sum()])
+    cnt = torch.stack([conv, r2[:, A.REC_NEVAL].sum(), r2[:, A.REC_NTHERMO].sum(), r2[:, A.REC_NFUSED].sum()])
     if world > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
     total_ms, kernel_ms = float(tot[0]), float(tot[1])
-    n_conv, n_fj, n_th = (float(v) for v in cnt)
+    n_conv, n_fj, n_th, n_ft = (float(v) for v in cnt)
     value = n_conv * args.steps / (total_ms * 1e-3)
-    fl = alg_flops(n_nodes, n_fj, n_th, 2)            # whole job, one step, flavours actually evaluated (u == d)
-    fl_ref = alg_flops(n_nodes, n_fj, n_th, 3)        # same passes counted the way the reference loops (3 flavours)
+    fl = alg_flops(n_nodes, n_fj, n_th, 2, n_ft)      # whole job, one step, flavours actually evaluated (u == d)
+    fl_ref = alg_flops(n_nodes, n_fj, n_th, 3, n_ft)        # same passes counted the way the reference loops (3 flavours)
     st = eng.stats()
 
     # ---- e2e: the reference-facing call with HOST buffers (pnjl_scan_lines_host / pnjl_solve_points_host):
@@ -413,6 +417,7 @@ def main():
                               "reference_equivalent_tflops": fl_ref * args.steps / (kernel_ms * 1e-3) / 1e12,
                               "fj_passes_per_point": n_fj / max(1.0, float(n_total)),
                               "thermo_passes_per_point": n_th / max(1.0, float(n_total)),
+                              "fused_final_passes_per_point": n_ft / max(1.0, float(n_total)),
                               "kernel_ms_per_step": kernel_ms / args.steps}, **extra),
             "gpu_launches": int(args.steps) * world,
             "clocks": clocks,

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define PNJL_ABI_VERSION 2
+#define PNJL_ABI_VERSION 3
 
 /* ---- result record layout (doubles) --------------------------------------------------------- */
 #define PNJL_REC_DOUBLES 32
@@ -49,13 +49,14 @@ extern "C" {
 #define PNJL_REC_RESNORM 19    /* ||F||_inf of the returned nlsolve result  SolverResult.residual_norm :191 */
 #define PNJL_REC_ITER 20       /* iterations of the returned nlsolve result :190 */
 #define PNJL_REC_STATUS 21     /* PNJL_ST_* bits */
-#define PNJL_REC_NEVAL 22      /* Omega-gradient/Jacobian quadrature passes spent on this point (all seeds, all fallbacks) */
+#define PNJL_REC_NEVAL 22      /* full Omega-gradient/Jacobian quadrature passes spent on this point (all seeds, all fallbacks) */
 #define PNJL_REC_RHO 23        /* [3] rho_i = dP/dmu_i                      calculate_rho  Thermodynamics.jl:215-220 */
 #define PNJL_REC_NTHERMO 26    /* thermo quadrature passes spent on this point */
 #define PNJL_REC_T 27          /* echo: T_fm */
 #define PNJL_REC_MU 28         /* echo: mu_fm */
 #define PNJL_REC_XI 29         /* echo: xi */
-/* 30, 31 reserved (zero) */
+#define PNJL_REC_NFUSED 30     /* fused final passes (residual F + thermo sums in one quadrature pass) spent on this point */
+/* 31 reserved (zero) */
 
 /* ---- status bits ---------------------------------------------------------------------------- */
 #define PNJL_ST_CONVERGED 1          /* SolverResult.converged  ImplicitSolver.jl:287 */
@@ -103,6 +104,9 @@ typedef struct pnjl_config {
     double omega_tie_rel;           /* MultiSeed argmin-Omega tie window (relative); ties -> lowest seed index. 1e-12 */
     int32_t device;                 /* CUDA device ordinal; -1 = current device */
     int32_t lanes_per_solve;        /* 0 = auto (8/16/32 by mesh size); else 8, 16 or 32 */
+    double predict_tol;             /* a Newton pass that follows a residual <= predict_tol is run as a fused "final pass"
+                                       (F + thermo sums, no Jacobian); if the solve does not stop there, J is evaluated
+                                       by an ordinary pass at the same x.  Iterates are unaffected.  Default 1e-4; 0 = off */
     int32_t isospin_symmetric;      /* 1 (default): when phi_u == phi_d bitwise (always true from the built-in seeds, since
                                        mu_u = mu_d and m_u0 = m_d0 on this path) evaluate the d flavour as the u flavour and
                                        keep Newton/dogleg steps u<->d symmetric (a <= 1 ulp change of the step).  0: three

@@ -152,6 +152,28 @@ struct GroupEval {
         return ok;
     }
 
+    // Fused final pass: F(x) and the thermo pass at x from one sweep over the mesh (fast path only; returns false
+    // without doing anything otherwise).
+    __device__ __noinline__ bool f_thermo(double T, double mu, double xi, const double x[5], double F[5], Thermo& th) {
+        PointCtx c;
+        make_ctx(*m, T, mu, xi, x, c);
+        {
+            const double k2max = mv.p2max + (c.xi > 0.0 ? c.xi * mv.pc2max : 0.0);
+            if (!fast_path_ok(c.T, c.mu, c.Phi, c.Phib, k2max, c.M2)) return false;   // group-uniform
+        }
+        double facc[kFtAcc], tacc[kThAcc];
+        pass_begin();
+        ft_partial(*m, isospin != 0, c, x, mv, lane, G, facc, tacc);
+        pass_end();
+#pragma unroll
+        for (int i = 0; i < kFtAcc; ++i) facc[i] = gsum(facc[i]);
+#pragma unroll
+        for (int i = 0; i < kThAcc; ++i) tacc[i] = gsum(tacc[i]);
+        finish_f(*m, c, x, facc, F);
+        finish_thermo(*m, c, x, tacc, th);
+        return true;
+    }
+
     __device__ __noinline__ void thermo(double T, double mu, double xi, const double x[5], Thermo& th) {
         PointCtx c;
         make_ctx(*m, T, mu, xi, x, c);
@@ -237,6 +259,7 @@ __global__ void __launch_bounds__(512, 1) k_solve_points(const DeviceConfig* __r
         sv.set_point(T, mu, x_i);
         sv.n_fj = 0;
         sv.n_th = 0;
+        sv.n_ft = 0;
         PointRes r;
         if (seed_mode == PNJL_SEED_EXPLICIT && n_seeds == 1) {
             double x0[5];
@@ -252,7 +275,7 @@ __global__ void __launch_bounds__(512, 1) k_solve_points(const DeviceConfig* __r
             sv.solve_multi(nullptr, 6, r);
         }
         double rec[PNJL_REC_DOUBLES];
-        fill_record(r, T, mu, x_i, sv.n_fj, sv.n_th, rec);
+        fill_record(r, T, mu, x_i, sv.n_fj, sv.n_th, sv.n_ft, rec);
         store_record<G>(ev, rec, records + PNJL_REC_DOUBLES * i);
     }
     ev.drain();
@@ -264,9 +287,10 @@ struct LineSink {
     const GroupEval<G>* ev;
     double* base;
     double xi;
-    __device__ __forceinline__ void operator()(int it, const PointRes& r, double T_fm, double mu_fm, int n_fj, int n_th) {
+    __device__ __forceinline__ void operator()(int it, const PointRes& r, double T_fm, double mu_fm, int n_fj, int n_th,
+                                               int n_ft) {
         double rec[PNJL_REC_DOUBLES];
-        fill_record(r, T_fm, mu_fm, xi, n_fj, n_th, rec);
+        fill_record(r, T_fm, mu_fm, xi, n_fj, n_th, n_ft, rec);
         store_record<G>(*ev, rec, base + (long long)PNJL_REC_DOUBLES * it);
     }
 };
@@ -587,6 +611,7 @@ void pnjl_default_config(pnjl_config* c) {
     c->omega_tie_rel = 1e-12;
     c->device = -1;
     c->lanes_per_solve = 0;
+    c->predict_tol = 1e-4;
     c->isospin_symmetric = 1;
 }
 
@@ -664,6 +689,7 @@ int pnjl_create(const pnjl_config* c, pnjl_handle** out) {
     dc.sp.omega_tie_rel = c->omega_tie_rel; dc.sp.max_iter = c->max_iter; dc.sp.tr_fallback = c->tr_fallback;
     dc.sp.auto_multiseed_fallback = c->auto_multiseed_fallback;
     dc.sp.isospin = c->isospin_symmetric;
+    dc.sp.predict_tol = getenv("PNJL_PREDICT_TOL") ? atof(getenv("PNJL_PREDICT_TOL")) : c->predict_tol;
     {
         // launch shape: lock-stepped 512-thread CTAs (one per SM) for the 32-lane layout, small CTAs otherwise;
         // PNJL_BLOCK_THREADS / PNJL_LOCKSTEP override for experiments

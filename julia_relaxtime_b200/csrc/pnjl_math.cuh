@@ -42,6 +42,7 @@ struct SolverParams {
     double xtol, ftol, residual_norm_max, phi_tol, omega_tie_rel;
     int max_iter, tr_fallback, auto_multiseed_fallback;
     int isospin;   // exploit M_u == M_d when phi_u == phi_d bitwise (mu_u = mu_d on this path)
+    double predict_tol;   // a Newton pass after a residual <= predict_tol is run as a fused "final pass" (0: never)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -359,6 +360,31 @@ PNJL_HD void thermo_node_fast(const FastCtx& fc, double mu, double M2, double k2
     th[3] = f_fma(coef, f_fma(np, E - mu, nm * (E + mu)), th[3]);
 }
 
+// "Final pass" on the fast path: the residual F (no second derivatives) together with the thermo sums, for the
+// Newton pass that is expected to satisfy the stopping rule (NLsolve itself evaluates only F after a step,
+// ImplicitSolver.jl:112 -> newton_: value!(df, x)).  ft[7] of one flavour =
+//   {S1 = sum c (n+ + n-)/E,  GP = sum c (r1+ + r2-),  GPB = sum c (r2+ + r1-),  sum c n+,  sum c n-,
+//    sum c ln(f+ f-),  sum c [n+ (E - mu) + n- (E + mu)]}
+PNJL_HD void ft_node_fast(const FastCtx& fc, double mu, double M2, double k2, double coef, double ft[7]) {
+    const double E2 = k2 + M2;
+    const double rE = fast_rsqrt(E2);
+    const double E = E2 * rE;
+    const double e1 = fast_exp_nonpos(E * fc.nInvT);
+    const double y = e1 * fc.kapP;
+    const double z = e1 * fc.kapM;
+    double np, qp, r1p, r2p, fp, nm, qm, r1m, r2m, fm;
+    species_fast(y, fc.Phi, fc.Phi3, fc.Phib2, fc.Phib3, fc.Phib4, np, qp, r1p, r2p, fp);
+    species_fast(z, fc.Phib, fc.Phib3, fc.Phi2, fc.Phi3, fc.Phi4, nm, qm, r1m, r2m, fm);
+    const double L = fast_log_pos(fp * fm);
+    ft[0] = f_fma(coef * rE, np + nm, ft[0]);
+    ft[1] = f_fma(coef, r1p + r2m, ft[1]);
+    ft[2] = f_fma(coef, r2p + r1m, ft[2]);
+    ft[3] = f_fma(coef, np, ft[3]);
+    ft[4] = f_fma(coef, nm, ft[4]);
+    ft[5] = f_fma(coef, L, ft[5]);
+    ft[6] = f_fma(coef, f_fma(np, E - mu, nm * (E + mu)), ft[6]);
+}
+
 // Mesh slice seen by one lane: nodes lane, lane+stride, ...   (host build: lane 0, stride 1)
 struct MeshView {
     const double* p2;     // p^2
@@ -540,6 +566,25 @@ PNJL_HD void finish_fj(const Model& m, const PointCtx& c, const double x[5], con
     J[4 * 5 + 4] = -9.0 * twoT * acc[ACC_HPBPB] - u.U_PbPb;
 }
 
+// F = grad_x P alone, from the reduced sums of a fused final pass (same formulas as finish_fj).
+PNJL_HD void finish_f(const Model& m, const PointCtx& c, const double x[5], const double facc[5], double F[5]) {
+    const double twoT = 2.0 * c.T;
+    double PM[3];
+    double I0 = 0, I1 = 0, I2 = 0;
+    for (int i = 0; i < 3; ++i) {
+        if (!(i == 1 && c.M[1] == c.M[0])) vacuum_terms(m.Lambda, c.M[i], I0, I1, I2);
+        PM[i] = twoT * (-3.0 * c.invT * c.M[i] * facc[i]) + 2.0 * m.Nc * I1;
+    }
+    const double g4 = -4.0 * m.G, k2 = 2.0 * m.K;
+    UTerms u;
+    polyakov_U(m, c.T, c.invT, x[3], x[4], u);
+    F[0] = PM[0] * g4 + PM[1] * (k2 * x[2]) + PM[2] * (k2 * x[1]) + (-4 * m.G * x[0] + 4 * m.K * x[1] * x[2]);
+    F[1] = PM[0] * (k2 * x[2]) + PM[1] * g4 + PM[2] * (k2 * x[0]) + (-4 * m.G * x[1] + 4 * m.K * x[0] * x[2]);
+    F[2] = PM[0] * (k2 * x[1]) + PM[1] * (k2 * x[0]) + PM[2] * g4 + (-4 * m.G * x[2] + 4 * m.K * x[0] * x[1]);
+    F[3] = twoT * 3.0 * facc[3] - u.U_P;
+    F[4] = twoT * 3.0 * facc[4] - u.U_Pb;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Thermo pass: value of the thermal sum, occupation sums and the T-derivative sum.
 //   per flavour i: TN+ = sum c n+, TN- = sum c n-        (-> rho_i, n_i, n_ibar)
@@ -611,6 +656,47 @@ PNJL_HD void thermo_partial(const Model& m, bool isospin, const PointCtx& c, con
         thermo_node<1>(c, k2, cf, acc);
         thermo_node<2>(c, k2, cf, acc);
     }
+}
+
+// Per-lane partial sums of a fused "final pass": facc[0..2] = S1 per flavour, facc[3] = GP, facc[4] = GPB (flavour
+// sums), tacc[8] in the thermo layout.  Returns false when the state is not on the fast path (the caller then
+// runs the two ordinary passes).
+constexpr int kFtAcc = 5;
+PNJL_HD bool ft_partial(const Model& m, bool isospin, const PointCtx& c, const double x[5], const MeshView& mv, int lane,
+                        int stride, double facc[kFtAcc], double tacc[kThAcc]) {
+    const double k2max = mv.p2max + (c.xi > 0.0 ? c.xi * mv.pc2max : 0.0);
+    if (!fast_path_ok(c.T, c.mu, c.Phi, c.Phib, k2max, c.M2)) return false;
+    FastCtx fc;
+    make_fast_ctx(c, fc);
+    double a0[7] = {0, 0, 0, 0, 0, 0, 0}, a1[7] = {0, 0, 0, 0, 0, 0, 0}, a2[7] = {0, 0, 0, 0, 0, 0, 0};
+    const bool iso = isospin && x[0] == x[1];
+    if (iso) {
+#pragma unroll 2
+        for (int k = lane; k < mv.n; k += stride) {
+            const double k2 = f_fma(c.xi, mv.pc2[k], mv.p2[k]);
+            const double cf = mv.coef[k];
+            ft_node_fast(fc, c.mu, c.M2[0], k2, cf, a0);
+            ft_node_fast(fc, c.mu, c.M2[2], k2, cf, a2);
+        }
+#pragma unroll
+        for (int q = 0; q < 7; ++q) a1[q] = a0[q];
+    } else {
+        for (int k = lane; k < mv.n; k += stride) {
+            const double k2 = f_fma(c.xi, mv.pc2[k], mv.p2[k]);
+            const double cf = mv.coef[k];
+            ft_node_fast(fc, c.mu, c.M2[0], k2, cf, a0);
+            ft_node_fast(fc, c.mu, c.M2[1], k2, cf, a1);
+            ft_node_fast(fc, c.mu, c.M2[2], k2, cf, a2);
+        }
+    }
+    facc[0] = a0[0]; facc[1] = a1[0]; facc[2] = a2[0];
+    facc[3] = (a0[1] + a1[1]) + a2[1];
+    facc[4] = (a0[2] + a1[2]) + a2[2];
+    tacc[TH_NP + 0] = a0[3]; tacc[TH_NP + 1] = a1[3]; tacc[TH_NP + 2] = a2[3];
+    tacc[TH_NM + 0] = a0[4]; tacc[TH_NM + 1] = a1[4]; tacc[TH_NM + 2] = a2[4];
+    tacc[TH_L] = (a0[5] + a1[5]) + a2[5];
+    tacc[TH_T] = (a0[6] + a1[6]) + a2[6];
+    return true;
 }
 
 struct Thermo {

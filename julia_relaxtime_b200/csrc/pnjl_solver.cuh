@@ -29,6 +29,8 @@ struct NLRes {
     double res;
     int it;
     bool xc, fc, threw;
+    bool have_th;   // th holds the thermo pass at x (it came for free with a fused final pass)
+    Thermo th;
 };
 
 struct PointRes {
@@ -127,9 +129,10 @@ struct Solver {
     const SolverParams& sp;
     Ev& ev;
     double T, mu, xi;
-    int n_fj, n_th;
+    int n_fj, n_th, n_ft;   // full FJ passes, thermo-only passes, fused final passes (F + thermo)
 
-    PNJL_HD Solver(const Model& m_, const SolverParams& sp_, Ev& ev_) : m(m_), sp(sp_), ev(ev_), T(0), mu(0), xi(0), n_fj(0), n_th(0) {}
+    PNJL_HD Solver(const Model& m_, const SolverParams& sp_, Ev& ev_)
+        : m(m_), sp(sp_), ev(ev_), T(0), mu(0), xi(0), n_fj(0), n_th(0), n_ft(0) {}
 
     PNJL_HD void set_point(double T_, double mu_, double xi_) { T = T_; mu = mu_; xi = xi_; }
 
@@ -148,9 +151,11 @@ struct Solver {
         copy5(x, x0);
         bool nonsing = FJ_step(x, f, p);   // F(x0) and the first Newton direction from J(x0)
         r.threw = !all_finite5(f);
+        r.have_th = false;
         int it = 0;
         bool xc = false;
-        bool fc = norm_inf5(f) <= sp.ftol;
+        double res = norm_inf5(f);
+        bool fc = res <= sp.ftol;
         bool stopped = any_nan5(x) || any_nan5(f);
         if (!r.threw) {
             while (!stopped && !(xc || fc) && it < sp.max_iter) {
@@ -166,7 +171,12 @@ struct Solver {
                 copy5(xold, x);
 #pragma unroll
                 for (int i = 0; i < 5; ++i) x[i] = x[i] + p[i];
-                nonsing = FJ_step(x, f, p);  // F for the test, and the next direction from J (one fused pass)
+                // NLsolve evaluates only F here and J at the top of the next iteration.  When the previous residual
+                // says this pass will most likely end the solve, run it as a fused final pass (F + thermo sums);
+                // otherwise fuse F with the next direction.  Either way the iterates are the same.
+                bool fused = (res <= sp.predict_tol) && ev.f_thermo(T, mu, xi, x, f, r.th);
+                if (fused) ++n_ft;
+                else nonsing = FJ_step(x, f, p);
                 double dx = 0.0;
 #pragma unroll
                 for (int i = 0; i < 5; ++i) {
@@ -174,8 +184,14 @@ struct Solver {
                     if (a > dx || a != a) dx = a;
                 }
                 xc = dx <= sp.xtol;
-                fc = norm_inf5(f) <= sp.ftol;
+                res = norm_inf5(f);
+                fc = res <= sp.ftol;
                 stopped = any_nan5(x) || any_nan5(f);
+                r.have_th = fused;
+                if (fused && !stopped && !(xc || fc) && it < sp.max_iter) {
+                    nonsing = FJ_step(x, f, p);   // mispredicted: the solve goes on and needs J(x)
+                    r.have_th = false;
+                }
             }
         }
         copy5(r.x, x);
@@ -320,6 +336,7 @@ struct Solver {
                 stopped = any_nan5(x) || any_nan5(fv);
             }
         }
+        res.have_th = false;
         copy5(res.x, x);
         res.it = it;
         res.res = norm_inf5(r);
@@ -354,7 +371,8 @@ struct Solver {
             return;
         }
         Thermo pth;
-        thermo_at(pr.x, pth);
+        if (pr.have_th) pth = pr.th;
+        else thermo_at(pr.x, pth);
         const bool pphys = physical(pr.x, pth);
         const double rmax = sp.residual_norm_max;
         const bool pgood = pr.fc && finite_d(pr.res) && pr.res <= rmax && pphys;
@@ -483,7 +501,8 @@ struct Solver {
 };
 
 // Record writer shared by host-sim and device code: fills a 32-double record from a PointRes.
-PNJL_HD void fill_record(const PointRes& r, double T, double mu, double xi, int n_fj, int n_th, double rec[PNJL_REC_DOUBLES]) {
+PNJL_HD void fill_record(const PointRes& r, double T, double mu, double xi, int n_fj, int n_th, int n_ft,
+                         double rec[PNJL_REC_DOUBLES]) {
 #pragma unroll
     for (int i = 0; i < 5; ++i) rec[PNJL_REC_X + i] = r.x[i];
 #pragma unroll
@@ -506,7 +525,7 @@ PNJL_HD void fill_record(const PointRes& r, double T, double mu, double xi, int 
     rec[PNJL_REC_T] = T;
     rec[PNJL_REC_MU] = mu;
     rec[PNJL_REC_XI] = xi;
-    rec[30] = 0.0;
+    rec[PNJL_REC_NFUSED] = (double)n_ft;
     rec[31] = 0.0;
 }
 
@@ -514,7 +533,7 @@ PNJL_HD void fill_record(const PointRes& r, double T, double mu, double xi, int 
 // no previous converged solution, afterwards PhaseAwareContinuitySeed (+ solve()'s own fallbacks).
 // Units as in the script: T_fm = T_MeV / hbarc, mu_fm = muq_MeV / hbarc (:425-427); the tracker's update!
 // receives (T_MeV, muq_MeV) as given (:441), its get_seed converts back from fm with 197.327.
-// sink(iT, result, T_fm, mu_fm, n_fj, n_th) consumes each point.
+// sink(iT, result, T_fm, mu_fm, n_fj, n_th, n_ft) consumes each point.
 template <class Ev, class Sink>
 PNJL_HD_NOINL void scan_line(Solver<Ev>& sv, const PhaseTables* pt, int ti, double muq_MeV, double xi, int n_T,
                        const double* T_MeV, Sink& sink) {
@@ -529,6 +548,7 @@ PNJL_HD_NOINL void scan_line(Solver<Ev>& sv, const PhaseTables* pt, int ti, doub
         sv.set_point(T_fm, mu_fm, xi);
         sv.n_fj = 0;
         sv.n_th = 0;
+        sv.n_ft = 0;
         if (!tk.has_prev) {
             sv.solve_multi(nullptr, 6, r);
         } else {
@@ -542,7 +562,7 @@ PNJL_HD_NOINL void scan_line(Solver<Ev>& sv, const PhaseTables* pt, int ti, doub
             tk.has_prev = true;
             tk.prev_phase = current_phase(pt, ti, Tm, muq_MeV);
         }
-        sink(it, r, T_fm, mu_fm, sv.n_fj, sv.n_th);
+        sink(it, r, T_fm, mu_fm, sv.n_fj, sv.n_th, sv.n_ft);
     }
 }
 

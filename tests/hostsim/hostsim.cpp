@@ -48,6 +48,15 @@ struct HostEval {
         for (int i = 0; i < 5; ++i) p[i] = -p[i];
         return ok;
     }
+    bool f_thermo(double T, double mu, double xi, const double x[5], double F[5], Thermo& th) {
+        PointCtx c;
+        make_ctx(*m, T, mu, xi, x, c);
+        double facc[kFtAcc], tacc[kThAcc];
+        if (!ft_partial(*m, isospin != 0, c, x, view(), 0, 1, facc, tacc)) return false;
+        finish_f(*m, c, x, facc, F);
+        finish_thermo(*m, c, x, tacc, th);
+        return true;
+    }
     void thermo(double T, double mu, double xi, const double x[5], Thermo& th) {
         PointCtx c;
         make_ctx(*m, T, mu, xi, x, c);
@@ -67,7 +76,7 @@ SolverParams params_of(const pnjl_config* c) {
     SolverParams s;
     s.xtol = c->xtol; s.ftol = c->ftol; s.residual_norm_max = c->residual_norm_max; s.phi_tol = c->phi_tol;
     s.omega_tie_rel = c->omega_tie_rel; s.max_iter = c->max_iter; s.tr_fallback = c->tr_fallback;
-    s.auto_multiseed_fallback = c->auto_multiseed_fallback; s.isospin = c->isospin_symmetric;
+    s.auto_multiseed_fallback = c->auto_multiseed_fallback; s.isospin = c->isospin_symmetric; s.predict_tol = c->predict_tol;
     return s;
 }
 HostMesh mesh_of(const pnjl_config* c) {
@@ -122,15 +131,15 @@ void hostsim_solve_points(const pnjl_config* c, int64_t n, const double* T, cons
         else if (seed_mode == PNJL_SEED_EXPLICIT) sv.solve_multi(seeds + 5 * n_seeds * i, n_seeds, r);
         else if (seed_mode == PNJL_SEED_AUTO) { double x0[5]; default_seed(2, T[i], mu[i], x0); sv.solve_with_fallback(x0, r); }
         else sv.solve_multi(nullptr, 6, r);
-        fill_record(r, T[i], mu[i], xi[i], sv.n_fj, sv.n_th, records + PNJL_REC_DOUBLES * i);
+        fill_record(r, T[i], mu[i], xi[i], sv.n_fj, sv.n_th, sv.n_ft, records + PNJL_REC_DOUBLES * i);
     }
 }
 
 struct Sink {
     double* base;
     double xi;
-    void operator()(int it, const PointRes& r, double T_fm, double mu_fm, int n_fj, int n_th) {
-        fill_record(r, T_fm, mu_fm, xi, n_fj, n_th, base + PNJL_REC_DOUBLES * it);
+    void operator()(int it, const PointRes& r, double T_fm, double mu_fm, int n_fj, int n_th, int n_ft) {
+        fill_record(r, T_fm, mu_fm, xi, n_fj, n_th, n_ft, base + PNJL_REC_DOUBLES * it);
     }
 };
 
