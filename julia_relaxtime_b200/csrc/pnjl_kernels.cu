@@ -315,6 +315,293 @@ __global__ void __launch_bounds__(512, 1) k_scan_lines(const DeviceConfig* __res
     ev.drain();
 }
 
+// ---- warp-specialised line march -------------------------------------------------------------------
+// Workers and controllers.  In the layouts above every lane of a warp runs the scalar solver code redundantly
+// (~3000 instructions per quadrature pass, a third of all issued instructions) and the warps of a CTA have to be
+// phase-aligned to keep the quadrature loop in the instruction cache.  Here the two kinds of work get their own
+// warps:
+//   * NW worker warps only ever run quadrature loops + the warp reduction (a few KB of code, always cached);
+//   * controller warps run the solver cascade with ONE LINE PER LANE (real SIMT: the scalar code is no longer
+//     replicated 32x), and hand quadrature passes to the workers through mailboxes in shared memory.
+// Every worker serves two mailboxes, so while it sweeps the mesh for one line the controller lane of its other
+// line assembles F/J, does the 5x5 elimination and posts the next request: the FP64 pipe never waits for scalar
+// code.  Hand-off is a sequence number per mailbox (volatile shared + __threadfence_block, short __nanosleep
+// polls); there are no CTA barriers after the prologue, so divergent controller lanes cannot dead-lock.
+enum { WS_FJ = 0, WS_FT = 1, WS_TH = 2, WS_EXIT = 3 };
+
+struct WsSlot {
+    double d[9];      // T, mu, xi, x[5]
+    double r[21];     // reduced sums (20 FJ | 5 + 8 fused | 8 thermo) ; r[20] = fast-path flag
+    int type;
+    int pad[3];
+};
+
+// One request queue per controller warp ("group"): its lanes fill their mailboxes, lane 0 publishes the round,
+// any idle worker pulls the next mailbox index, and the lanes resume when all mailboxes of the round are served.
+struct WsGroup {
+    volatile int round;      // published round number (0 = nothing yet)
+    volatile int exit_flag;  // set when every line of the group is finished
+    int next;                // next mailbox index to hand out in the current round   (atomic)
+    int done;                // mailboxes served in total, monotonic                   (atomic)
+    int n_slots;             // mailboxes of this group
+    int first_slot;          // index of its first mailbox in s_slots
+    int pad[2];
+};
+
+struct CtrlEval {
+    const Model* m;
+    WsSlot* slot;
+    WsGroup* group;
+    int seq;          // rounds posted so far
+    unsigned grp;     // lanes of this controller warp that own a mailbox
+    bool leader;      // lowest lane of the group
+    double p2max, pc2max;
+
+    // Post one request and wait for the worker.  One code location for every caller (noinline) and a fixed lane
+    // group per mailbox phase: all lines of a phase meet here, poll with one instruction stream, and leave together,
+    // so the scalar code between passes runs SIMT-converged over the lines of the phase.
+    // Returns true (without posting anything) once every line of the group is finished.
+    __device__ __noinline__ bool request(int type, double T, double mu, double xi, const double x[5]) {
+        slot->d[0] = T; slot->d[1] = mu; slot->d[2] = xi;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) slot->d[3 + i] = x[i];
+        slot->type = type;
+        __threadfence_block();
+        // every lane of the group meets here once per round (lanes without lines come from retire())
+        if (__ballot_sync(grp, finished) == grp) return true;
+        ++seq;
+        if (leader) {
+            group->next = 0;
+            __threadfence_block();
+            group->round = seq;                // publish the round to the workers
+        }
+        const int target = seq * group->n_slots;
+        for (;;) {
+            const bool ready = (*((volatile int*)&group->done) >= target);
+            if (__all_sync(grp, ready)) break;
+            __nanosleep(256);
+        }
+        __threadfence_block();
+        return false;
+    }
+    // A lane without lines left keeps posting empty requests so that the round size stays fixed; returns when the
+    // whole group has run out of lines.
+    __device__ __noinline__ void retire() {
+        finished = true;
+        const double zero[5] = {0, 0, 0, 0, 0};
+        while (!request(WS_EXIT, 0.0, 0.0, 0.0, zero)) {}   // WS_EXIT as a mailbox type = "nothing to do"
+        if (leader) {
+            __threadfence_block();
+            group->exit_flag = 1;
+        }
+    }
+    bool finished;
+    __device__ __noinline__ void fj(double T, double mu, double xi, const double x[5], double F[5], double J[25]) {
+        PointCtx c;
+        make_ctx(*m, T, mu, xi, x, c);
+        request(WS_FJ, T, mu, xi, x);
+        double acc[kFJAcc];
+#pragma unroll
+        for (int i = 0; i < kFJAcc; ++i) acc[i] = slot->r[i];
+        finish_fj(*m, c, x, acc, F, J, slot->r[20] != 0.0);
+    }
+    __device__ __noinline__ bool fj_step(double T, double mu, double xi, const double x[5], double F[5], double p[5]) {
+        double J[25], b[5];
+        fj(T, mu, xi, x, F, J);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) b[i] = F[i];
+        const bool ok = lu_solve5(J, b, p);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) p[i] = -p[i];
+        return ok;
+    }
+    __device__ __noinline__ bool f_thermo(double T, double mu, double xi, const double x[5], double F[5], Thermo& th) {
+        PointCtx c;
+        make_ctx(*m, T, mu, xi, x, c);
+        const double k2max = p2max + (xi > 0.0 ? xi * pc2max : 0.0);
+        if (!fast_path_ok(c.T, c.mu, c.Phi, c.Phib, k2max, c.M2)) return false;
+        request(WS_FT, T, mu, xi, x);
+        double facc[kFtAcc], tacc[kThAcc];
+#pragma unroll
+        for (int i = 0; i < kFtAcc; ++i) facc[i] = slot->r[i];
+#pragma unroll
+        for (int i = 0; i < kThAcc; ++i) tacc[i] = slot->r[kFtAcc + i];
+        finish_f(*m, c, x, facc, F);
+        finish_thermo(*m, c, x, tacc, th);
+        return true;
+    }
+    __device__ __noinline__ void thermo(double T, double mu, double xi, const double x[5], Thermo& th) {
+        PointCtx c;
+        make_ctx(*m, T, mu, xi, x, c);
+        request(WS_TH, T, mu, xi, x);
+        double tacc[kThAcc];
+#pragma unroll
+        for (int i = 0; i < kThAcc; ++i) tacc[i] = slot->r[i];
+        finish_thermo(*m, c, x, tacc, th);
+    }
+};
+
+struct CtrlSink {
+    double* base;
+    double xi;
+    __device__ __forceinline__ void operator()(int it, const PointRes& r, double T_fm, double mu_fm, int n_fj, int n_th,
+                                               int n_ft) {
+        double rec[PNJL_REC_DOUBLES];
+        fill_record(r, T_fm, mu_fm, xi, n_fj, n_th, n_ft, rec);
+        double* out = base + (long long)PNJL_REC_DOUBLES * it;
+#pragma unroll
+        for (int q = 0; q < PNJL_REC_DOUBLES; q += 2) *reinterpret_cast<double2*>(out + q) = make_double2(rec[q], rec[q + 1]);
+    }
+};
+
+constexpr int kWsMaxSlots = 64;
+constexpr int kWsMaxSpw = 4;   // mailboxes per worker
+
+// One quadrature pass of a worker warp for mailbox `sl`.
+__device__ __noinline__ void ws_worker_pass(const DeviceConfig* cfg, const MeshView& mv, WsSlot* sl, int type, int lane) {
+    const double T = sl->d[0], mu = sl->d[1], xi = sl->d[2];
+    double x[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) x[i] = sl->d[3 + i];
+    PointCtx c;
+    make_ctx(cfg->m, T, mu, xi, x, c);
+    const bool iso = cfg->sp.isospin != 0;
+    if (type == WS_FJ) {
+        double acc[kFJAcc];
+        const bool fast = fj_partial(cfg->m, iso, c, x, mv, lane, 32, acc);
+#pragma unroll
+        for (int i = 0; i < kFJAcc; ++i) {
+            double v = acc[i];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+            if (lane == 0) sl->r[i] = v;
+        }
+        if (lane == 0) sl->r[20] = fast ? 1.0 : 0.0;
+    } else if (type == WS_FT) {
+        double facc[kFtAcc], tacc[kThAcc];
+        ft_partial(cfg->m, iso, c, x, mv, lane, 32, facc, tacc);
+#pragma unroll
+        for (int i = 0; i < kFtAcc; ++i) {
+            double v = facc[i];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+            if (lane == 0) sl->r[i] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < kThAcc; ++i) {
+            double v = tacc[i];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+            if (lane == 0) sl->r[kFtAcc + i] = v;
+        }
+    } else {
+        double tacc[kThAcc];
+        thermo_partial(cfg->m, iso, c, x, mv, lane, 32, tacc);
+#pragma unroll
+        for (int i = 0; i < kThAcc; ++i) {
+            double v = tacc[i];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+            if (lane == 0) sl->r[i] = v;
+        }
+    }
+}
+
+// blockDim.x = 32 * (n_workers + n_ctrl_warps); slots = 2 * n_workers, spread evenly over the controller warps.
+__global__ void __launch_bounds__(512, 1) k_scan_lines_ws(const DeviceConfig* __restrict__ cfg, const double* __restrict__ g_mesh,
+                                                          long long n_lines, const double* __restrict__ muq_MeV,
+                                                          const double* __restrict__ xi, const int* __restrict__ table_idx,
+                                                          int n_T, const double* __restrict__ T_MeV,
+                                                          double* __restrict__ records, unsigned long long* counter,
+                                                          int n_workers, int n_ctrl_warps, int spw) {
+    extern __shared__ double s_mesh[];
+    __shared__ WsSlot s_slots[kWsMaxSlots];
+    __shared__ WsGroup s_groups[8];
+    const int n = cfg->n_nodes;
+    for (int i = threadIdx.x; i < 3 * n; i += blockDim.x) s_mesh[i] = g_mesh[i];
+    // mailbox phases j = 0..spw-1 (n_workers mailboxes each); controller warp cw owns phases [cw*ppc, (cw+1)*ppc)
+    const int ppc = (spw + n_ctrl_warps - 1) / n_ctrl_warps;
+    if (threadIdx.x < n_ctrl_warps) {
+        const int cw = threadIdx.x;
+        int phases = spw - cw * ppc;
+        phases = phases < 0 ? 0 : (phases > ppc ? ppc : phases);
+        s_groups[cw].round = 0;
+        s_groups[cw].exit_flag = phases == 0 ? 1 : 0;
+        s_groups[cw].next = 0;
+        s_groups[cw].done = 0;
+        s_groups[cw].n_slots = phases * n_workers;
+        s_groups[cw].first_slot = cw * ppc * n_workers;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp < n_workers) {
+        // ---------------- worker: pull mailboxes from whichever group has a round open ----------------
+        MeshView mv;
+        mv.p2 = s_mesh; mv.pc2 = s_mesh + n; mv.coef = s_mesh + 2 * n; mv.n = n;
+        mv.p2max = cfg->p2max; mv.pc2max = cfg->pc2max;
+#ifdef PNJL_PROFILE_PHASES
+        long long t_idle = 0;
+#endif
+        for (;;) {
+            bool any_live = false, did = false;
+            for (int g = 0; g < n_ctrl_warps; ++g) {
+                WsGroup* gr = &s_groups[g];
+                if (gr->exit_flag) continue;
+                any_live = true;
+                const int round = gr->round;
+                if (round == 0) continue;
+                // rounds are strictly sequential per group: mailboxes of round r are all served before r+1 opens
+                if (*((volatile int*)&gr->done) >= round * gr->n_slots) continue;
+                int idx = 0;
+                if (lane == 0) idx = atomicAdd(&gr->next, 1);
+                idx = __shfl_sync(0xffffffffu, idx, 0);
+                if (idx >= gr->n_slots) continue;           // the round is fully handed out
+                __threadfence_block();
+                WsSlot* sl = &s_slots[gr->first_slot + idx];
+                const int type = sl->type;
+#ifdef PNJL_PROFILE_PHASES
+                const long long tp0 = clock64();
+                if (lane == 0 && cfg->dbg && t_idle) atomicAdd(cfg->dbg + 3, (unsigned long long)(tp0 - t_idle));
+#endif
+                if (type != WS_EXIT) ws_worker_pass(cfg, mv, sl, type, lane);
+                __syncwarp();
+                __threadfence_block();
+                if (lane == 0) atomicAdd(&gr->done, 1);
+                did = true;
+#ifdef PNJL_PROFILE_PHASES
+                t_idle = clock64();
+                if (lane == 0 && cfg->dbg && type != WS_EXIT) { atomicAdd(cfg->dbg + 0, (unsigned long long)(t_idle - tp0)); atomicAdd(cfg->dbg + 2, 1ULL); }
+#endif
+            }
+            if (!any_live) break;
+            if (!did) __nanosleep(128);
+        }
+        return;
+    }
+    // ---------------- controller: lane <-> mailbox <-> one line at a time ----------------
+    const int cw = warp - n_workers;
+    WsGroup* gr = &s_groups[cw];
+    if (lane >= gr->n_slots) return;
+    CtrlEval ev;
+    ev.m = &cfg->m;
+    ev.slot = &s_slots[gr->first_slot + lane];
+    ev.group = gr;
+    ev.seq = 0;
+    ev.grp = gr->n_slots >= 32 ? 0xffffffffu : ((1u << gr->n_slots) - 1u);
+    ev.leader = lane == 0;
+    ev.finished = false;
+    ev.p2max = cfg->p2max;
+    ev.pc2max = cfg->pc2max;
+    Solver<CtrlEval> sv(cfg->m, cfg->sp, ev);
+    for (;;) {
+        const long long l = (long long)atomicAdd(counter, 1ULL);
+        if (l >= n_lines) break;
+        CtrlSink sink{records + (long long)PNJL_REC_DOUBLES * n_T * l, xi[l]};
+        scan_line(sv, &cfg->pt, table_idx ? table_idx[l] : -1, muq_MeV[l], xi[l], n_T, T_MeV, sink);
+    }
+    ev.retire();
+}
+
 // ---- single FJ evaluation (test hook) ------------------------------------------------------------
 template <int G>
 __global__ void __launch_bounds__(512, 1) k_eval_fj(const DeviceConfig* __restrict__ cfg, const double* __restrict__ g_mesh,
@@ -452,6 +739,8 @@ struct pnjl_handle {
     int n_nodes = 0;
     int G = 32;
     int block_threads = 128;
+    int schedule = 0;             // 0: every warp owns a line (phase-aligned CTAs); 1: worker/controller warps
+    int ws_workers = 14, ws_ctrl_warps = 2, ws_spw = 4;
     DeviceConfig host_cfg;
     DeviceConfig* d_cfg = nullptr;
     double* d_mesh = nullptr;
@@ -522,6 +811,40 @@ int launch_points(pnjl_handle* h, long long n, const double* T, const double* mu
     return PNJL_OK;
 }
 
+int launch_lines_ws(pnjl_handle* h, long long n_lines, const double* muq, const double* xi, const int* tidx, int n_T,
+                    const double* T, double* rec, cudaStream_t st) {
+    const size_t smem = sizeof(double) * 3 * h->n_nodes;
+    int nw = h->ws_workers, nc = h->ws_ctrl_warps, spw = h->ws_spw;
+    // few lines per GPU: fewer mailboxes per worker first, then fewer workers, so that every SM still gets lines
+    const long long per_sm = (n_lines + h->sm_count - 1) / h->sm_count;
+    while (spw > 1 && per_sm < (long long)spw * nw) --spw;
+    if (per_sm < nw) {
+        nw = (int)(per_sm < 1 ? 1 : per_sm);
+    }
+    while (((spw + nc - 1) / nc) * nw > 32) ++nc;      // lanes of one controller warp = phases per warp x workers
+    if (nw + nc > 16) nw = 16 - nc;
+    const int threads = 32 * (nw + nc);
+    cudaFuncAttributes fa;
+    CUDA_TRY(cudaFuncGetAttributes(&fa, k_scan_lines_ws));
+    if (smem > 40 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_scan_lines_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long need = (n_lines + (long long)spw * nw - 1) / ((long long)spw * nw);
+    int per_sm_ctas = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_ctas, k_scan_lines_ws, threads, smem));
+    if (per_sm_ctas < 1) return fail(PNJL_ERR_CUDA, "warp-specialised kernel does not fit on an SM");
+    const long long cap = (long long)per_sm_ctas * h->sm_count;
+    const int blocks = (int)(need < cap ? need : cap);
+    h->stats.regs_per_thread = fa.numRegs;
+    h->stats.smem_bytes = (int)smem;
+    h->stats.blocks = blocks;
+    h->stats.threads = threads;
+    h->stats.lanes_per_solve = 32;
+    CUDA_TRY(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned long long), st));
+    k_scan_lines_ws<<<blocks, threads, smem, st>>>(h->d_cfg, h->d_mesh, n_lines, muq, xi, tidx, n_T, T, rec, h->d_counter, nw, nc, spw);
+    CUDA_TRY(cudaGetLastError());
+    h->stats.kernel_launches += 1;
+    return PNJL_OK;
+}
+
 template <int G>
 int launch_lines(pnjl_handle* h, long long n_lines, const double* muq, const double* xi, const int* tidx, int n_T,
                  const double* T, double* rec, cudaStream_t st) {
@@ -572,7 +895,9 @@ int dispatch_lines(pnjl_handle* h, long long n_lines, const double* muq, const d
     switch (h->G) {
         case 8: return launch_lines<8>(h, n_lines, muq, xi, tidx, n_T, T, rec, st);
         case 16: return launch_lines<16>(h, n_lines, muq, xi, tidx, n_T, T, rec, st);
-        default: return launch_lines<32>(h, n_lines, muq, xi, tidx, n_T, T, rec, st);
+        default:
+            if (h->schedule == 1) return launch_lines_ws(h, n_lines, muq, xi, tidx, n_T, T, rec, st);
+            return launch_lines<32>(h, n_lines, muq, xi, tidx, n_T, T, rec, st);
     }
 }
 int dispatch_fj(pnjl_handle* h, long long n, const double* T, const double* mu, const double* xi, const double* x,
@@ -698,6 +1023,14 @@ int pnjl_create(const pnjl_config* c, pnjl_handle** out) {
         dc.lockstep = el ? atoi(el) : (h->G == 32 ? 1 : 0);   // 0 off, 1 align loop entry, 3 align entry and exit
         h->block_threads = eb ? atoi(eb) : (h->G == 32 ? 512 : 128);
         if (h->block_threads < 32 || h->block_threads > 512 || (h->block_threads & 31)) h->block_threads = 128;
+        const char* es = getenv("PNJL_SCHEDULE");
+        h->schedule = es ? atoi(es) : 1;
+        if (getenv("PNJL_WS_WORKERS")) h->ws_workers = atoi(getenv("PNJL_WS_WORKERS"));
+        if (getenv("PNJL_WS_CTRL")) h->ws_ctrl_warps = atoi(getenv("PNJL_WS_CTRL"));
+        if (getenv("PNJL_WS_SPW")) h->ws_spw = atoi(getenv("PNJL_WS_SPW"));
+        if (h->ws_spw < 1 || h->ws_spw > kWsMaxSpw) h->ws_spw = 2;
+        if (h->ws_workers < 1 || h->ws_workers > 15) h->ws_workers = 15;
+        if (h->ws_ctrl_warps < 1 || h->ws_workers + h->ws_ctrl_warps > 16) h->ws_ctrl_warps = 16 - h->ws_workers;
     }
     dc.n_nodes = h->n_nodes;
     dc.p2max = 0.0;
