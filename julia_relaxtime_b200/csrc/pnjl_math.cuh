@@ -385,6 +385,197 @@ PNJL_HD void ft_node_fast(const FastCtx& fc, double mu, double M2, double k2, do
     ft[6] = f_fma(coef, f_fma(np, E - mu, nm * (E + mu)), ft[6]);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Paired fast path (isospin case): the u and the s flavour of one node are advanced step by step together, so
+// that two (four, inside the species block) independent dependency chains are adjacent in program order.  A
+// DFMA result is available after 8 cycles and a warp can issue one every 2, so a lone chain leaves the FP64 pipe
+// idle three quarters of the time (scripts/microbench_dfma.cu); ptxas keeps the chains apart when they are
+// written one after the other.  Same arithmetic as fast_rsqrt / fast_exp_nonpos / fast_rcp / species_fast.
+// ------------------------------------------------------------------------------------------------
+template <int W>
+PNJL_HD void v_rsqrt(const double x[W], double y[W]) {
+#if defined(__CUDA_ARCH__)
+    double h[W], e[W];
+#pragma unroll
+    for (int j = 0; j < W; ++j) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y[j]) : "d"(x[j]));
+#pragma unroll
+    for (int j = 0; j < W; ++j) h[j] = 0.5 * x[j];
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+#pragma unroll
+        for (int j = 0; j < W; ++j) e[j] = fma(-(h[j] * y[j]), y[j], 0.5);
+#pragma unroll
+        for (int j = 0; j < W; ++j) y[j] = fma(y[j], e[j], y[j]);
+    }
+#else
+    for (int j = 0; j < W; ++j) y[j] = 1.0 / sqrt(x[j]);
+#endif
+}
+
+template <int W>
+PNJL_HD void v_rcp(const double x[W], double y[W]) {
+#if defined(__CUDA_ARCH__)
+    double e[W];
+#pragma unroll
+    for (int j = 0; j < W; ++j) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y[j]) : "d"(x[j]));
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+#pragma unroll
+        for (int j = 0; j < W; ++j) e[j] = fma(-x[j], y[j], 1.0);
+#pragma unroll
+        for (int j = 0; j < W; ++j) y[j] = fma(y[j], e[j], y[j]);
+    }
+#else
+    for (int j = 0; j < W; ++j) y[j] = 1.0 / x[j];
+#endif
+}
+
+template <int W>
+PNJL_HD void v_exp_nonpos(const double t[W], double out[W]) {
+#if defined(__CUDA_ARCH__)
+    const double kShift = 6755399441055744.0;
+    double kd[W], r[W], p[W];
+    int k[W];
+#pragma unroll
+    for (int j = 0; j < W; ++j) kd[j] = fma(t[j], 1.4426950408889634, kShift);
+#pragma unroll
+    for (int j = 0; j < W; ++j) k[j] = __double2loint(kd[j]);
+#pragma unroll
+    for (int j = 0; j < W; ++j) kd[j] -= kShift;
+#pragma unroll
+    for (int j = 0; j < W; ++j) r[j] = fma(kd[j], -6.93147180369123816490e-01, t[j]);
+#pragma unroll
+    for (int j = 0; j < W; ++j) r[j] = fma(kd[j], -1.90821492927058770002e-10, r[j]);
+    const double c[11] = {0x1.28b43a93fe57ap-22, 0x1.71ddf5514be0cp-19, 0x1.a01991731e6fap-16, 0x1.a01a01b150ad2p-13,
+                          0x1.6c16c1881156bp-10, 0x1.111111110f205p-7,  0x1.555555554f067p-5,  0x1.555555555555ap-3,
+                          0x1.0000000000011p-1,  1.0,                   1.0};
+#pragma unroll
+    for (int j = 0; j < W; ++j) p[j] = 0x1.af635e4f6b5eep-26;
+#pragma unroll
+    for (int q = 0; q < 11; ++q) {
+#pragma unroll
+        for (int j = 0; j < W; ++j) p[j] = fma(p[j], r[j], c[q]);
+    }
+#pragma unroll
+    for (int j = 0; j < W; ++j) out[j] = __hiloint2double(__double2hiint(p[j]) + (k[j] << 20), __double2loint(p[j]));
+#else
+    for (int j = 0; j < W; ++j) out[j] = exp(t[j]);
+#endif
+}
+
+// Four species (u quark, u antiquark, s quark, s antiquark) evaluated together.  Y[4] = {y_u, z_u, y_s, z_s}.
+// Even entries use (P1, P2) = (Phi, Phibar), odd entries (Phibar, Phi).
+struct Species4 {
+    double n[4], qf[4], r1[4], r2[4], f[4];
+};
+PNJL_HD void species4_fast(const FastCtx& fc, const double Y[4], Species4& o, bool need_q) {
+    double g[4], q[4], inv[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const double P13 = (s & 1) ? fc.Phib3 : fc.Phi3, P2 = (s & 1) ? fc.Phi : fc.Phib;
+        o.f[s] = f_fma(Y[s], f_fma(Y[s], f_fma(3.0, P2, Y[s]), P13), 1.0);
+    }
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const double P1 = (s & 1) ? fc.Phib : fc.Phi, P2 = (s & 1) ? fc.Phi : fc.Phib;
+        g[s] = f_fma(Y[s], f_fma(2.0, P2, Y[s]), P1);
+    }
+    if (need_q) {
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const double P1 = (s & 1) ? fc.Phib : fc.Phi, P24 = (s & 1) ? fc.Phi4 : fc.Phib4;
+            q[s] = f_fma(Y[s], f_fma(3.0, Y[s], P24), P1);
+        }
+    }
+    v_rcp<4>(o.f, inv);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) o.r1[s] = Y[s] * inv[s];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) o.r2[s] = o.r1[s] * Y[s];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) o.n[s] = g[s] * o.r1[s];
+    if (need_q) {
+#pragma unroll
+        for (int s = 0; s < 4; ++s) o.qf[s] = q[s] * o.r1[s];
+    }
+}
+
+// Common front end of the paired passes: E, 1/E and the four Boltzmann factors of the u and s flavour of one node.
+PNJL_HD void pair_front(const FastCtx& fc, double M2u, double M2s, double k2, double rE[2], double E[2], double Y[4]) {
+    double E2[2] = {k2 + M2u, k2 + M2s}, t[2], e1[2];
+    v_rsqrt<2>(E2, rE);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) E[j] = E2[j] * rE[j];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) t[j] = E[j] * fc.nInvT;
+    v_exp_nonpos<2>(t, e1);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) { Y[2 * j] = e1[j] * fc.kapP; Y[2 * j + 1] = e1[j] * fc.kapM; }
+}
+
+// FJ pass, u and s flavour of one node.  fu/fs: per-flavour sums as in fj_node_fast; sh: flavour-summed sums with
+// the u contribution counted twice (u and d are the same flavour here).
+PNJL_HD void fj_pair_fast(const FastCtx& fc, double M2u, double M2s, double k2, double coef, double fu[5], double fs[5],
+                          double sh[5]) {
+    double rE[2], E[2], Y[4];
+    pair_front(fc, M2u, M2s, k2, rE, E, Y);
+    Species4 sp;
+    species4_fast(fc, Y, sp, true);
+    double nsum[2], Q[2], crE[2], crE2[2], m3[4], s3[2], s4[2], gp[2], gpb[2], hpp[2], hppb[2], hpbpb[2];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) m3[s] = -3.0 * sp.n[s];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int a = 2 * j, b = 2 * j + 1;   // quark, antiquark
+        nsum[j] = sp.n[a] + sp.n[b];
+        Q[j] = f_fma(m3[a], sp.n[a], sp.qf[a]) + f_fma(m3[b], sp.n[b], sp.qf[b]);
+        crE[j] = coef * rE[j];
+        crE2[j] = crE[j] * rE[j];
+        s3[j] = f_fma(sp.r1[a], 1.0 + m3[a], sp.r2[b] * (2.0 + m3[b]));
+        s4[j] = f_fma(sp.r2[a], 2.0 + m3[a], sp.r1[b] * (1.0 + m3[b]));
+        gp[j] = sp.r1[a] + sp.r2[b];
+        gpb[j] = sp.r2[a] + sp.r1[b];
+        hpp[j] = f_fma(sp.r1[a], sp.r1[a], sp.r2[b] * sp.r2[b]);
+        hppb[j] = f_fma(sp.r1[a], sp.r2[a], sp.r2[b] * sp.r1[b]);
+        hpbpb[j] = f_fma(sp.r2[a], sp.r2[a], sp.r1[b] * sp.r1[b]);
+    }
+    fu[0] = f_fma(crE[0], nsum[0], fu[0]);           fs[0] = f_fma(crE[1], nsum[1], fs[0]);
+    fu[1] = f_fma(crE2[0], Q[0], fu[1]);             fs[1] = f_fma(crE2[1], Q[1], fs[1]);
+    fu[2] = f_fma(crE2[0] * rE[0], nsum[0], fu[2]);  fs[2] = f_fma(crE2[1] * rE[1], nsum[1], fs[2]);
+    fu[3] = f_fma(crE[0], s3[0], fu[3]);             fs[3] = f_fma(crE[1], s3[1], fs[3]);
+    fu[4] = f_fma(crE[0], s4[0], fu[4]);             fs[4] = f_fma(crE[1], s4[1], fs[4]);
+    sh[0] = f_fma(coef, f_fma(2.0, gp[0], gp[1]), sh[0]);
+    sh[1] = f_fma(coef, f_fma(2.0, gpb[0], gpb[1]), sh[1]);
+    sh[2] = f_fma(coef, f_fma(2.0, hpp[0], hpp[1]), sh[2]);
+    sh[3] = f_fma(coef, f_fma(2.0, hppb[0], hppb[1]), sh[3]);
+    sh[4] = f_fma(coef, f_fma(2.0, hpbpb[0], hpbpb[1]), sh[4]);
+}
+
+// Thermo pass / fused final pass, u and s flavour of one node.  tu/ts: {sum c n+, sum c n-, sum c ln(f+ f-),
+// sum c [n+ (E-mu) + n- (E+mu)]} per flavour; when WITH_F also s1u/s1s (sum c (n+ + n-)/E) and the flavour-summed
+// gsh[2] = {GP, GPB} (u counted twice).
+template <bool WITH_F>
+PNJL_HD void th_pair_fast(const FastCtx& fc, double mu, double M2u, double M2s, double k2, double coef, double tu[4],
+                          double ts[4], double& s1u, double& s1s, double gsh[2]) {
+    double rE[2], E[2], Y[4];
+    pair_front(fc, M2u, M2s, k2, rE, E, Y);
+    Species4 sp;
+    species4_fast(fc, Y, sp, false);
+    const double Lu = fast_log_pos(sp.f[0] * sp.f[1]);
+    const double Ls = fast_log_pos(sp.f[2] * sp.f[3]);
+    tu[0] = f_fma(coef, sp.n[0], tu[0]);  ts[0] = f_fma(coef, sp.n[2], ts[0]);
+    tu[1] = f_fma(coef, sp.n[1], tu[1]);  ts[1] = f_fma(coef, sp.n[3], ts[1]);
+    tu[2] = f_fma(coef, Lu, tu[2]);       ts[2] = f_fma(coef, Ls, ts[2]);
+    tu[3] = f_fma(coef, f_fma(sp.n[0], E[0] - mu, sp.n[1] * (E[0] + mu)), tu[3]);
+    ts[3] = f_fma(coef, f_fma(sp.n[2], E[1] - mu, sp.n[3] * (E[1] + mu)), ts[3]);
+    if (WITH_F) {
+        s1u = f_fma(coef * rE[0], sp.n[0] + sp.n[1], s1u);
+        s1s = f_fma(coef * rE[1], sp.n[2] + sp.n[3], s1s);
+        gsh[0] = f_fma(coef, f_fma(2.0, sp.r1[0] + sp.r2[1], sp.r1[2] + sp.r2[3]), gsh[0]);
+        gsh[1] = f_fma(coef, f_fma(2.0, sp.r2[0] + sp.r1[1], sp.r2[2] + sp.r1[3]), gsh[1]);
+    }
+}
+
 // Mesh slice seen by one lane: nodes lane, lane+stride, ...   (host build: lane 0, stride 1)
 struct MeshView {
     const double* p2;     // p^2
@@ -407,20 +598,18 @@ PNJL_HD bool fj_partial(const Model& m, bool isospin, const PointCtx& c, const d
         FastCtx fc;
         make_fast_ctx(c, fc);
         if (isospin && x[0] == x[1]) {
-            double fu[5] = {0, 0, 0, 0, 0}, fs[5] = {0, 0, 0, 0, 0}, su[5] = {0, 0, 0, 0, 0}, ss[5] = {0, 0, 0, 0, 0};
-#pragma unroll 2
+            double fu[5] = {0, 0, 0, 0, 0}, fs[5] = {0, 0, 0, 0, 0}, sh[5] = {0, 0, 0, 0, 0};
+#pragma unroll 1
             for (int k = lane; k < mv.n; k += stride) {
                 const double k2 = f_fma(c.xi, mv.pc2[k], mv.p2[k]);
-                const double cf = mv.coef[k];
-                fj_node_fast(fc, c.M2[0], k2, cf, fu, su);
-                fj_node_fast(fc, c.M2[2], k2, cf, fs, ss);
+                fj_pair_fast(fc, c.M2[0], c.M2[2], k2, mv.coef[k], fu, fs, sh);
             }
 #pragma unroll
             for (int q = 0; q < 5; ++q) {
                 acc[3 * q + 0] = fu[q];
                 acc[3 * q + 1] = fu[q];
                 acc[3 * q + 2] = fs[q];
-                acc[15 + q] = f_fma(2.0, su[q], ss[q]);
+                acc[15 + q] = sh[q];
             }
         } else {
             double f0[5] = {0, 0, 0, 0, 0}, f1[5] = {0, 0, 0, 0, 0}, f2[5] = {0, 0, 0, 0, 0}, sh[5] = {0, 0, 0, 0, 0};
@@ -623,12 +812,11 @@ PNJL_HD void thermo_partial(const Model& m, bool isospin, const PointCtx& c, con
         double t0[4] = {0, 0, 0, 0}, t1[4] = {0, 0, 0, 0}, t2[4] = {0, 0, 0, 0};
         const bool iso = isospin && x[0] == x[1];
         if (iso) {
-#pragma unroll 2
+            double d0 = 0, d1 = 0, dg[2] = {0, 0};
+#pragma unroll 1
             for (int k = lane; k < mv.n; k += stride) {
                 const double k2 = f_fma(c.xi, mv.pc2[k], mv.p2[k]);
-                const double cf = mv.coef[k];
-                thermo_node_fast(fc, c.mu, c.M2[0], k2, cf, t0);
-                thermo_node_fast(fc, c.mu, c.M2[2], k2, cf, t2);
+                th_pair_fast<false>(fc, c.mu, c.M2[0], c.M2[2], k2, mv.coef[k], t0, t2, d0, d1, dg);
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) t1[q] = t0[q];
@@ -671,15 +859,19 @@ PNJL_HD bool ft_partial(const Model& m, bool isospin, const PointCtx& c, const d
     double a0[7] = {0, 0, 0, 0, 0, 0, 0}, a1[7] = {0, 0, 0, 0, 0, 0, 0}, a2[7] = {0, 0, 0, 0, 0, 0, 0};
     const bool iso = isospin && x[0] == x[1];
     if (iso) {
-#pragma unroll 2
+        double tu[4] = {0, 0, 0, 0}, ts[4] = {0, 0, 0, 0}, s1u = 0, s1s = 0, gsh[2] = {0, 0};
+#pragma unroll 1
         for (int k = lane; k < mv.n; k += stride) {
             const double k2 = f_fma(c.xi, mv.pc2[k], mv.p2[k]);
-            const double cf = mv.coef[k];
-            ft_node_fast(fc, c.mu, c.M2[0], k2, cf, a0);
-            ft_node_fast(fc, c.mu, c.M2[2], k2, cf, a2);
+            th_pair_fast<true>(fc, c.mu, c.M2[0], c.M2[2], k2, mv.coef[k], tu, ts, s1u, s1s, gsh);
         }
-#pragma unroll
-        for (int q = 0; q < 7; ++q) a1[q] = a0[q];
+        facc[0] = s1u; facc[1] = s1u; facc[2] = s1s;
+        facc[3] = gsh[0]; facc[4] = gsh[1];
+        tacc[TH_NP + 0] = tu[0]; tacc[TH_NP + 1] = tu[0]; tacc[TH_NP + 2] = ts[0];
+        tacc[TH_NM + 0] = tu[1]; tacc[TH_NM + 1] = tu[1]; tacc[TH_NM + 2] = ts[1];
+        tacc[TH_L] = f_fma(2.0, tu[2], ts[2]);
+        tacc[TH_T] = f_fma(2.0, tu[3], ts[3]);
+        return true;
     } else {
         for (int k = lane; k < mv.n; k += stride) {
             const double k2 = f_fma(c.xi, mv.pc2[k], mv.p2[k]);

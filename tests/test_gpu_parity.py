@@ -44,7 +44,7 @@ def assert_state_parity(rec, res, tol=TOL, label="", max_wander=0):
     rec = rec.reshape(-1, A.REC_DOUBLES)
     st = rec[:, A.REC_STATUS].astype(np.int64)
     conv_g = (st & A.ST_CONVERGED) != 0
-    wander = res.n_fj > 25 * (6 if (res.status & A.ST_USED_MULTISEED).any() else 1)
+    wander = res.n_fj > 25 * np.where((res.status & A.ST_USED_MULTISEED) != 0, 6, 1)
     assert ((conv_g == res.converged) | wander).all(), (label, np.nonzero(conv_g != res.converged)[0][:10])
     w = state_errors(rec, res)
     bad = conv_g & res.converged & (w > tol)
