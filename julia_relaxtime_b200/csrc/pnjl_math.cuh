@@ -72,6 +72,16 @@ PNJL_HD double f_fma(double a, double b, double c) {
 #endif
 }
 
+// exp polynomial (degree 11, highest power first) and range-reduction constants.  On the device they live in
+// constant memory so that every DFMA takes them as a constant-bank operand instead of pinning 2 registers each.
+#if defined(__CUDACC__)
+__constant__ double kExpC[12] = {0x1.af635e4f6b5eep-26, 0x1.28b43a93fe57ap-22, 0x1.71ddf5514be0cp-19, 0x1.a01991731e6fap-16,
+                                 0x1.a01a01b150ad2p-13, 0x1.6c16c1881156bp-10, 0x1.111111110f205p-7,  0x1.555555554f067p-5,
+                                 0x1.555555555555ap-3,  0x1.0000000000011p-1,  1.0,                   1.0};
+__constant__ double kExpR[4] = {1.4426950408889634, 6755399441055744.0, -6.93147180369123816490e-01,
+                                -1.90821492927058770002e-10};
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // Branch-free FP64 primitives for the fast path (device: MUFU seed + Newton-Raphson in DFMA, a
 // degree-11 polynomial exp; host build: libm).  Domain restrictions are guaranteed by the
@@ -433,28 +443,24 @@ PNJL_HD void v_rcp(const double x[W], double y[W]) {
 template <int W>
 PNJL_HD void v_exp_nonpos(const double t[W], double out[W]) {
 #if defined(__CUDA_ARCH__)
-    const double kShift = 6755399441055744.0;
     double kd[W], r[W], p[W];
     int k[W];
 #pragma unroll
-    for (int j = 0; j < W; ++j) kd[j] = fma(t[j], 1.4426950408889634, kShift);
+    for (int j = 0; j < W; ++j) kd[j] = fma(t[j], kExpR[0], kExpR[1]);
 #pragma unroll
     for (int j = 0; j < W; ++j) k[j] = __double2loint(kd[j]);
 #pragma unroll
-    for (int j = 0; j < W; ++j) kd[j] -= kShift;
+    for (int j = 0; j < W; ++j) kd[j] -= kExpR[1];
 #pragma unroll
-    for (int j = 0; j < W; ++j) r[j] = fma(kd[j], -6.93147180369123816490e-01, t[j]);
+    for (int j = 0; j < W; ++j) r[j] = fma(kd[j], kExpR[2], t[j]);
 #pragma unroll
-    for (int j = 0; j < W; ++j) r[j] = fma(kd[j], -1.90821492927058770002e-10, r[j]);
-    const double c[11] = {0x1.28b43a93fe57ap-22, 0x1.71ddf5514be0cp-19, 0x1.a01991731e6fap-16, 0x1.a01a01b150ad2p-13,
-                          0x1.6c16c1881156bp-10, 0x1.111111110f205p-7,  0x1.555555554f067p-5,  0x1.555555555555ap-3,
-                          0x1.0000000000011p-1,  1.0,                   1.0};
+    for (int j = 0; j < W; ++j) r[j] = fma(kd[j], kExpR[3], r[j]);
 #pragma unroll
-    for (int j = 0; j < W; ++j) p[j] = 0x1.af635e4f6b5eep-26;
+    for (int j = 0; j < W; ++j) p[j] = fma(kExpC[0], r[j], kExpC[1]);
 #pragma unroll
-    for (int q = 0; q < 11; ++q) {
+    for (int q = 2; q < 12; ++q) {
 #pragma unroll
-        for (int j = 0; j < W; ++j) p[j] = fma(p[j], r[j], c[q]);
+        for (int j = 0; j < W; ++j) p[j] = fma(p[j], r[j], kExpC[q]);
     }
 #pragma unroll
     for (int j = 0; j < W; ++j) out[j] = __hiloint2double(__double2hiint(p[j]) + (k[j] << 20), __double2loint(p[j]));
