@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define PNJL_ABI_VERSION 3
+#define PNJL_ABI_VERSION 4
 
 /* ---- result record layout (doubles) --------------------------------------------------------- */
 #define PNJL_REC_DOUBLES 32
@@ -111,6 +111,11 @@ typedef struct pnjl_config {
                                        mu_u = mu_d and m_u0 = m_d0 on this path) evaluate the d flavour as the u flavour and
                                        keep Newton/dogleg steps u<->d symmetric (a <= 1 ulp change of the step).  0: three
                                        independent flavours everywhere, like the reference's loop (Integrals.jl:250-257). */
+    int32_t schedule;               /* kernel organisation for the 32-lane layout.  0 (default): warp-specialised — worker warps
+                                       run only quadrature loops, controller lanes own one line/point each and run the
+                                       solve cascade in SIMT, passes are handed over through shared-memory mailboxes.
+                                       1: every warp owns a line/point, CTAs phase-aligned by named barriers.
+                                       Results agree to round-off; the 8- and 16-lane layouts always use organisation 1. */
 } pnjl_config;
 
 /* First-order phase boundary mu_c(T) for one xi (data/reference/pnjl/boundary.csv + cep.csv;

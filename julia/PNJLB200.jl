@@ -33,6 +33,7 @@ struct Config
     device::Int32; lanes_per_solve::Int32
     predict_tol::Cdouble
     isospin_symmetric::Int32
+    schedule::Int32
 end
 
 struct Boundary                      # struct pnjl_boundary
@@ -64,7 +65,7 @@ function Engine(; p_num::Int=64, t_num::Int=8, iterations::Int=1000, trust_regio
                  C.a0, C.a1, C.a2, C.b3, C.ρ0_inv_fm3, Int32(C.N_color), Int32(p_num), Int32(t_num),
                  pointer(pn), pointer(pw), pointer(cn), pointer(cw),
                  1e-9, 1e-9, residual_norm_max, 1e-8, Int32(iterations), Int32(trust_region_fallback),
-                 Int32(auto_multiseed_fallback), 1e-12, Int32(device), Int32(0), 1e-4, Int32(1))
+                 Int32(auto_multiseed_fallback), 1e-12, Int32(device), Int32(0), 1e-4, Int32(1), Int32(0))
     h = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve pn pw cn cw begin
         check(ccall((:pnjl_create, LIB), Cint, (Ref{Config}, Ref{Ptr{Cvoid}}), cfg, h), "pnjl_create")

@@ -106,7 +106,7 @@ class Engine:
 
     def __init__(self, p_num=64, t_num=8, max_iter=1000, trust_region_fallback=True, auto_multiseed_fallback=True,
                  residual_norm_max=1e-6, omega_tie_rel=1e-12, device=-1, lanes_per_solve=0, nodes=None,
-                 isospin_symmetric=True, predict_tol=1e-4, consts: PNJLConstants = DEFAULT):
+                 isospin_symmetric=True, predict_tol=1e-4, schedule=0, consts: PNJLConstants = DEFAULT):
         self.L = load()
         self.p_num, self.t_num = int(p_num), int(t_num)
         self._keep = None
@@ -118,7 +118,7 @@ class Engine:
             xtol=1e-9, ftol=1e-9, residual_norm_max=residual_norm_max, phi_tol=1e-8, max_iter=int(max_iter),
             tr_fallback=int(trust_region_fallback), auto_multiseed_fallback=int(auto_multiseed_fallback),
             omega_tie_rel=omega_tie_rel, device=int(device), lanes_per_solve=int(lanes_per_solve),
-            predict_tol=float(predict_tol), isospin_symmetric=int(isospin_symmetric))
+            predict_tol=float(predict_tol), isospin_symmetric=int(isospin_symmetric), schedule=int(schedule))
         if nodes is not None:
             self._keep = [np.ascontiguousarray(a, dtype=np.float64) for a in nodes]
             cfg.p_nodes, cfg.p_w, cfg.c_nodes, cfg.c_w = [_abi.dptr(a) for a in self._keep]

@@ -328,24 +328,37 @@ __global__ void __launch_bounds__(512, 1) k_scan_lines(const DeviceConfig* __res
 // code.  Hand-off is a sequence number per mailbox (volatile shared + __threadfence_block, short __nanosleep
 // polls); there are no CTA barriers after the prologue, so divergent controller lanes cannot dead-lock.
 enum { WS_FJ = 0, WS_FT = 1, WS_TH = 2, WS_EXIT = 3 };
+constexpr int kWsR = 21;   // doubles per result block: up to 20 sums + the fast-path flag
 
 struct WsSlot {
-    double d[9];      // T, mu, xi, x[5]
-    double r[21];     // reduced sums (20 FJ | 5 + 8 fused | 8 thermo) ; r[20] = fast-path flag
+    double d[9];        // T, mu, xi, x[5]
+    double r[kWsR];     // reduced sums (20 FJ | 5 + 8 fused | 8 thermo) ; r[20] = fast-path flag
     int type;
-    int pad[3];
+    int parts_done;     // parts of the current pass finished so far (atomic; only when a pass is split)
+    int pad[2];
 };
 
 // One request queue per controller warp ("group"): its lanes fill their mailboxes, lane 0 publishes the round,
-// any idle worker pulls the next mailbox index, and the lanes resume when all mailboxes of the round are served.
+// any idle worker pulls the next work item, and the lanes resume when all mailboxes of the round are served.
 struct WsGroup {
     volatile int round;      // published round number (0 = nothing yet)
-    volatile int exit_flag;  // set when every line of the group is finished
-    int next;                // next mailbox index to hand out in the current round   (atomic)
-    int done;                // mailboxes served in total, monotonic                   (atomic)
+    volatile int exit_flag;  // set when every task of the group is finished
+    int next;                // next work item (mailbox x part) to hand out in the current round   (atomic)
+    int done;                // mailboxes served in total, monotonic                                (atomic)
     int n_slots;             // mailboxes of this group
-    int first_slot;          // index of its first mailbox in s_slots
+    int first_slot;          // index of its first mailbox
     int pad[2];
+};
+
+// What the controller lanes work on: whole continuity lines or independent points.
+struct WsTask {
+    int mode;                // 0: lines (scan_line), 1: points (solve / solve_multi)
+    long long n_tasks;
+    // lines
+    const double* muq_MeV; const double* xi; const int* table_idx; int n_T; const double* T_MeV;
+    // points
+    const double* T_fm; const double* mu_fm; int seed_mode; int n_seeds; const double* seeds;
+    double* records;
 };
 
 struct CtrlEval {
@@ -355,19 +368,27 @@ struct CtrlEval {
     int seq;          // rounds posted so far
     unsigned grp;     // lanes of this controller warp that own a mailbox
     bool leader;      // lowest lane of the group
+    bool finished;    // this lane has no task left
     double p2max, pc2max;
+#ifdef PNJL_PROFILE_PHASES
+    unsigned long long* dbg;
+    long long t_ret;
+#endif
 
-    // Post one request and wait for the worker.  One code location for every caller (noinline) and a fixed lane
-    // group per mailbox phase: all lines of a phase meet here, poll with one instruction stream, and leave together,
-    // so the scalar code between passes runs SIMT-converged over the lines of the phase.
-    // Returns true (without posting anything) once every line of the group is finished.
+    // Post one request and wait for the workers.  One code location for every caller (noinline) and one wait group
+    // per controller warp: all its lanes meet here once per round (lanes without tasks come from retire()), poll
+    // with one instruction stream and leave together, so the scalar code between passes runs SIMT-converged.
+    // Returns true (without posting anything) once every task of the group is finished.
     __device__ __noinline__ bool request(int type, double T, double mu, double xi, const double x[5]) {
+#ifdef PNJL_PROFILE_PHASES
+        if (dbg && t_ret) { atomicAdd(dbg + 4, (unsigned long long)(clock64() - t_ret)); atomicAdd(dbg + 5, 1ULL); }
+        const long long t_in = clock64();
+#endif
         slot->d[0] = T; slot->d[1] = mu; slot->d[2] = xi;
 #pragma unroll
         for (int i = 0; i < 5; ++i) slot->d[3 + i] = x[i];
         slot->type = type;
         __threadfence_block();
-        // every lane of the group meets here once per round (lanes without lines come from retire())
         if (__ballot_sync(grp, finished) == grp) return true;
         ++seq;
         if (leader) {
@@ -382,10 +403,14 @@ struct CtrlEval {
             __nanosleep(256);
         }
         __threadfence_block();
+#ifdef PNJL_PROFILE_PHASES
+        t_ret = clock64();
+        if (dbg) atomicAdd(dbg + 6, (unsigned long long)(t_ret - t_in));
+#endif
         return false;
     }
-    // A lane without lines left keeps posting empty requests so that the round size stays fixed; returns when the
-    // whole group has run out of lines.
+    // A lane without tasks left keeps posting empty requests so that the round size stays fixed; returns when the
+    // whole group has run out of tasks.
     __device__ __noinline__ void retire() {
         finished = true;
         const double zero[5] = {0, 0, 0, 0, 0};
@@ -395,7 +420,6 @@ struct CtrlEval {
             group->exit_flag = 1;
         }
     }
-    bool finished;
     __device__ __noinline__ void fj(double T, double mu, double xi, const double x[5], double F[5], double J[25]) {
         PointCtx c;
         make_ctx(*m, T, mu, xi, x, c);
@@ -406,11 +430,17 @@ struct CtrlEval {
         finish_fj(*m, c, x, acc, F, J, slot->r[20] != 0.0);
     }
     __device__ __noinline__ bool fj_step(double T, double mu, double xi, const double x[5], double F[5], double p[5]) {
+        PointCtx c;
+        make_ctx(*m, T, mu, xi, x, c);
+        request(WS_FJ, T, mu, xi, x);
+        double acc[kFJAcc];
+#pragma unroll
+        for (int i = 0; i < kFJAcc; ++i) acc[i] = slot->r[i];
         double J[25], b[5];
-        fj(T, mu, xi, x, F, J);
+        finish_fj(*m, c, x, acc, F, J, slot->r[20] != 0.0);
 #pragma unroll
         for (int i = 0; i < 5; ++i) b[i] = F[i];
-        const bool ok = lu_solve5(J, b, p);
+        const bool ok = lu_solve5_regs(J, b, p);     // J and the elimination stay in registers
 #pragma unroll
         for (int i = 0; i < 5; ++i) p[i] = -p[i];
         return ok;
@@ -441,6 +471,11 @@ struct CtrlEval {
     }
 };
 
+__device__ __forceinline__ void ctrl_store_record(const double rec[PNJL_REC_DOUBLES], double* out) {
+#pragma unroll
+    for (int q = 0; q < PNJL_REC_DOUBLES; q += 2) *reinterpret_cast<double2*>(out + q) = make_double2(rec[q], rec[q + 1]);
+}
+
 struct CtrlSink {
     double* base;
     double xi;
@@ -448,17 +483,14 @@ struct CtrlSink {
                                                int n_ft) {
         double rec[PNJL_REC_DOUBLES];
         fill_record(r, T_fm, mu_fm, xi, n_fj, n_th, n_ft, rec);
-        double* out = base + (long long)PNJL_REC_DOUBLES * it;
-#pragma unroll
-        for (int q = 0; q < PNJL_REC_DOUBLES; q += 2) *reinterpret_cast<double2*>(out + q) = make_double2(rec[q], rec[q + 1]);
+        ctrl_store_record(rec, base + (long long)PNJL_REC_DOUBLES * it);
     }
 };
 
-constexpr int kWsMaxSlots = 64;
-constexpr int kWsMaxSpw = 4;   // mailboxes per worker
-
-// One quadrature pass of a worker warp for mailbox `sl`.
-__device__ __noinline__ void ws_worker_pass(const DeviceConfig* cfg, const MeshView& mv, WsSlot* sl, int type, int lane) {
+// One quadrature pass (or one part of it: nodes lane + 32 part, stride 32 parts) of a worker warp for mailbox `sl`;
+// the warp-reduced sums go to out[0..20].
+__device__ __noinline__ void ws_worker_pass(const DeviceConfig* cfg, const MeshView& mv, const WsSlot* sl, int type, int lane,
+                                            int part, int parts, double* out) {
     const double T = sl->d[0], mu = sl->d[1], xi = sl->d[2];
     double x[5];
 #pragma unroll
@@ -466,76 +498,83 @@ __device__ __noinline__ void ws_worker_pass(const DeviceConfig* cfg, const MeshV
     PointCtx c;
     make_ctx(cfg->m, T, mu, xi, x, c);
     const bool iso = cfg->sp.isospin != 0;
+    const int l0 = lane + 32 * part, stride = 32 * parts;
     if (type == WS_FJ) {
         double acc[kFJAcc];
-        const bool fast = fj_partial(cfg->m, iso, c, x, mv, lane, 32, acc);
+        const bool fast = fj_partial(cfg->m, iso, c, x, mv, l0, stride, acc);
 #pragma unroll
         for (int i = 0; i < kFJAcc; ++i) {
             double v = acc[i];
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-            if (lane == 0) sl->r[i] = v;
+            if (lane == 0) out[i] = v;
         }
-        if (lane == 0) sl->r[20] = fast ? 1.0 : 0.0;
+        if (lane == 0) out[20] = fast ? 1.0 : 0.0;
     } else if (type == WS_FT) {
         double facc[kFtAcc], tacc[kThAcc];
-        ft_partial(cfg->m, iso, c, x, mv, lane, 32, facc, tacc);
+        ft_partial(cfg->m, iso, c, x, mv, l0, stride, facc, tacc);
 #pragma unroll
         for (int i = 0; i < kFtAcc; ++i) {
             double v = facc[i];
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-            if (lane == 0) sl->r[i] = v;
+            if (lane == 0) out[i] = v;
         }
 #pragma unroll
         for (int i = 0; i < kThAcc; ++i) {
             double v = tacc[i];
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-            if (lane == 0) sl->r[kFtAcc + i] = v;
+            if (lane == 0) out[kFtAcc + i] = v;
         }
     } else {
         double tacc[kThAcc];
-        thermo_partial(cfg->m, iso, c, x, mv, lane, 32, tacc);
+        thermo_partial(cfg->m, iso, c, x, mv, l0, stride, tacc);
 #pragma unroll
         for (int i = 0; i < kThAcc; ++i) {
             double v = tacc[i];
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-            if (lane == 0) sl->r[i] = v;
+            if (lane == 0) out[i] = v;
         }
     }
 }
 
-// blockDim.x = 32 * (n_workers + n_ctrl_warps); slots = 2 * n_workers, spread evenly over the controller warps.
-__global__ void __launch_bounds__(512, 1) k_scan_lines_ws(const DeviceConfig* __restrict__ cfg, const double* __restrict__ g_mesh,
-                                                          long long n_lines, const double* __restrict__ muq_MeV,
-                                                          const double* __restrict__ xi, const int* __restrict__ table_idx,
-                                                          int n_T, const double* __restrict__ T_MeV,
-                                                          double* __restrict__ records, unsigned long long* counter,
-                                                          int n_workers, int n_ctrl_warps, int spw) {
-    extern __shared__ double s_mesh[];
-    __shared__ WsSlot s_slots[kWsMaxSlots];
-    __shared__ WsGroup s_groups[8];
+constexpr int kWsMaxGroups = 8;
+
+// blockDim.x = 32 * (n_workers + n_ctrl_warps).  n_slots mailboxes (one task each) are spread evenly over the
+// controller warps; a pass may be split into `parts` node ranges served by different workers (few tasks per SM).
+// Dynamic shared memory: mesh [3 n] | mailboxes [n_slots] | partial sums [n_slots][parts][21] (parts > 1 only).
+__global__ void __launch_bounds__(512, 1) k_solve_ws(const DeviceConfig* __restrict__ cfg, const double* __restrict__ g_mesh,
+                                                     WsTask task, unsigned long long* counter, int n_workers,
+                                                     int n_ctrl_warps, int n_slots, int parts) {
+    extern __shared__ double s_dyn[];
+    __shared__ WsGroup s_groups[kWsMaxGroups];
     const int n = cfg->n_nodes;
+    double* s_mesh = s_dyn;
+    WsSlot* s_slots = reinterpret_cast<WsSlot*>(s_dyn + 3 * n);
+    double* s_part = reinterpret_cast<double*>(s_slots + n_slots);
     for (int i = threadIdx.x; i < 3 * n; i += blockDim.x) s_mesh[i] = g_mesh[i];
-    // mailbox phases j = 0..spw-1 (n_workers mailboxes each); controller warp cw owns phases [cw*ppc, (cw+1)*ppc)
-    const int ppc = (spw + n_ctrl_warps - 1) / n_ctrl_warps;
+    const int per = (n_slots + n_ctrl_warps - 1) / n_ctrl_warps;
     if (threadIdx.x < n_ctrl_warps) {
         const int cw = threadIdx.x;
-        int phases = spw - cw * ppc;
-        phases = phases < 0 ? 0 : (phases > ppc ? ppc : phases);
+        int cnt = n_slots - cw * per;
+        cnt = cnt < 0 ? 0 : (cnt > per ? per : cnt);
         s_groups[cw].round = 0;
-        s_groups[cw].exit_flag = phases == 0 ? 1 : 0;
+        s_groups[cw].exit_flag = cnt == 0 ? 1 : 0;
         s_groups[cw].next = 0;
         s_groups[cw].done = 0;
-        s_groups[cw].n_slots = phases * n_workers;
-        s_groups[cw].first_slot = cw * ppc * n_workers;
+        s_groups[cw].n_slots = cnt;
+        s_groups[cw].first_slot = cw * per;
+    }
+    for (int i = threadIdx.x; i < n_slots; i += blockDim.x) {
+        s_slots[i].type = WS_EXIT;
+        s_slots[i].parts_done = 0;
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp < n_workers) {
-        // ---------------- worker: pull mailboxes from whichever group has a round open ----------------
+        // ---------------- worker: pull work items from whichever group has a round open ----------------
         MeshView mv;
         mv.p2 = s_mesh; mv.pc2 = s_mesh + n; mv.coef = s_mesh + 2 * n; mv.n = n;
         mv.p2max = cfg->p2max; mv.pc2max = cfg->pc2max;
@@ -550,23 +589,55 @@ __global__ void __launch_bounds__(512, 1) k_scan_lines_ws(const DeviceConfig* __
                 any_live = true;
                 const int round = gr->round;
                 if (round == 0) continue;
-                // rounds are strictly sequential per group: mailboxes of round r are all served before r+1 opens
+                // rounds are strictly sequential per group: all mailboxes of round r are served before r+1 opens
                 if (*((volatile int*)&gr->done) >= round * gr->n_slots) continue;
                 int idx = 0;
                 if (lane == 0) idx = atomicAdd(&gr->next, 1);
                 idx = __shfl_sync(0xffffffffu, idx, 0);
-                if (idx >= gr->n_slots) continue;           // the round is fully handed out
+                if (idx >= gr->n_slots * parts) continue;    // the round is fully handed out
                 __threadfence_block();
-                WsSlot* sl = &s_slots[gr->first_slot + idx];
+                const int si = gr->first_slot + idx / parts, part = idx % parts;
+                WsSlot* sl = &s_slots[si];
                 const int type = sl->type;
 #ifdef PNJL_PROFILE_PHASES
                 const long long tp0 = clock64();
                 if (lane == 0 && cfg->dbg && t_idle) atomicAdd(cfg->dbg + 3, (unsigned long long)(tp0 - t_idle));
 #endif
-                if (type != WS_EXIT) ws_worker_pass(cfg, mv, sl, type, lane);
+                bool slot_complete = true;
+                if (type != WS_EXIT) {
+                    if (parts == 1) {
+                        ws_worker_pass(cfg, mv, sl, type, lane, 0, 1, sl->r);
+                    } else {
+                        double* mine = s_part + ((size_t)si * parts + part) * kWsR;
+                        ws_worker_pass(cfg, mv, sl, type, lane, part, parts, mine);
+                        __syncwarp();
+                        __threadfence_block();
+                        int c = 0;
+                        if (lane == 0) c = atomicAdd(&sl->parts_done, 1);
+                        c = __shfl_sync(0xffffffffu, c, 0);
+                        slot_complete = (c == parts - 1);
+                        if (slot_complete) {
+                            // last part in: add the partial sums in part order (the same order whoever finishes last)
+                            __threadfence_block();
+                            if (lane < kWsR) {
+                                const double* base = s_part + (size_t)si * parts * kWsR + lane;
+                                double v = base[0];
+                                for (int q = 1; q < parts; ++q) v += base[q * kWsR];
+                                sl->r[lane] = (lane == 20) ? base[0] : v;
+                            }
+                            if (lane == 0) sl->parts_done = 0;
+                        }
+                    }
+                } else if (parts > 1) {
+                    int c = 0;
+                    if (lane == 0) c = atomicAdd(&sl->parts_done, 1);
+                    c = __shfl_sync(0xffffffffu, c, 0);
+                    slot_complete = (c == parts - 1);
+                    if (slot_complete && lane == 0) sl->parts_done = 0;
+                }
                 __syncwarp();
                 __threadfence_block();
-                if (lane == 0) atomicAdd(&gr->done, 1);
+                if (slot_complete && lane == 0) atomicAdd(&gr->done, 1);
                 did = true;
 #ifdef PNJL_PROFILE_PHASES
                 t_idle = clock64();
@@ -578,7 +649,7 @@ __global__ void __launch_bounds__(512, 1) k_scan_lines_ws(const DeviceConfig* __
         }
         return;
     }
-    // ---------------- controller: lane <-> mailbox <-> one line at a time ----------------
+    // ---------------- controller: lane <-> mailbox <-> one task at a time ----------------
     const int cw = warp - n_workers;
     WsGroup* gr = &s_groups[cw];
     if (lane >= gr->n_slots) return;
@@ -592,12 +663,40 @@ __global__ void __launch_bounds__(512, 1) k_scan_lines_ws(const DeviceConfig* __
     ev.finished = false;
     ev.p2max = cfg->p2max;
     ev.pc2max = cfg->pc2max;
+#ifdef PNJL_PROFILE_PHASES
+    ev.dbg = cfg->dbg;
+    ev.t_ret = 0;
+#endif
     Solver<CtrlEval> sv(cfg->m, cfg->sp, ev);
     for (;;) {
-        const long long l = (long long)atomicAdd(counter, 1ULL);
-        if (l >= n_lines) break;
-        CtrlSink sink{records + (long long)PNJL_REC_DOUBLES * n_T * l, xi[l]};
-        scan_line(sv, &cfg->pt, table_idx ? table_idx[l] : -1, muq_MeV[l], xi[l], n_T, T_MeV, sink);
+        const long long t = (long long)atomicAdd(counter, 1ULL);
+        if (t >= task.n_tasks) break;
+        if (task.mode == 0) {
+            CtrlSink sink{task.records + (long long)PNJL_REC_DOUBLES * task.n_T * t, task.xi[t]};
+            scan_line(sv, &cfg->pt, task.table_idx ? task.table_idx[t] : -1, task.muq_MeV[t], task.xi[t], task.n_T, task.T_MeV,
+                      sink);
+        } else {
+            const double T = task.T_fm[t], mu = task.mu_fm[t], x_i = task.xi[t];
+            sv.set_point(T, mu, x_i);
+            sv.n_fj = 0; sv.n_th = 0; sv.n_ft = 0;
+            PointRes r;
+            if (task.seed_mode == PNJL_SEED_EXPLICIT && task.n_seeds == 1) {
+                double x0[5];
+                copy5(x0, task.seeds + 5 * t);
+                sv.solve_with_fallback(x0, r);
+            } else if (task.seed_mode == PNJL_SEED_EXPLICIT) {
+                sv.solve_multi(task.seeds + 5 * (long long)task.n_seeds * t, task.n_seeds, r);
+            } else if (task.seed_mode == PNJL_SEED_AUTO) {
+                double x0[5];
+                default_seed(2, T, mu, x0);
+                sv.solve_with_fallback(x0, r);
+            } else {
+                sv.solve_multi(nullptr, 6, r);
+            }
+            double rec[PNJL_REC_DOUBLES];
+            fill_record(r, T, mu, x_i, sv.n_fj, sv.n_th, sv.n_ft, rec);
+            ctrl_store_record(rec, task.records + (long long)PNJL_REC_DOUBLES * t);
+        }
     }
     ev.retire();
 }
@@ -811,25 +910,33 @@ int launch_points(pnjl_handle* h, long long n, const double* T, const double* mu
     return PNJL_OK;
 }
 
-int launch_lines_ws(pnjl_handle* h, long long n_lines, const double* muq, const double* xi, const int* tidx, int n_T,
-                    const double* T, double* rec, cudaStream_t st) {
-    const size_t smem = sizeof(double) * 3 * h->n_nodes;
-    int nw = h->ws_workers, nc = h->ws_ctrl_warps, spw = h->ws_spw;
-    // few lines per GPU: fewer mailboxes per worker first, then fewer workers, so that every SM still gets lines
-    const long long per_sm = (n_lines + h->sm_count - 1) / h->sm_count;
-    while (spw > 1 && per_sm < (long long)spw * nw) --spw;
-    if (per_sm < nw) {
-        nw = (int)(per_sm < 1 ? 1 : per_sm);
+// Launch geometry of the warp-specialised kernel for `n_tasks` lines/points on this GPU.
+int launch_ws(pnjl_handle* h, const WsTask& task, cudaStream_t st) {
+    int nw = h->ws_workers, nc = h->ws_ctrl_warps, spw = h->ws_spw, parts = 1;
+    const long long per_sm = (task.n_tasks + h->sm_count - 1) / h->sm_count;   // tasks an SM has to carry at least
+    long long n_slots = (long long)spw * nw;
+    if (per_sm < n_slots) {
+        // few tasks per SM (multi-GPU slabs, small grids): one mailbox per task and split every pass over
+        // several workers so that all workers stay busy
+        n_slots = per_sm < 1 ? 1 : per_sm;
+        while (parts < 4 && n_slots * parts * 2 <= 2LL * nw) parts *= 2;
+        if (n_slots * parts < nw) nw = (int)(n_slots * parts);
     }
-    while (((spw + nc - 1) / nc) * nw > 32) ++nc;      // lanes of one controller warp = phases per warp x workers
+    if (getenv("PNJL_WS_PARTS")) parts = atoi(getenv("PNJL_WS_PARTS"));
+    if (parts < 1) parts = 1;
+    if (parts > 4) parts = 4;
+    while ((n_slots + nc - 1) / nc > 32 && nc < kWsMaxGroups) ++nc;
+    if (nc > (int)n_slots) nc = (int)n_slots;
     if (nw + nc > 16) nw = 16 - nc;
     const int threads = 32 * (nw + nc);
+    const size_t smem = sizeof(double) * 3 * h->n_nodes + sizeof(WsSlot) * (size_t)n_slots +
+                        (parts > 1 ? sizeof(double) * kWsR * (size_t)n_slots * parts : 0);
     cudaFuncAttributes fa;
-    CUDA_TRY(cudaFuncGetAttributes(&fa, k_scan_lines_ws));
-    if (smem > 40 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_scan_lines_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    long long need = (n_lines + (long long)spw * nw - 1) / ((long long)spw * nw);
+    CUDA_TRY(cudaFuncGetAttributes(&fa, k_solve_ws));
+    if (smem > 40 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_solve_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long need = (task.n_tasks + n_slots - 1) / n_slots;
     int per_sm_ctas = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_ctas, k_scan_lines_ws, threads, smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_ctas, k_solve_ws, threads, smem));
     if (per_sm_ctas < 1) return fail(PNJL_ERR_CUDA, "warp-specialised kernel does not fit on an SM");
     const long long cap = (long long)per_sm_ctas * h->sm_count;
     const int blocks = (int)(need < cap ? need : cap);
@@ -837,12 +944,29 @@ int launch_lines_ws(pnjl_handle* h, long long n_lines, const double* muq, const 
     h->stats.smem_bytes = (int)smem;
     h->stats.blocks = blocks;
     h->stats.threads = threads;
-    h->stats.lanes_per_solve = 32;
+    h->stats.lanes_per_solve = 32 * parts;
     CUDA_TRY(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned long long), st));
-    k_scan_lines_ws<<<blocks, threads, smem, st>>>(h->d_cfg, h->d_mesh, n_lines, muq, xi, tidx, n_T, T, rec, h->d_counter, nw, nc, spw);
+    k_solve_ws<<<blocks, threads, smem, st>>>(h->d_cfg, h->d_mesh, task, h->d_counter, nw, nc, (int)n_slots, parts);
     CUDA_TRY(cudaGetLastError());
     h->stats.kernel_launches += 1;
     return PNJL_OK;
+}
+
+int launch_lines_ws(pnjl_handle* h, long long n_lines, const double* muq, const double* xi, const int* tidx, int n_T,
+                    const double* T, double* rec, cudaStream_t st) {
+    WsTask t;
+    std::memset(&t, 0, sizeof(t));
+    t.mode = 0; t.n_tasks = n_lines; t.muq_MeV = muq; t.xi = xi; t.table_idx = tidx; t.n_T = n_T; t.T_MeV = T; t.records = rec;
+    return launch_ws(h, t, st);
+}
+
+int launch_points_ws(pnjl_handle* h, long long n, const double* T, const double* mu, const double* xi, int seed_mode,
+                     int n_seeds, const double* seeds, double* rec, cudaStream_t st) {
+    WsTask t;
+    std::memset(&t, 0, sizeof(t));
+    t.mode = 1; t.n_tasks = n; t.T_fm = T; t.mu_fm = mu; t.xi = xi; t.seed_mode = seed_mode; t.n_seeds = n_seeds; t.seeds = seeds;
+    t.records = rec;
+    return launch_ws(h, t, st);
 }
 
 template <int G>
@@ -887,7 +1011,9 @@ int dispatch_points(pnjl_handle* h, long long n, const double* T, const double* 
     switch (h->G) {
         case 8: return launch_points<8>(h, n, T, mu, xi, seed_mode, n_seeds, seeds, rec, st);
         case 16: return launch_points<16>(h, n, T, mu, xi, seed_mode, n_seeds, seeds, rec, st);
-        default: return launch_points<32>(h, n, T, mu, xi, seed_mode, n_seeds, seeds, rec, st);
+        default:
+            if (h->schedule == 1) return launch_points_ws(h, n, T, mu, xi, seed_mode, n_seeds, seeds, rec, st);
+            return launch_points<32>(h, n, T, mu, xi, seed_mode, n_seeds, seeds, rec, st);
     }
 }
 int dispatch_lines(pnjl_handle* h, long long n_lines, const double* muq, const double* xi, const int* tidx, int n_T,
@@ -938,6 +1064,7 @@ void pnjl_default_config(pnjl_config* c) {
     c->lanes_per_solve = 0;
     c->predict_tol = 1e-4;
     c->isospin_symmetric = 1;
+    c->schedule = 0;
 }
 
 int pnjl_gauleg(double a, double b, int32_t n, double* nodes, double* weights) {
@@ -1023,12 +1150,13 @@ int pnjl_create(const pnjl_config* c, pnjl_handle** out) {
         dc.lockstep = el ? atoi(el) : (h->G == 32 ? 1 : 0);   // 0 off, 1 align loop entry, 3 align entry and exit
         h->block_threads = eb ? atoi(eb) : (h->G == 32 ? 512 : 128);
         if (h->block_threads < 32 || h->block_threads > 512 || (h->block_threads & 31)) h->block_threads = 128;
+        // internal numbering: 1 = warp-specialised, 0 = one warp per line; PNJL_SCHEDULE overrides for experiments
         const char* es = getenv("PNJL_SCHEDULE");
-        h->schedule = es ? atoi(es) : 1;
+        h->schedule = es ? atoi(es) : (c->schedule == 1 ? 0 : 1);
         if (getenv("PNJL_WS_WORKERS")) h->ws_workers = atoi(getenv("PNJL_WS_WORKERS"));
         if (getenv("PNJL_WS_CTRL")) h->ws_ctrl_warps = atoi(getenv("PNJL_WS_CTRL"));
         if (getenv("PNJL_WS_SPW")) h->ws_spw = atoi(getenv("PNJL_WS_SPW"));
-        if (h->ws_spw < 1 || h->ws_spw > kWsMaxSpw) h->ws_spw = 2;
+        if (h->ws_spw < 1 || h->ws_spw > 8) h->ws_spw = 4;
         if (h->ws_workers < 1 || h->ws_workers > 15) h->ws_workers = 15;
         if (h->ws_ctrl_warps < 1 || h->ws_workers + h->ws_ctrl_warps > 16) h->ws_ctrl_warps = 16 - h->ws_workers;
     }
@@ -1076,8 +1204,10 @@ void pnjl_destroy(pnjl_handle* h) {
         cudaDeviceSynchronize();
         cudaMemcpy(d, h->host_cfg.dbg, sizeof(d), cudaMemcpyDeviceToHost);
         if (d[2])
-            fprintf(stderr, "[phases] passes %llu: loop %.0f cyc/pass; barrier wait %.0f cyc/pass; scalar phase %.0f cyc/pass\n", d[2],
-                    (double)d[0] / d[2], (double)d[1] / d[2], (double)d[3] / d[2]);
+            fprintf(stderr, "[phases] passes %llu: loop %.0f cyc/pass; barrier wait %.0f cyc/pass; scalar/idle phase %.0f cyc/pass; "
+                            "controller: %llu requests, scalar %.0f cyc/request, wait %.0f cyc/request\n", d[2],
+                    (double)d[0] / d[2], (double)d[1] / d[2], (double)d[3] / d[2], d[5], d[5] ? (double)d[4] / d[5] : 0.0,
+                    d[5] ? (double)d[6] / d[5] : 0.0);
         cudaFree(h->host_cfg.dbg);
     }
 #endif

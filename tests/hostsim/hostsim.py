@@ -37,7 +37,7 @@ class HostSim:
             xtol=1e-9, ftol=1e-9, residual_norm_max=1e-6, phi_tol=1e-8, max_iter=max_iter,
             tr_fallback=int(tr_fallback), auto_multiseed_fallback=int(auto_multiseed_fallback),
             omega_tie_rel=omega_tie_rel, device=-1, lanes_per_solve=0, predict_tol=predict_tol,
-            isospin_symmetric=int(isospin_symmetric))
+            isospin_symmetric=int(isospin_symmetric), schedule=0)
 
     def fj(self, x, T, mu, xi):
         x = _abi.as_f64(x)

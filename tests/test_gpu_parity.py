@@ -269,3 +269,28 @@ def test_isospin_fast_path_equals_three_flavour_path():
         scale = np.maximum(np.abs(b[:, q]), 1e-3 if q in (3, 4) else 1e-300)
         assert (np.abs(a[:, q] - b[:, q]) / scale).max() <= 1e-10
     assert (a[:, 0] == a[:, 1]).all() and (a[:, 5] == a[:, 6]).all()      # phi_u == phi_d, M_u == M_d exactly
+
+
+@pytest.mark.parametrize("schedule,parts", [(0, 1), (0, 2), (0, 4), (1, 1)])
+def test_kernel_organisations_agree(schedule, parts, monkeypatch):
+    """Warp-specialised kernel (passes whole or split over 2/4 workers) and the one-warp-per-line kernel against the
+    oracle on lines and on MultiSeed points at 64x16 nodes: same converged flags, ≤ 1e-9 on the state."""
+    monkeypatch.setenv("PNJL_WS_PARTS", str(parts))
+    o = Oracle(p_num=64, t_num=16, max_iter=40)
+    tables, index = load_phase_tables(os.path.join(GOLDEN, "boundary.csv"), os.path.join(GOLDEN, "cep.csv"), [0.0, 0.2])
+    e = engine(p_num=64, t_num=16, max_iter=40, schedule=schedule, nodes=(o.p_nodes, o.p_w, o.c_nodes, o.c_w))
+    e.set_boundaries(tables)
+    T = np.linspace(60, 280, 12)
+    muq = np.array([0.0, 120.0, 300.0, 335.0, 350.0, 400.0, 310.0, 345.0, 20.0, 250.0])
+    xi = np.array([0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.2, 0.2, 0.2, -0.4])
+    tidx = np.array([index.get(x, -1) for x in xi], dtype=np.int32)
+    res = o.scan_lines(muq, xi, T, tables, tidx)
+    rec = e.scan_lines(muq, xi, T, tidx)
+    assert_state_parity(rec, res, label="org-lines")
+    rng = np.random.default_rng(11)
+    n = 40
+    Tp, mup, xip = rng.uniform(40, 350, n) / HBARC, rng.uniform(0, 420, n) / HBARC, rng.uniform(-0.6, 0.8, n)
+    resp = o.solve_points(Tp, mup, xip, "multi")
+    recp = e.solve_points(Tp, mup, xip, A.SEED_MULTI)
+    assert_state_parity(recp, resp, label="org-points", max_wander=2)
+    assert e.stats()["lanes_per_solve"] == (32 * parts if schedule == 0 else 32)
