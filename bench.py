@@ -11,9 +11,12 @@ A "step" is one full pass of the hot path over the workload grid:
   cfg4: 2048x2048 window near the CEP (T 100..160, mu_q 260..330, xi=0), 64x16.
   cfg3: 256x256x8 independent points, MultiSeed at every point, 64x16.
   cfg2: 128x128 isotropic scan, 12x6 nodes (the script's defaults).
-With N GPUs the SAME grid is split by contiguous mu-slabs ("strong" scaling: the config is a fixed grid at
-1/2/4/8 GPUs in BASELINE.json); each rank runs its slab, rank 0 gathers the records over NCCL (inside the timed
-region), `value` = all converged points / max-over-ranks device time.
+With N GPUs the grid is split by contiguous mu-slabs; each rank runs its slab with no exchange, rank 0 gathers the
+records over NCCL (inside the timed region), `value` = all converged points / max-over-ranks device time.
+  --scaling weak   (default, the contract's rule for a path that partitions): every GPU carries one full workload
+                   slab, i.e. the mu axis is refined to N x n_mu points over the same range; N = 1 is exactly the
+                   BASELINE config.
+  --scaling strong the SAME grid at every N (BASELINE's "1024x1024x8 at 1/2/4/8 B200"): n_mu / N mu-values per GPU.
 """
 import argparse
 import json
@@ -189,7 +192,7 @@ def run_reference(args):
     val = tot_pts / tot_s
     out = {"impl": "reference", "metric": "converged PNJL gap points/sec", "value": val, "unit": "points/s",
            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps,
-           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": w, "description": DESCR[w]},
            "cpu_baseline": {"value": val, "unit": "points/s", "cores": last["threads"], "kind": "port",
                             "sample": last["sample"],
@@ -214,6 +217,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--no-flush", action="store_true", help="skip the L2 flush between steps (ncu traffic captures only)")
     ap.add_argument("--n-mu", type=int, default=0, help="override the mu density (profiling runs only; recorded in config)")
     ap.add_argument("--n-t", type=int, default=0, help="override the T density (profiling runs only; recorded in config)")
     args = ap.parse_args()
@@ -246,6 +251,10 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     w = args.workload
+    if args.scaling == "weak" and world > 1:
+        k_, xs_, nm_, mr_, nt_, tr_, pp_, tt_ = WORKLOADS[w]
+        WORKLOADS[w] = (k_, xs_, nm_ * world, mr_, nt_, tr_, pp_, tt_)
+        DESCR[w] += " [weak scaling: mu axis refined to %d points, one %d-mu slab per GPU]" % (nm_ * world, nm_)
     kind, xis, n_mu, _, n_T, _, p, t = WORKLOADS[w]
     xis, mus, T, p, t = build_lines(w)
     n_nodes = p * t
@@ -312,7 +321,8 @@ def main():
         sampler.start()
     step_ms, kern_ms = [], []
     for _ in range(args.steps):
-        flush.fill_(1.0)                               # L2 flush between timed iterations (not timed)
+        if not args.no_flush:
+            flush.fill_(1.0)                           # L2 flush between timed iterations (not timed)
         barrier()
         e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         e0.record()
@@ -395,15 +405,16 @@ def main():
         if os.path.exists(pj):
             try:
                 prof = json.load(open(pj))
-                traffic = prof.get("dram_bytes_per_launch")
-                extra = {k: prof[k] for k in ("fp64_pipe_util_pct", "profile") if k in prof}
+                if prof.get("dram_bytes_per_point") is not None:
+                    traffic = prof["dram_bytes_per_point"] * float(n_total) / world   # per launch (one per GPU)
+                extra = {k: prof[k] for k in ("fp64_pipe_util_pct", "issue_active_pct", "profile") if k in prof}
             except Exception:
                 pass
         achieved = fl * args.steps / (kernel_ms * 1e-3) / 1e12
         out = {
             "metric": "converged PNJL gap points/sec", "value": value, "unit": "points/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": w, "description": DESCR[w], "points": int(n_total), "converged": int(n_conv),
                        "nodes": "%dx%d" % (p, t), "max_iter": MAX_ITER, "sharding": "contiguous mu-slabs, %d rank(s)" % world,
                        "l2": "512 MB buffer written between timed steps (L2 flush); inputs are O(100 KB), outputs 256 B/point",

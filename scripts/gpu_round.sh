@@ -6,6 +6,6 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv
 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_cfg5.json 2> gpurun_out/bench_cfg5.err; tail -c 3000 gpurun_out/bench_cfg5.json; tail -5 gpurun_out/bench_cfg5.err
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --n-mu 1024 --n-t 96 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_scan_lines -s 3 -c 1 -f -o gpurun_out/prof python bench.py --steps 1 --warmup 3 --n-mu 1024 --n-t 96 --no-cpu-baseline --no-e2e > gpurun_out/ncu_full.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --n-mu 1024 --n-t 128 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_solve_ws -s 3 -c 1 -f -o gpurun_out/prof python bench.py --steps 1 --warmup 3 --n-mu 1024 --n-t 128 --no-cpu-baseline --no-e2e --no-flush > gpurun_out/ncu_full.log 2>&1
 ls -la gpurun_out

@@ -48,6 +48,21 @@ def main():
                     pass
         summ.append(rec)
     json.dump({"report": rep, "note": note, "launches": summ}, open(out + ".json", "w"), indent=1)
+    if len(sys.argv) > 5:
+        # top_kernel.json for bench.py: python summarize_ncu.py rep out note <points in the profiled launch> <top_kernel.json>
+        pts = float(sys.argv[4])
+        m = summ[0]["metrics"]
+
+        def val(k):
+            v, u = m[k]
+            v = float(v.replace(",", ""))
+            return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}.get(u, 1.0)
+        top = {"profile": out + ".md", "kernel": summ[0]["kernel"][:60],
+               "dram_bytes_per_point": (val("dram__bytes_read.sum") + val("dram__bytes_write.sum")) / pts,
+               "fp64_pipe_util_pct": float(m["sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed"][0]),
+               "issue_active_pct": float(m["smsp__issue_active.avg.pct_of_peak_sustained_active"][0]),
+               "points_in_profiled_launch": pts}
+        json.dump(top, open(sys.argv[5], "w"), indent=1)
     with open(out + ".md", "w") as f:
         f.write("# ncu summary: %s\n\n%s\n\n" % (rep, note))
         for rec in summ:
