@@ -91,12 +91,12 @@ __constant__ double kExpR[4] = {1.4426950408889634, 6755399441055744.0, -6.93147
 // ------------------------------------------------------------------------------------------------
 PNJL_HD double fast_rcp(double x) {
 #if defined(__CUDA_ARCH__)
+    // MUFU seed (rel. error < 2^-22) + one third-order step: y (1 + e + e^2), e = 1 - x y  ->  error ~ e^3
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-x, y, 1.0);
-    return fma(y, e, y);
+    const double e = fma(-x, y, 1.0);
+    const double t = fma(e, e, e);
+    return fma(y, t, y);
 #else
     return 1.0 / x;
 #endif
@@ -104,13 +104,12 @@ PNJL_HD double fast_rcp(double x) {
 
 PNJL_HD double fast_rsqrt(double x) {
 #if defined(__CUDA_ARCH__)
+    // MUFU seed + one third-order step: y (1 + e/2 + 3 e^2/8), e = 1 - x y^2
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    const double h = 0.5 * x;
-    double e = fma(-(h * y), y, 0.5);
-    y = fma(y, e, y);
-    e = fma(-(h * y), y, 0.5);
-    return fma(y, e, y);
+    const double e = fma(-(x * y), y, 1.0);
+    const double p = fma(0.375, e, 0.5);
+    return fma(y * e, p, y);
 #else
     return 1.0 / sqrt(x);
 #endif
@@ -405,18 +404,19 @@ PNJL_HD void ft_node_fast(const FastCtx& fc, double mu, double M2, double k2, do
 template <int W>
 PNJL_HD void v_rsqrt(const double x[W], double y[W]) {
 #if defined(__CUDA_ARCH__)
-    double h[W], e[W];
+    double e[W], p[W], t[W];
 #pragma unroll
     for (int j = 0; j < W; ++j) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y[j]) : "d"(x[j]));
 #pragma unroll
-    for (int j = 0; j < W; ++j) h[j] = 0.5 * x[j];
+    for (int j = 0; j < W; ++j) t[j] = x[j] * y[j];
 #pragma unroll
-    for (int it = 0; it < 2; ++it) {
+    for (int j = 0; j < W; ++j) e[j] = fma(-t[j], y[j], 1.0);
 #pragma unroll
-        for (int j = 0; j < W; ++j) e[j] = fma(-(h[j] * y[j]), y[j], 0.5);
+    for (int j = 0; j < W; ++j) p[j] = fma(0.375, e[j], 0.5);
 #pragma unroll
-        for (int j = 0; j < W; ++j) y[j] = fma(y[j], e[j], y[j]);
-    }
+    for (int j = 0; j < W; ++j) t[j] = y[j] * e[j];
+#pragma unroll
+    for (int j = 0; j < W; ++j) y[j] = fma(t[j], p[j], y[j]);
 #else
     for (int j = 0; j < W; ++j) y[j] = 1.0 / sqrt(x[j]);
 #endif
@@ -429,12 +429,11 @@ PNJL_HD void v_rcp(const double x[W], double y[W]) {
 #pragma unroll
     for (int j = 0; j < W; ++j) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y[j]) : "d"(x[j]));
 #pragma unroll
-    for (int it = 0; it < 2; ++it) {
+    for (int j = 0; j < W; ++j) e[j] = fma(-x[j], y[j], 1.0);
 #pragma unroll
-        for (int j = 0; j < W; ++j) e[j] = fma(-x[j], y[j], 1.0);
+    for (int j = 0; j < W; ++j) e[j] = fma(e[j], e[j], e[j]);
 #pragma unroll
-        for (int j = 0; j < W; ++j) y[j] = fma(y[j], e[j], y[j]);
-    }
+    for (int j = 0; j < W; ++j) y[j] = fma(y[j], e[j], y[j]);
 #else
     for (int j = 0; j < W; ++j) y[j] = 1.0 / x[j];
 #endif
