@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define PNJL_ABI_VERSION 4
+#define PNJL_ABI_VERSION 5
 
 /* ---- result record layout (doubles) --------------------------------------------------------- */
 #define PNJL_REC_DOUBLES 32
@@ -68,6 +68,11 @@ extern "C" {
 #define PNJL_ST_PHASE_SWITCH 128     /* PhaseAwareContinuitySeed re-seeded at a hadron<->quark flip  SeedStrategies.jl:818-826 */
 #define PNJL_ST_NONFINITE 256        /* seed residual not finite (NLsolve IsFiniteException) */
 #define PNJL_ST_ALL_SEEDS_FAILED 512 /* solve_multi found no converged candidate */
+#define PNJL_ST_PROMOTED 1024        /* TmuScan: residual <= 1e-4 force-marked converged   src/pnjl/scans/TmuScan.jl:422-458 */
+#define PNJL_ST_REFINED 2048         /* TmuScan: re-solved from a near-converged state      TmuScan.jl:391-408 */
+#define PNJL_ST_CAND_SHIFT 12        /* bits 12..13: index of the TmuScan seed candidate that succeeded   TmuScan.jl:269-300 */
+#define PNJL_ST_CAND_MASK 0x3000
+#define PNJL_ST_NO_RESULT 16384      /* TmuScan: every candidate failed (the reference writes an all-NaN row) */
 
 /* ---- errors --------------------------------------------------------------------------------- */
 #define PNJL_OK 0
@@ -155,6 +160,16 @@ int pnjl_scan_lines_host(pnjl_handle* h, int64_t n_lines, const double* muq_MeV,
 int pnjl_scan_lines_device(pnjl_handle* h, int64_t n_lines, const double* d_muq_MeV, const double* d_xi,
                            const int32_t* d_table_idx, int32_t n_T, const double* d_T_MeV, double* d_records,
                            void* stream);
+
+/* T-mu scan with TmuScan.run_tmu_scan semantics (src/pnjl/scans/TmuScan.jl:120-234): line l = (xi[l], T_MeV[l]) marches
+ * mu_MeV[0..n_mu) in the given order with a fresh PhaseAwareContinuitySeed tracker per line, the four-candidate seed
+ * list, solve() with its automatic fallbacks per candidate, the 1e-4 acceptance / refine / force-promote rules.
+ * records: [n_lines][n_mu][32]; rows without any successful candidate carry PNJL_ST_NO_RESULT and NaNs. */
+int pnjl_tmu_scan_host(pnjl_handle* h, int64_t n_lines, const double* T_MeV, const double* xi, const int32_t* table_idx,
+                       int32_t n_mu, const double* mu_MeV, double* records);
+int pnjl_tmu_scan_device(pnjl_handle* h, int64_t n_lines, const double* d_T_MeV, const double* d_xi,
+                         const int32_t* d_table_idx, int32_t n_mu, const double* d_mu_MeV, double* d_records,
+                         void* stream);
 
 /* Single Omega-gradient/Jacobian evaluation at given states (test hook for per-iterate parity):
  * FJ: [n][30] = F[5] then J[5][5] row-major. */

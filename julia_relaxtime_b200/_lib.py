@@ -74,6 +74,9 @@ def load():
     L.pnjl_scan_lines_host.argtypes = [H, C.c_int64, dp, dp, ip, C.c_int32, dp, dp]
     L.pnjl_scan_lines_device.argtypes = [H, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                          C.c_void_p, C.c_void_p]
+    L.pnjl_tmu_scan_host.argtypes = [H, C.c_int64, dp, dp, ip, C.c_int32, dp, dp]
+    L.pnjl_tmu_scan_device.argtypes = [H, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                       C.c_void_p, C.c_void_p]
     L.pnjl_eval_fj_host.argtypes = [H, C.c_int64, dp, dp, dp, dp, dp]
     L.pnjl_selftest_math.argtypes = [H, C.c_int64, dp, C.c_int32, dp]
     L.pnjl_get_stats.argtypes = [H, C.POINTER(_abi.PnjlStats)]
@@ -87,7 +90,7 @@ def load():
 EXPORTED_SYMBOLS = [
     "pnjl_default_config", "pnjl_abi_version", "pnjl_last_error", "pnjl_create", "pnjl_destroy", "pnjl_gauleg",
     "pnjl_solve_points_host", "pnjl_solve_points_device", "pnjl_set_boundaries", "pnjl_scan_lines_host",
-    "pnjl_scan_lines_device", "pnjl_eval_fj_host", "pnjl_selftest_math", "pnjl_get_stats", "pnjl_measure_fp64_peak"]
+    "pnjl_scan_lines_device", "pnjl_tmu_scan_host", "pnjl_tmu_scan_device", "pnjl_eval_fj_host", "pnjl_selftest_math", "pnjl_get_stats", "pnjl_measure_fp64_peak"]
 
 
 def gauleg(a, b, n):
@@ -188,6 +191,21 @@ class Engine:
         self._check(self.L.pnjl_scan_lines_host(self.h, n_lines, _abi.dptr(muq_MeV), _abi.dptr(xi), ti,
                                                 int(T_MeV.size), _abi.dptr(T_MeV), _abi.dptr(rec)),
                     "pnjl_scan_lines_host")
+        return rec
+
+    def tmu_scan(self, T_MeV, xi, mu_MeV, table_idx=None, out=None):
+        """TmuScan semantics: line l = (xi[l], T_MeV[l]) marches mu_MeV; records [n_lines][n_mu][32]."""
+        T_MeV = _abi.as_f64(T_MeV)
+        n_lines = T_MeV.size
+        xi = _abi.as_f64(xi, n_lines)
+        mu_MeV = _abi.as_f64(mu_MeV)
+        ti = None
+        if table_idx is not None:
+            table_idx = np.ascontiguousarray(table_idx, dtype=np.int32)
+            ti = _abi.iptr(table_idx)
+        rec = out if out is not None else np.empty((n_lines, mu_MeV.size, _abi.REC_DOUBLES))
+        self._check(self.L.pnjl_tmu_scan_host(self.h, n_lines, _abi.dptr(T_MeV), _abi.dptr(xi), ti, int(mu_MeV.size),
+                                              _abi.dptr(mu_MeV), _abi.dptr(rec)), "pnjl_tmu_scan_host")
         return rec
 
     def eval_fj(self, T_fm, mu_fm, xi, x):

@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(512, 1) k_scan_lines(const DeviceConfig* __res
                                                     long long n_lines, const double* __restrict__ muq_MeV,
                                                     const double* __restrict__ xi, const int* __restrict__ table_idx,
                                                     int n_T, const double* __restrict__ T_MeV, double* __restrict__ records,
-                                                    unsigned long long* counter) {
+                                                    unsigned long long* counter, int mode) {
     extern __shared__ double s_mesh[];
     __shared__ int s_done;
     stage_mesh<G>(g_mesh, cfg->n_nodes, s_mesh, &s_done);
@@ -310,7 +310,9 @@ __global__ void __launch_bounds__(512, 1) k_scan_lines(const DeviceConfig* __res
         const long long l = next_task<G>(counter, ev);
         if (l >= n_lines) break;
         LineSink<G> sink{&ev, records + (long long)PNJL_REC_DOUBLES * n_T * l, xi[l]};
-        scan_line(sv, &cfg->pt, table_idx ? table_idx[l] : -1, muq_MeV[l], xi[l], n_T, T_MeV, sink);
+        // mode 0: (xi, mu) line marching T (run_gap_transport_scan.jl); mode 1: (xi, T) line marching mu (TmuScan.jl)
+        if (mode == 0) scan_line(sv, &cfg->pt, table_idx ? table_idx[l] : -1, muq_MeV[l], xi[l], n_T, T_MeV, sink);
+        else scan_tmu_line(sv, &cfg->pt, table_idx ? table_idx[l] : -1, muq_MeV[l], xi[l], n_T, T_MeV, sink);
     }
     ev.drain();
 }
@@ -352,7 +354,7 @@ struct WsGroup {
 
 // What the controller lanes work on: whole continuity lines or independent points.
 struct WsTask {
-    int mode;                // 0: lines (scan_line), 1: points (solve / solve_multi)
+    int mode;                // 0: lines (scan_line), 1: points (solve / solve_multi), 2: TmuScan lines (scan_tmu_line)
     long long n_tasks;
     long long perm_mult;     // tasks are handed out in the order (k * perm_mult) mod n_tasks (coprime multiplier): neighbouring
                              // lines cost alike, so a contiguous hand-out loads the SMs unevenly (measured 1.12 vs 1.02 max/mean)
@@ -678,6 +680,11 @@ __global__ void __launch_bounds__(512, 1) k_solve_ws(const DeviceConfig* __restr
             CtrlSink sink{task.records + (long long)PNJL_REC_DOUBLES * task.n_T * t, task.xi[t]};
             scan_line(sv, &cfg->pt, task.table_idx ? task.table_idx[t] : -1, task.muq_MeV[t], task.xi[t], task.n_T, task.T_MeV,
                       sink);
+        } else if (task.mode == 2) {
+            // here muq_MeV holds the line's T_MeV and T_MeV the shared mu grid
+            CtrlSink sink{task.records + (long long)PNJL_REC_DOUBLES * task.n_T * t, task.xi[t]};
+            scan_tmu_line(sv, &cfg->pt, task.table_idx ? task.table_idx[t] : -1, task.muq_MeV[t], task.xi[t], task.n_T,
+                          task.T_MeV, sink);
         } else {
             const double T = task.T_fm[t], mu = task.mu_fm[t], x_i = task.xi[t];
             sv.set_point(T, mu, x_i);
@@ -966,10 +973,10 @@ int launch_ws(pnjl_handle* h, const WsTask& task_in, cudaStream_t st) {
 }
 
 int launch_lines_ws(pnjl_handle* h, long long n_lines, const double* muq, const double* xi, const int* tidx, int n_T,
-                    const double* T, double* rec, cudaStream_t st) {
+                    const double* T, double* rec, cudaStream_t st, int mode) {
     WsTask t;
     std::memset(&t, 0, sizeof(t));
-    t.mode = 0; t.n_tasks = n_lines; t.muq_MeV = muq; t.xi = xi; t.table_idx = tidx; t.n_T = n_T; t.T_MeV = T; t.records = rec;
+    t.mode = mode == 0 ? 0 : 2; t.n_tasks = n_lines; t.muq_MeV = muq; t.xi = xi; t.table_idx = tidx; t.n_T = n_T; t.T_MeV = T; t.records = rec;
     return launch_ws(h, t, st);
 }
 
@@ -984,13 +991,13 @@ int launch_points_ws(pnjl_handle* h, long long n, const double* T, const double*
 
 template <int G>
 int launch_lines(pnjl_handle* h, long long n_lines, const double* muq, const double* xi, const int* tidx, int n_T,
-                 const double* T, double* rec, cudaStream_t st) {
+                 const double* T, double* rec, cudaStream_t st, int mode) {
     const size_t smem = sizeof(double) * 3 * h->n_nodes;
     int blocks, threads;
     int rc = launch_geometry(h, k_scan_lines<G>, smem, n_lines, G, &blocks, &threads);
     if (rc) return rc;
     CUDA_TRY(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned long long), st));
-    k_scan_lines<G><<<blocks, threads, smem, st>>>(h->d_cfg, h->d_mesh, n_lines, muq, xi, tidx, n_T, T, rec, h->d_counter);
+    k_scan_lines<G><<<blocks, threads, smem, st>>>(h->d_cfg, h->d_mesh, n_lines, muq, xi, tidx, n_T, T, rec, h->d_counter, mode);
     CUDA_TRY(cudaGetLastError());
     h->stats.kernel_launches += 1;
     return PNJL_OK;
@@ -1030,13 +1037,13 @@ int dispatch_points(pnjl_handle* h, long long n, const double* T, const double* 
     }
 }
 int dispatch_lines(pnjl_handle* h, long long n_lines, const double* muq, const double* xi, const int* tidx, int n_T,
-                   const double* T, double* rec, cudaStream_t st) {
+                   const double* T, double* rec, cudaStream_t st, int mode = 0) {
     switch (h->G) {
-        case 8: return launch_lines<8>(h, n_lines, muq, xi, tidx, n_T, T, rec, st);
-        case 16: return launch_lines<16>(h, n_lines, muq, xi, tidx, n_T, T, rec, st);
+        case 8: return launch_lines<8>(h, n_lines, muq, xi, tidx, n_T, T, rec, st, mode);
+        case 16: return launch_lines<16>(h, n_lines, muq, xi, tidx, n_T, T, rec, st, mode);
         default:
-            if (h->schedule == 1) return launch_lines_ws(h, n_lines, muq, xi, tidx, n_T, T, rec, st);
-            return launch_lines<32>(h, n_lines, muq, xi, tidx, n_T, T, rec, st);
+            if (h->schedule == 1) return launch_lines_ws(h, n_lines, muq, xi, tidx, n_T, T, rec, st, mode);
+            return launch_lines<32>(h, n_lines, muq, xi, tidx, n_T, T, rec, st, mode);
     }
 }
 int dispatch_fj(pnjl_handle* h, long long n, const double* T, const double* mu, const double* xi, const double* x,
@@ -1344,6 +1351,53 @@ int pnjl_scan_lines_host(pnjl_handle* h, int64_t n_lines, const double* muq, con
     CUDA_TRY(cudaEventRecord(h->ev0, st));
     int rc = pnjl_scan_lines_device(h, n_lines, (const double*)h->in_mu.p, (const double*)h->in_xi.p, d_idx, n_T,
                                     (const double*)h->in_T.p, (double*)h->out_rec.p, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(h->ev1, st));
+    CUDA_TRY(cudaMemcpyAsync(records, h->out_rec.p, nrec, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->stats.kernel_ms = ms;
+    return PNJL_OK;
+}
+
+int pnjl_tmu_scan_device(pnjl_handle* h, int64_t n_lines, const double* d_T, const double* d_xi, const int32_t* d_tidx,
+                         int32_t n_mu, const double* d_mu, double* d_records, void* stream) {
+    if (!h) return fail(PNJL_ERR_ARG, "null handle");
+    if (n_lines < 0 || n_mu < 0) return fail(PNJL_ERR_ARG, "negative size");
+    h->stats.kernel_launches = 0;
+    if (n_lines == 0 || n_mu == 0) return PNJL_OK;
+    if (!d_T || !d_xi || !d_mu || !d_records) return fail(PNJL_ERR_ARG, "null buffer");
+    DeviceGuard guard(h->device);
+    return dispatch_lines(h, n_lines, d_T, d_xi, d_tidx, n_mu, d_mu, d_records, (cudaStream_t)stream, 1);
+}
+
+int pnjl_tmu_scan_host(pnjl_handle* h, int64_t n_lines, const double* T_MeV, const double* xi, const int32_t* tidx,
+                       int32_t n_mu, const double* mu_MeV, double* records) {
+    if (!h) return fail(PNJL_ERR_ARG, "null handle");
+    if (n_lines < 0 || n_mu < 0) return fail(PNJL_ERR_ARG, "negative size");
+    if (n_lines == 0 || n_mu == 0) { h->stats.kernel_launches = 0; return PNJL_OK; }
+    if (!T_MeV || !xi || !mu_MeV || !records) return fail(PNJL_ERR_ARG, "null buffer");
+    DeviceGuard guard(h->device);
+    const size_t nl = sizeof(double) * (size_t)n_lines;
+    const size_t nrec = sizeof(double) * (size_t)n_lines * n_mu * PNJL_REC_DOUBLES;
+    CUDA_TRY(h->in_mu.reserve(nl));
+    CUDA_TRY(h->in_xi.reserve(nl));
+    CUDA_TRY(h->in_T.reserve(sizeof(double) * n_mu));
+    CUDA_TRY(h->in_idx.reserve(sizeof(int32_t) * (size_t)n_lines));
+    CUDA_TRY(h->out_rec.reserve(nrec));
+    cudaStream_t st = h->stream;
+    CUDA_TRY(cudaMemcpyAsync(h->in_mu.p, T_MeV, nl, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(h->in_xi.p, xi, nl, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(h->in_T.p, mu_MeV, sizeof(double) * n_mu, cudaMemcpyHostToDevice, st));
+    const int32_t* d_idx = nullptr;
+    if (tidx) {
+        CUDA_TRY(cudaMemcpyAsync(h->in_idx.p, tidx, sizeof(int32_t) * (size_t)n_lines, cudaMemcpyHostToDevice, st));
+        d_idx = (const int32_t*)h->in_idx.p;
+    }
+    CUDA_TRY(cudaEventRecord(h->ev0, st));
+    int rc = pnjl_tmu_scan_device(h, n_lines, (const double*)h->in_mu.p, (const double*)h->in_xi.p, d_idx, n_mu,
+                                  (const double*)h->in_T.p, (double*)h->out_rec.p, st);
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(h->ev1, st));
     CUDA_TRY(cudaMemcpyAsync(records, h->out_rec.p, nrec, cudaMemcpyDeviceToHost, st));

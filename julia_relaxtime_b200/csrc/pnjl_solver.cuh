@@ -566,4 +566,78 @@ PNJL_HD_NOINL void scan_line(Solver<Ev>& sv, const PhaseTables* pt, int ti, doub
     }
 }
 
+// One (xi, T) line of TmuScan.run_tmu_scan (src/pnjl/scans/TmuScan.jl:120-234): march mu in the given order.
+// The tracker starts empty on every line (:169-172).  Seed candidates per point (:269-300): the phase-aware seed,
+// the continuation cache (last success on this line), then the quark/hadron defaults ordered by
+// (T > 150 MeV || mu > 300 MeV).  Every candidate runs through solve() with its automatic fallbacks (:349-368); a
+// candidate succeeds when converged or when its residual is <= 1e-4 (:411-419); a near-converged success is re-solved
+// from its own state once (:391-408) and otherwise force-marked converged (:422-458).  Rows where every candidate
+// failed get PNJL_ST_NO_RESULT and NaNs (the reference writes an all-NaN CSV row).
+template <class Ev, class Sink>
+PNJL_HD_NOINL void scan_tmu_line(Solver<Ev>& sv, const PhaseTables* pt, int ti, double T_MeV, double xi, int n_mu,
+                                 const double* mu_MeV, Sink& sink) {
+    Tracker tk;
+    tk.has_prev = false;
+    tk.prev_phase = PH_UNKNOWN;
+    bool have_cache = false;
+    double cache[5];
+    const double T_fm = T_MeV / sv.m.hbarc;
+    const double kAcceptable = 1e-4;
+    PointRes r, a;
+    for (int im = 0; im < n_mu; ++im) {
+        const double mu_fm = mu_MeV[im] / sv.m.hbarc;
+        sv.set_point(T_fm, mu_fm, xi);
+        sv.n_fj = 0;
+        sv.n_th = 0;
+        sv.n_ft = 0;
+        const bool quark_first = (T_MeV > 150.0) || (mu_MeV[im] > 300.0);
+        bool success = false;
+        for (int ci = 0; ci < 4 && !success; ++ci) {
+            double x0[5];
+            if (ci == 0) sv.tracker_seed(pt, ti, tk, x0);
+            else if (ci == 1) { if (!have_cache) continue; copy5(x0, cache); }
+            else seed_const(((ci == 2) == quark_first) ? 1 : 0, x0);
+            sv.solve_with_fallback(x0, a);
+            if (a.status & PNJL_ST_NONFINITE) continue;
+            const bool ok = a.converged || (finite_d(a.res) && a.res <= kAcceptable);
+            if (!ok) continue;
+            int extra = 0;
+            if (!a.converged) {
+                double xs[5];
+                copy5(xs, a.x);
+                sv.solve_with_fallback(xs, r);
+                if (!(r.status & PNJL_ST_NONFINITE) && r.converged) extra = PNJL_ST_REFINED;
+                else r = a;
+            } else {
+                r = a;
+            }
+            r.status |= extra;
+            if (!r.converged) {
+                r.converged = true;
+                r.status |= PNJL_ST_PROMOTED | PNJL_ST_CONVERGED;
+            }
+            r.status |= (ci << PNJL_ST_CAND_SHIFT);
+            success = true;
+        }
+        if (!success) {
+#pragma unroll
+            for (int q = 0; q < 5; ++q) r.x[q] = NAN;
+            sv.nan_thermo(r);
+#pragma unroll
+            for (int q = 0; q < 3; ++q) r.th.M[q] = NAN;
+            r.res = NAN;
+            r.it = -1;
+            r.converged = false;
+            r.status = PNJL_ST_NO_RESULT;
+        } else {
+            copy5(tk.prev, r.x);
+            tk.has_prev = true;
+            tk.prev_phase = current_phase(pt, ti, T_MeV, mu_MeV[im]);
+            copy5(cache, r.x);
+            have_cache = true;
+        }
+        sink(im, r, T_fm, mu_fm, sv.n_fj, sv.n_th, sv.n_ft);
+    }
+}
+
 }  // namespace pnjl

@@ -60,6 +60,7 @@ def _ip(a):
 
 ST_CONVERGED, ST_USED_TR, ST_TR_ATTEMPTED, ST_USED_MULTISEED = 1, 2, 4, 8
 ST_SEED_SHIFT, ST_PHASE_SWITCH, ST_NONFINITE, ST_ALL_SEEDS_FAILED = 4, 128, 256, 512
+ST_PROMOTED, ST_REFINED, ST_CAND_SHIFT, ST_NO_RESULT = 1024, 2048, 12, 16384
 
 
 class Result:
@@ -114,6 +115,9 @@ class Oracle:
         L.oracle_scan_lines.argtypes = [C.POINTER(Config), C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                         C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_double), C.c_int32,
                                         C.POINTER(Table), C.POINTER(Out)]
+        L.oracle_tmu_scan.argtypes = [C.POINTER(Config), C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                      C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_double), C.c_int32,
+                                      C.POINTER(Table), C.POINTER(Out)]
         L.oracle_gauleg.argtypes = [C.c_double, C.c_double, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.oracle_num_threads.restype = C.c_int32
 
@@ -215,6 +219,34 @@ class Oracle:
                                    _dp(T_MeV), len(tables), ctabs, C.byref(cs))
         out.n_lines, out.n_T = n_lines, T_MeV.size
         return out
+
+
+def _tmu_scan(self, T_MeV, xi, mu_MeV, tables=None, table_idx=None):
+    """TmuScan semantics: one line per (xi, T), marching mu_MeV in the given order."""
+    T_MeV = np.ascontiguousarray(T_MeV, dtype=np.float64)
+    n_lines = T_MeV.size
+    xi = np.ascontiguousarray(np.broadcast_to(np.atleast_1d(xi), (n_lines,)), dtype=np.float64)
+    mu_MeV = np.ascontiguousarray(mu_MeV, dtype=np.float64)
+    tables = tables or []
+    keep = []
+    ctabs = (Table * max(1, len(tables)))()
+    for i, (tt, mm, tcep) in enumerate(tables):
+        tt = np.ascontiguousarray(tt, dtype=np.float64)
+        mm = np.ascontiguousarray(mm, dtype=np.float64)
+        keep += [tt, mm]
+        ctabs[i] = Table(_dp(tt), _dp(mm), tt.size, tcep)
+    if table_idx is None:
+        table_idx = np.full(n_lines, -1, dtype=np.int32)
+    table_idx = np.ascontiguousarray(table_idx, dtype=np.int32)
+    out = Result(n_lines * mu_MeV.size)
+    cs = out.c_struct()
+    self.lib.oracle_tmu_scan(C.byref(self.cfg), n_lines, _dp(T_MeV), _dp(xi), _ip(table_idx), mu_MeV.size, _dp(mu_MeV),
+                             len(tables), ctabs, C.byref(cs))
+    out.n_lines, out.n_mu = n_lines, mu_MeV.size
+    return out
+
+
+Oracle.tmu_scan = _tmu_scan
 
 
 def load_phase_tables(boundary_csv, cep_csv, xis):

@@ -676,6 +676,10 @@ enum StatusBits : int32_t {
     ST_PHASE_SWITCH = 128, // PhaseAwareContinuitySeed re-seeded at a hadron<->quark flip
     ST_NONFINITE = 256,    // initial residual non-finite (IsFiniteException)
     ST_ALL_SEEDS_FAILED = 512,
+    ST_PROMOTED = 1024,     // TmuScan: residual <= 1e-4 force-marked converged (TmuScan.jl:428-458)
+    ST_REFINED = 2048,      // TmuScan: re-solved from a near-converged state (TmuScan.jl:391-408)
+    ST_CAND_SHIFT = 12,     // bits 12..13: index of the TmuScan seed candidate that succeeded
+    ST_NO_RESULT = 16384,   // TmuScan: every candidate failed (the CSV row is all NaN)
 };
 
 struct Candidate {
@@ -1212,6 +1216,104 @@ int32_t oracle_scan_lines(const oracle_config* c, int64_t n_lines, const double*
             }
             if (r.converged) tracker_update(tk, r.x, T_MeV[it], muq_MeV[l]);
             store(out, n, l * n_T + it, pb, r);
+        }
+    }
+    return 0;
+}
+
+// TmuScan.run_tmu_scan (src/pnjl/scans/TmuScan.jl:120-234): for each (xi, T) line march mu in the given order.
+// Tracker reset per line (:169-172); candidates (:269-300): phase-aware seed, continuation cache, then quark/hadron
+// defaults ordered by (T > 150 || mu > 300); every candidate goes through solve() with its automatic fallbacks
+// (:349-368); success = converged or residual <= 1e-4 (:411-419); refine (:391-408) and force-promote (:422-458).
+// Output index = line * n_mu + imu; rows where every candidate failed carry ST_NO_RESULT and NaNs.
+int32_t oracle_tmu_scan(const oracle_config* c, int64_t n_lines, const double* T_MeV, const double* xi,
+                        const int32_t* table_idx, int32_t n_mu, const double* mu_MeV, int32_t n_tables,
+                        const oracle_table* tables, const oracle_out* out) {
+    Consts k = consts_of(c);
+    Mesh m = mesh_of(c);
+    SolverOpts o = opts_of(c);
+    std::vector<PhaseTable> pts(n_tables + 1);
+    for (int t = 0; t < n_tables; ++t) {
+        pts[t].T.assign(tables[t].T_MeV, tables[t].T_MeV + tables[t].n);
+        pts[t].mu.assign(tables[t].mu_c_MeV, tables[t].mu_c_MeV + tables[t].n);
+        pts[t].T_CEP = tables[t].T_CEP;
+    }
+    const int64_t n = n_lines * (int64_t)n_mu;
+    const double kAcceptable = 1e-4;  // TmuScan.jl:60
+#ifdef _OPENMP
+    int nt = c->n_threads > 0 ? c->n_threads : omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nt)
+#endif
+    for (int64_t l = 0; l < n_lines; ++l) {
+        Tracker tk;
+        int ti = table_idx ? table_idx[l] : -1;
+        tk.table = (ti >= 0 && ti < n_tables) ? &pts[ti] : &pts[n_tables];
+        bool have_cache = false;
+        double cache[5];
+        const double T_fm = T_MeV[l] / k.hbarc;
+        for (int im = 0; im < n_mu; ++im) {
+            const double mu_fm = mu_MeV[im] / k.hbarc;
+            Problem pb{&k, &m, T_fm, mu_fm, xi[l]};
+            // candidate slots are numbered 0 phase-aware, 1 continuation cache, 2 and 3 the defaults, whether or not
+            // the cache slot is filled (the number is reported in the status word)
+            double cand[4][5];
+            bool have[4] = {true, have_cache, true, true};
+            tracker_get_seed(tk, T_fm, mu_fm, cand[0]);
+            if (have_cache) std::memcpy(cand[1], cache, 40);
+            if (T_MeV[l] > 150 || mu_MeV[im] > 300) {
+                std::memcpy(cand[2], HIGH_TEMP_SEED, 40);
+                std::memcpy(cand[3], HADRON_SEED, 40);
+            } else {
+                std::memcpy(cand[2], HADRON_SEED, 40);
+                std::memcpy(cand[3], HIGH_TEMP_SEED, 40);
+            }
+            PointResult r;
+            bool success = false;
+            int n_fj = 0;
+            for (int ci = 0; ci < 4 && !success; ++ci) {
+                if (!have[ci]) continue;
+                PointResult a = solve_with_fallback(pb, cand[ci], o);
+                n_fj += a.n_fj;
+                if (a.status & ST_NONFINITE) continue;   // IsFiniteException -> caught in _solve_point -> next candidate
+                bool ok = a.converged || (std::isfinite(a.residual_norm) && a.residual_norm <= kAcceptable);
+                if (!ok) continue;
+                if (!a.converged) {
+                    PointResult b = solve_with_fallback(pb, a.x, o);
+                    n_fj += b.n_fj;
+                    if (!(b.status & ST_NONFINITE) && b.converged) { a = b; a.status |= ST_REFINED; }
+                }
+                if (!a.converged) { a.converged = true; a.status |= ST_PROMOTED | ST_CONVERGED; }
+                a.status |= (ci << ST_CAND_SHIFT);
+                r = a;
+                success = true;
+            }
+            if (!success) {
+                r = PointResult{};
+                for (int q = 0; q < 5; ++q) r.x[q] = std::numeric_limits<double>::quiet_NaN();
+                r.th = Thermo{};
+                const double nan = std::numeric_limits<double>::quiet_NaN();
+                r.th.omega = r.th.pressure = r.th.rho_norm = r.th.entropy = r.th.energy = nan;
+                for (int q = 0; q < 3; ++q) r.th.masses[q] = r.th.rho[q] = nan;
+                r.iterations = -1;
+                r.residual_norm = nan;
+                r.status = ST_NO_RESULT;
+            } else {
+                tracker_update(tk, r.x, T_MeV[l], mu_MeV[im]);
+                std::memcpy(cache, r.x, 40);
+                have_cache = true;
+            }
+            r.n_fj = n_fj;
+            if (success) store(out, n, l * n_mu + im, pb, r);
+            else {
+                const int64_t i = l * n_mu + im;
+                for (int q = 0; q < 5; ++q) out->x[q * n + i] = r.x[q];
+                for (int q = 0; q < 3; ++q) { out->mass[q * n + i] = r.th.masses[q]; out->n_q[q * n + i] = r.x[0]; out->n_qbar[q * n + i] = r.x[0]; }
+                out->omega[i] = out->pressure[i] = out->rho_norm[i] = out->entropy[i] = out->energy[i] = r.x[0];
+                out->residual_norm[i] = r.x[0];
+                out->iterations[i] = -1;
+                out->status[i] = r.status;
+                if (out->n_fj) out->n_fj[i] = n_fj;
+            }
         }
     }
     return 0;

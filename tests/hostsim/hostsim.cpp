@@ -143,9 +143,20 @@ struct Sink {
     }
 };
 
+void hostsim_scan_lines_mode(const pnjl_config* c, int64_t n_lines, const double* muq_MeV, const double* xi,
+                             const int32_t* table_idx, int32_t n_T, const double* T_MeV, int32_t n_tables,
+                             const pnjl_boundary* tables, double* records, int32_t mode);
+
 void hostsim_scan_lines(const pnjl_config* c, int64_t n_lines, const double* muq_MeV, const double* xi,
                         const int32_t* table_idx, int32_t n_T, const double* T_MeV, int32_t n_tables,
                         const pnjl_boundary* tables, double* records) {
+    hostsim_scan_lines_mode(c, n_lines, muq_MeV, xi, table_idx, n_T, T_MeV, n_tables, tables, records, 0);
+}
+
+// mode 0: (xi, muq) lines marching T; mode 1: TmuScan lines, i.e. muq_MeV = per-line T_MeV and T_MeV = the mu grid
+void hostsim_scan_lines_mode(const pnjl_config* c, int64_t n_lines, const double* muq_MeV, const double* xi,
+                             const int32_t* table_idx, int32_t n_T, const double* T_MeV, int32_t n_tables,
+                             const pnjl_boundary* tables, double* records, int32_t mode) {
     Model m = model_of(c);
     SolverParams sp = params_of(c);
     HostMesh mesh = mesh_of(c);
@@ -161,7 +172,8 @@ void hostsim_scan_lines(const pnjl_config* c, int64_t n_lines, const double* muq
         HostEval ev{&m, &mesh, c->isospin_symmetric};
         Solver<HostEval> sv(m, sp, ev);
         Sink sink{records + PNJL_REC_DOUBLES * n_T * l, xi[l]};
-        scan_line(sv, pt, table_idx ? table_idx[l] : -1, muq_MeV[l], xi[l], n_T, T_MeV, sink);
+        if (mode == 0) scan_line(sv, pt, table_idx ? table_idx[l] : -1, muq_MeV[l], xi[l], n_T, T_MeV, sink);
+        else scan_tmu_line(sv, pt, table_idx ? table_idx[l] : -1, muq_MeV[l], xi[l], n_T, T_MeV, sink);
     }
     delete pt;
 }

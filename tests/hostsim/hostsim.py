@@ -71,7 +71,10 @@ class HostSim:
                                       C.c_int32(seed_mode), C.c_int32(n_seeds), sp, _abi.dptr(rec))
         return rec
 
-    def scan_lines(self, muq_MeV, xi, T_MeV, tables=(), table_idx=None):
+    def tmu_scan(self, T_MeV, xi, mu_MeV, tables=(), table_idx=None):
+        return self.scan_lines(T_MeV, xi, mu_MeV, tables, table_idx, mode=1)
+
+    def scan_lines(self, muq_MeV, xi, T_MeV, tables=(), table_idx=None, mode=0):
         muq_MeV = _abi.as_f64(muq_MeV)
         n_lines = muq_MeV.size
         xi = _abi.as_f64(xi, n_lines)
@@ -87,7 +90,7 @@ class HostSim:
             table_idx = np.full(n_lines, -1, dtype=np.int32)
         table_idx = np.ascontiguousarray(table_idx, dtype=np.int32)
         rec = np.zeros((n_lines, T_MeV.size, _abi.REC_DOUBLES))
-        self.lib.hostsim_scan_lines(C.byref(self.cfg), C.c_int64(n_lines), _abi.dptr(muq_MeV), _abi.dptr(xi),
-                                    _abi.iptr(table_idx), C.c_int32(T_MeV.size), _abi.dptr(T_MeV),
-                                    C.c_int32(len(tables)), ctabs, _abi.dptr(rec))
+        self.lib.hostsim_scan_lines_mode(C.byref(self.cfg), C.c_int64(n_lines), _abi.dptr(muq_MeV), _abi.dptr(xi),
+                                         _abi.iptr(table_idx), C.c_int32(T_MeV.size), _abi.dptr(T_MeV),
+                                         C.c_int32(len(tables)), ctabs, _abi.dptr(rec), C.c_int32(mode))
         return rec
