@@ -344,15 +344,20 @@ def main():
     # converged points / evaluation counts of this rank's slab (identical every step; counted once)
     r2 = d_rec.reshape(-1, A.REC_DOUBLES)
     conv = ((r2[:, A.REC_STATUS].to(torch.int64) & 1) != 0).sum().to(torch.float64)
-    cnt = torch.stack([conv, r2[:, A.REC_NEVAL].sum(), r2[:, A.REC_NTHERMO].sum(), r2[:, A.REC_NFUSED].sum()])
+    # quadrature nodes a pass actually sweeps at each point: p_num when xi == 0 (isotropic collapse: the cos(theta) sum
+    # is pre-summed into the weights), p_num * t_num otherwise — the algorithmic FLOP count follows the evaluated nodes
+    nodes_pt = torch.where(r2[:, A.REC_XI] == 0.0, float(p if eng.isotropic_collapse else n_nodes), float(n_nodes))
+    unit = lambda col: (r2[:, col] * nodes_pt).sum()
+    cnt = torch.stack([conv, r2[:, A.REC_NEVAL].sum(), r2[:, A.REC_NTHERMO].sum(), r2[:, A.REC_NFUSED].sum(),
+                       unit(A.REC_NEVAL), unit(A.REC_NTHERMO), unit(A.REC_NFUSED)])
     if world > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
     total_ms, kernel_ms = float(tot[0]), float(tot[1])
-    n_conv, n_fj, n_th, n_ft = (float(v) for v in cnt)
+    n_conv, n_fj, n_th, n_ft, u_fj, u_th, u_ft = (float(v) for v in cnt)
     value = n_conv * args.steps / (total_ms * 1e-3)
-    fl = alg_flops(n_nodes, n_fj, n_th, 2, n_ft)      # whole job, one step, flavours actually evaluated (u == d)
-    fl_ref = alg_flops(n_nodes, n_fj, n_th, 3, n_ft)        # same passes counted the way the reference loops (3 flavours)
+    fl = alg_flops(1, u_fj, u_th, 2, u_ft)            # whole job, one step: evaluated nodes x flavours actually evaluated (u == d)
+    fl_ref = alg_flops(n_nodes, n_fj, n_th, 3, n_ft)  # same passes counted the way the reference loops (full mesh, 3 flavours)
     st = eng.stats()
 
     # ---- e2e: the reference-facing call with HOST buffers (pnjl_scan_lines_host / pnjl_solve_points_host):
@@ -425,6 +430,8 @@ def main():
                               "peak_source": "DFMA microbenchmark run in this process (pnjl_measure_fp64_peak): sustained %.2f, "
                                              "burst %.2f TFLOP/s per GPU; MEASURED_PEAKS.json has no FP64 figure" % (peak_sus, peak_burst),
                               "algorithmic_flop_per_step": fl, "flavours_evaluated": 2,
+                              "node_evaluations_per_step": u_fj + u_th + u_ft,
+                              "isotropic_collapse": bool(eng.isotropic_collapse),
                               "reference_equivalent_tflops": fl_ref * args.steps / (kernel_ms * 1e-3) / 1e12,
                               "fj_passes_per_point": n_fj / max(1.0, float(n_total)),
                               "thermo_passes_per_point": n_th / max(1.0, float(n_total)),

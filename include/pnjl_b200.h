@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define PNJL_ABI_VERSION 5
+#define PNJL_ABI_VERSION 6
 
 /* ---- result record layout (doubles) --------------------------------------------------------- */
 #define PNJL_REC_DOUBLES 32
@@ -121,6 +121,10 @@ typedef struct pnjl_config {
                                        solve cascade in SIMT, passes are handed over through shared-memory mailboxes.
                                        1: every warp owns a line/point, CTAs phase-aligned by named barriers.
                                        Results agree to round-off; the 8- and 16-lane layouts always use organisation 1. */
+    int32_t isotropic_collapse;     /* 1 (default): for xi == 0 exactly the integrand does not depend on cos(theta)
+                                       (E = sqrt(p^2 + M^2), Integrals.jl:178-180), so a pass sums over the p_num momentum
+                                       nodes with the cos(theta) weights pre-summed instead of over p_num * t_num nodes.
+                                       Same sums up to the order of additions.  0: always the full mesh like the reference. */
 } pnjl_config;
 
 /* First-order phase boundary mu_c(T) for one xi (data/reference/pnjl/boundary.csv + cep.csv;

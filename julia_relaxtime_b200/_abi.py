@@ -3,7 +3,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 REC_DOUBLES = 32
 REC_X, REC_MASS, REC_OMEGA, REC_PRESSURE, REC_RHO_NORM, REC_ENTROPY, REC_ENERGY = 0, 5, 8, 9, 10, 11, 12
 REC_NQ, REC_NQBAR, REC_RESNORM, REC_ITER, REC_STATUS, REC_NEVAL, REC_RHO, REC_NTHERMO = 13, 16, 19, 20, 21, 22, 23, 26
@@ -28,7 +28,8 @@ class PnjlConfig(C.Structure):
         ("xtol", C.c_double), ("ftol", C.c_double), ("residual_norm_max", C.c_double), ("phi_tol", C.c_double),
         ("max_iter", C.c_int32), ("tr_fallback", C.c_int32), ("auto_multiseed_fallback", C.c_int32),
         ("omega_tie_rel", C.c_double), ("device", C.c_int32), ("lanes_per_solve", C.c_int32),
-        ("predict_tol", C.c_double), ("isospin_symmetric", C.c_int32), ("schedule", C.c_int32)]
+        ("predict_tol", C.c_double), ("isospin_symmetric", C.c_int32), ("schedule", C.c_int32),
+        ("isotropic_collapse", C.c_int32)]
 
 
 class PnjlBoundary(C.Structure):

@@ -52,7 +52,8 @@ def load():
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = build()
+    # PNJL_LIB: developer knob — load an experimental build of the same sources (e.g. -DPNJL_PROFILE_PHASES) instead
+    path = os.environ.get("PNJL_LIB") or build()
     try:
         L = C.CDLL(path)
     except OSError as e:
@@ -109,9 +110,11 @@ class Engine:
 
     def __init__(self, p_num=64, t_num=8, max_iter=1000, trust_region_fallback=True, auto_multiseed_fallback=True,
                  residual_norm_max=1e-6, omega_tie_rel=1e-12, device=-1, lanes_per_solve=0, nodes=None,
-                 isospin_symmetric=True, predict_tol=1e-4, schedule=0, consts: PNJLConstants = DEFAULT):
+                 isospin_symmetric=True, predict_tol=1e-4, schedule=0, isotropic_collapse=True,
+                 consts: PNJLConstants = DEFAULT):
         self.L = load()
         self.p_num, self.t_num = int(p_num), int(t_num)
+        self.isotropic_collapse = bool(isotropic_collapse)
         self._keep = None
         k = consts
         cfg = _abi.PnjlConfig(
@@ -121,7 +124,8 @@ class Engine:
             xtol=1e-9, ftol=1e-9, residual_norm_max=residual_norm_max, phi_tol=1e-8, max_iter=int(max_iter),
             tr_fallback=int(trust_region_fallback), auto_multiseed_fallback=int(auto_multiseed_fallback),
             omega_tie_rel=omega_tie_rel, device=int(device), lanes_per_solve=int(lanes_per_solve),
-            predict_tol=float(predict_tol), isospin_symmetric=int(isospin_symmetric), schedule=int(schedule))
+            predict_tol=float(predict_tol), isospin_symmetric=int(isospin_symmetric), schedule=int(schedule),
+            isotropic_collapse=int(isotropic_collapse))
         if nodes is not None:
             self._keep = [np.ascontiguousarray(a, dtype=np.float64) for a in nodes]
             cfg.p_nodes, cfg.p_w, cfg.c_nodes, cfg.c_w = [_abi.dptr(a) for a in self._keep]

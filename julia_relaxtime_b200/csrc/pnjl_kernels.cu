@@ -32,6 +32,7 @@ struct DeviceConfig {
     Model m;
     SolverParams sp;
     int n_nodes;
+    int n_iso;              // p_num when the isotropic collapse is enabled (mesh buffer then carries 2 n_iso more doubles), else 0
     int lockstep;
     double p2max, pc2max;   // mesh maxima (bound on E for the fast-path test)
     unsigned long long* dbg;   // phase-profiling counters (PNJL_PROFILE_PHASES builds only)
@@ -188,8 +189,8 @@ struct GroupEval {
 };
 
 template <int G>
-__device__ __forceinline__ void stage_mesh(const double* __restrict__ g_mesh, int n, double* s_mesh, int* s_done) {
-    for (int i = threadIdx.x; i < 3 * n; i += blockDim.x) s_mesh[i] = g_mesh[i];
+__device__ __forceinline__ void stage_mesh(const double* __restrict__ g_mesh, int n /* doubles */, double* s_mesh, int* s_done) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s_mesh[i] = g_mesh[i];
     if (threadIdx.x == 0) *s_done = 0;
     __syncthreads();
 }
@@ -205,6 +206,9 @@ __device__ __forceinline__ GroupEval<G> make_eval(const DeviceConfig* cfg, const
     ev.mv.n = n;
     ev.mv.p2max = cfg->p2max;
     ev.mv.pc2max = cfg->pc2max;
+    ev.mv.p2_iso = s_mesh + 3 * n;
+    ev.mv.coef_iso = s_mesh + 3 * n + cfg->n_iso;
+    ev.mv.n_iso = cfg->n_iso;
     ev.isospin = cfg->sp.isospin;
     ev.lockstep = cfg->lockstep;
     ev.s_done = s_done;
@@ -249,7 +253,7 @@ __global__ void __launch_bounds__(512, 1) k_solve_points(const DeviceConfig* __r
                                                       double* __restrict__ records, unsigned long long* counter) {
     extern __shared__ double s_mesh[];
     __shared__ int s_done;
-    stage_mesh<G>(g_mesh, cfg->n_nodes, s_mesh, &s_done);
+    stage_mesh<G>(g_mesh, 3 * cfg->n_nodes + 2 * cfg->n_iso, s_mesh, &s_done);
     GroupEval<G> ev = make_eval<G>(cfg, s_mesh, &s_done);
     Solver<GroupEval<G>> sv(cfg->m, cfg->sp, ev);
     for (;;) {
@@ -303,7 +307,7 @@ __global__ void __launch_bounds__(512, 1) k_scan_lines(const DeviceConfig* __res
                                                     unsigned long long* counter, int mode) {
     extern __shared__ double s_mesh[];
     __shared__ int s_done;
-    stage_mesh<G>(g_mesh, cfg->n_nodes, s_mesh, &s_done);
+    stage_mesh<G>(g_mesh, 3 * cfg->n_nodes + 2 * cfg->n_iso, s_mesh, &s_done);
     GroupEval<G> ev = make_eval<G>(cfg, s_mesh, &s_done);
     Solver<GroupEval<G>> sv(cfg->m, cfg->sp, ev);
     for (;;) {
@@ -349,7 +353,8 @@ struct WsGroup {
     int done;                // mailboxes served in total, monotonic                                (atomic)
     int n_slots;             // mailboxes of this group
     int first_slot;          // index of its first mailbox
-    int pad[2];
+    volatile int ticket;     // CTA-wide sequence number of the published round: workers serve the oldest round first
+    int pad;
 };
 
 // What the controller lanes work on: whole continuity lines or independent points.
@@ -369,6 +374,7 @@ struct CtrlEval {
     const Model* m;
     WsSlot* slot;
     WsGroup* group;
+    int* ticket_ctr;  // CTA-wide round counter (shared memory)
     int seq;          // rounds posted so far
     unsigned grp;     // lanes of this controller warp that own a mailbox
     bool leader;      // lowest lane of the group
@@ -397,6 +403,7 @@ struct CtrlEval {
         ++seq;
         if (leader) {
             group->next = 0;
+            group->ticket = atomicAdd(ticket_ctr, 1);
             __threadfence_block();
             group->round = seq;                // publish the round to the workers
         }
@@ -545,20 +552,26 @@ __device__ __noinline__ void ws_worker_pass(const DeviceConfig* cfg, const MeshV
 }
 
 constexpr int kWsMaxGroups = 8;
+#ifndef PNJL_WS_MAX_THREADS
+#define PNJL_WS_MAX_THREADS 512   // 16 warps x 128 registers fill the register file of an SM
+#endif
+constexpr int kWsMaxWarps = PNJL_WS_MAX_THREADS / 32;
 
 // blockDim.x = 32 * (n_workers + n_ctrl_warps).  n_slots mailboxes (one task each) are spread evenly over the
 // controller warps; a pass may be split into `parts` node ranges served by different workers (few tasks per SM).
 // Dynamic shared memory: mesh [3 n] | mailboxes [n_slots] | partial sums [n_slots][parts][21] (parts > 1 only).
-__global__ void __launch_bounds__(512, 1) k_solve_ws(const DeviceConfig* __restrict__ cfg, const double* __restrict__ g_mesh,
+__global__ void __launch_bounds__(PNJL_WS_MAX_THREADS, 1) k_solve_ws(const DeviceConfig* __restrict__ cfg, const double* __restrict__ g_mesh,
                                                      WsTask task, unsigned long long* counter, int n_workers,
                                                      int n_ctrl_warps, int n_slots, int parts) {
     extern __shared__ double s_dyn[];
     __shared__ WsGroup s_groups[kWsMaxGroups];
+    __shared__ int s_ticket;
     const int n = cfg->n_nodes;
     double* s_mesh = s_dyn;
-    WsSlot* s_slots = reinterpret_cast<WsSlot*>(s_dyn + 3 * n);
+    const int n_mesh = 3 * n + 2 * cfg->n_iso;
+    WsSlot* s_slots = reinterpret_cast<WsSlot*>(s_dyn + n_mesh);
     double* s_part = reinterpret_cast<double*>(s_slots + n_slots);
-    for (int i = threadIdx.x; i < 3 * n; i += blockDim.x) s_mesh[i] = g_mesh[i];
+    for (int i = threadIdx.x; i < n_mesh; i += blockDim.x) s_mesh[i] = g_mesh[i];
     const int per = (n_slots + n_ctrl_warps - 1) / n_ctrl_warps;
     if (threadIdx.x < n_ctrl_warps) {
         const int cw = threadIdx.x;
@@ -570,6 +583,8 @@ __global__ void __launch_bounds__(512, 1) k_solve_ws(const DeviceConfig* __restr
         s_groups[cw].done = 0;
         s_groups[cw].n_slots = cnt;
         s_groups[cw].first_slot = cw * per;
+        s_groups[cw].ticket = 0;
+        if (cw == 0) s_ticket = 0;
     }
     for (int i = threadIdx.x; i < n_slots; i += blockDim.x) {
         s_slots[i].type = WS_EXIT;
@@ -582,11 +597,18 @@ __global__ void __launch_bounds__(512, 1) k_solve_ws(const DeviceConfig* __restr
         MeshView mv;
         mv.p2 = s_mesh; mv.pc2 = s_mesh + n; mv.coef = s_mesh + 2 * n; mv.n = n;
         mv.p2max = cfg->p2max; mv.pc2max = cfg->pc2max;
+        mv.p2_iso = s_mesh + 3 * n; mv.coef_iso = s_mesh + 3 * n + cfg->n_iso; mv.n_iso = cfg->n_iso;
 #ifdef PNJL_PROFILE_PHASES
         long long t_idle = 0;
 #endif
         for (;;) {
+            // Pick the open round that was published first (FIFO over the groups).  Serving the groups in turn locks
+            // their rounds in phase: all controller warps then sit in their scalar phase (~28 k cycles per round) at
+            // the same time and the workers starve meanwhile (measured: 13 % of worker time, scripts/ws_queue_sim.py
+            // reproduces it); a fixed priority is worse still.  Oldest-first lets the rounds drift apart, so one
+            // group's scalar phase hides behind another group's round.
             bool any_live = false, did = false;
+            int best = -1, best_ticket = 0;
             for (int g = 0; g < n_ctrl_warps; ++g) {
                 WsGroup* gr = &s_groups[g];
                 if (gr->exit_flag) continue;
@@ -595,10 +617,16 @@ __global__ void __launch_bounds__(512, 1) k_solve_ws(const DeviceConfig* __restr
                 if (round == 0) continue;
                 // rounds are strictly sequential per group: all mailboxes of round r are served before r+1 opens
                 if (*((volatile int*)&gr->done) >= round * gr->n_slots) continue;
+                if (*((volatile int*)&gr->next) >= gr->n_slots * parts) continue;   // the round is fully handed out
+                const int tk = gr->ticket;
+                if (best < 0 || tk - best_ticket < 0) { best = g; best_ticket = tk; }
+            }
+            if (best >= 0) {
+                WsGroup* gr = &s_groups[best];
                 int idx = 0;
                 if (lane == 0) idx = atomicAdd(&gr->next, 1);
                 idx = __shfl_sync(0xffffffffu, idx, 0);
-                if (idx >= gr->n_slots * parts) continue;    // the round is fully handed out
+                if (idx >= gr->n_slots * parts) continue;    // somebody else took the last item
                 __threadfence_block();
                 const int si = gr->first_slot + idx / parts, part = idx % parts;
                 WsSlot* sl = &s_slots[si];
@@ -661,6 +689,7 @@ __global__ void __launch_bounds__(512, 1) k_solve_ws(const DeviceConfig* __restr
     ev.m = &cfg->m;
     ev.slot = &s_slots[gr->first_slot + lane];
     ev.group = gr;
+    ev.ticket_ctr = &s_ticket;
     ev.seq = 0;
     ev.grp = gr->n_slots >= 32 ? 0xffffffffu : ((1u << gr->n_slots) - 1u);
     ev.leader = lane == 0;
@@ -719,7 +748,7 @@ __global__ void __launch_bounds__(512, 1) k_eval_fj(const DeviceConfig* __restri
                                                  double* __restrict__ FJ, unsigned long long* counter) {
     extern __shared__ double s_mesh[];
     __shared__ int s_done;
-    stage_mesh<G>(g_mesh, cfg->n_nodes, s_mesh, &s_done);
+    stage_mesh<G>(g_mesh, 3 * cfg->n_nodes + 2 * cfg->n_iso, s_mesh, &s_done);
     GroupEval<G> ev = make_eval<G>(cfg, s_mesh, &s_done);
     for (;;) {
         const long long i = next_task<G>(counter, ev);
@@ -849,7 +878,7 @@ struct pnjl_handle {
     int G = 32;
     int block_threads = 128;
     int schedule = 0;             // 0: every warp owns a line (phase-aligned CTAs); 1: worker/controller warps
-    int ws_workers = 14, ws_ctrl_warps = 2, ws_spw = 4;
+    int ws_workers = 14, ws_ctrl_warps = 2, ws_spw = 4, ws_slots = 0;
     DeviceConfig host_cfg;
     DeviceConfig* d_cfg = nullptr;
     double* d_mesh = nullptr;
@@ -908,7 +937,7 @@ int launch_geometry(pnjl_handle* h, K kernel, size_t smem, long long n_groups_ne
 template <int G>
 int launch_points(pnjl_handle* h, long long n, const double* T, const double* mu, const double* xi, int seed_mode,
                   int n_seeds, const double* seeds, double* rec, cudaStream_t st) {
-    const size_t smem = sizeof(double) * 3 * h->n_nodes;
+    const size_t smem = sizeof(double) * (3 * h->n_nodes + 2 * h->host_cfg.n_iso);
     int blocks, threads;
     int rc = launch_geometry(h, k_solve_points<G>, smem, n, G, &blocks, &threads);
     if (rc) return rc;
@@ -934,7 +963,7 @@ int launch_ws(pnjl_handle* h, const WsTask& task_in, cudaStream_t st) {
     task.perm_mult = coprime_multiplier(task.n_tasks);
     int nw = h->ws_workers, nc = h->ws_ctrl_warps, spw = h->ws_spw, parts = 1;
     const long long per_sm = (task.n_tasks + h->sm_count - 1) / h->sm_count;   // tasks an SM has to carry at least
-    long long n_slots = (long long)spw * nw;
+    long long n_slots = h->ws_slots > 0 ? h->ws_slots : (long long)spw * nw;
     if (per_sm < n_slots) {
         // few tasks per SM (multi-GPU slabs, small grids): one mailbox per task and split every pass over
         // several workers so that all workers stay busy
@@ -947,9 +976,9 @@ int launch_ws(pnjl_handle* h, const WsTask& task_in, cudaStream_t st) {
     if (parts > 4) parts = 4;
     while ((n_slots + nc - 1) / nc > 32 && nc < kWsMaxGroups) ++nc;
     if (nc > (int)n_slots) nc = (int)n_slots;
-    if (nw + nc > 16) nw = 16 - nc;
+    if (nw + nc > kWsMaxWarps) nw = kWsMaxWarps - nc;
     const int threads = 32 * (nw + nc);
-    const size_t smem = sizeof(double) * 3 * h->n_nodes + sizeof(WsSlot) * (size_t)n_slots +
+    const size_t smem = sizeof(double) * (3 * h->n_nodes + 2 * h->host_cfg.n_iso) + sizeof(WsSlot) * (size_t)n_slots +
                         (parts > 1 ? sizeof(double) * kWsR * (size_t)n_slots * parts : 0);
     cudaFuncAttributes fa;
     CUDA_TRY(cudaFuncGetAttributes(&fa, k_solve_ws));
@@ -992,7 +1021,7 @@ int launch_points_ws(pnjl_handle* h, long long n, const double* T, const double*
 template <int G>
 int launch_lines(pnjl_handle* h, long long n_lines, const double* muq, const double* xi, const int* tidx, int n_T,
                  const double* T, double* rec, cudaStream_t st, int mode) {
-    const size_t smem = sizeof(double) * 3 * h->n_nodes;
+    const size_t smem = sizeof(double) * (3 * h->n_nodes + 2 * h->host_cfg.n_iso);
     int blocks, threads;
     int rc = launch_geometry(h, k_scan_lines<G>, smem, n_lines, G, &blocks, &threads);
     if (rc) return rc;
@@ -1006,7 +1035,7 @@ int launch_lines(pnjl_handle* h, long long n_lines, const double* muq, const dou
 template <int G>
 int launch_fj(pnjl_handle* h, long long n, const double* T, const double* mu, const double* xi, const double* x,
               double* FJ, cudaStream_t st) {
-    const size_t smem = sizeof(double) * 3 * h->n_nodes;
+    const size_t smem = sizeof(double) * (3 * h->n_nodes + 2 * h->host_cfg.n_iso);
     int blocks, threads;
     int rc = launch_geometry(h, k_eval_fj<G>, smem, n, G, &blocks, &threads);
     if (rc) return rc;
@@ -1085,6 +1114,7 @@ void pnjl_default_config(pnjl_config* c) {
     c->predict_tol = 1e-4;
     c->isospin_symmetric = 1;
     c->schedule = 0;
+    c->isotropic_collapse = 1;
 }
 
 int pnjl_gauleg(double a, double b, int32_t n, double* nodes, double* weights) {
@@ -1142,7 +1172,8 @@ int pnjl_create(const pnjl_config* c, pnjl_handle** out) {
         pnjl_gauleg(0.0, 1.0, c->t_num, cn.data(), cw.data());   // Integrals.jl:67-73
     }
     // mesh in build_nodes order (Integrals.jl:87-96): column-major (p_num, t_num), p fastest
-    std::vector<double> mesh(3 * (size_t)h->n_nodes);
+    const int n_iso = c->isotropic_collapse ? c->p_num : 0;
+    std::vector<double> mesh(3 * (size_t)h->n_nodes + 2 * (size_t)n_iso);
     const double two_pi = 2 * kPi;
     for (int j = 0; j < c->t_num; ++j)
         for (int i = 0; i < c->p_num; ++i) {
@@ -1153,8 +1184,16 @@ int pnjl_create(const pnjl_config* c, pnjl_handle** out) {
             mesh[2 * h->n_nodes + k] = (pw[i] * (cw[j] * 2.0)) * (p * p) / (two_pi * two_pi);
         }
 
+    for (int i = 0; i < n_iso; ++i) {
+        double csum = 0.0;
+        for (int j = 0; j < c->t_num; ++j) csum += mesh[2 * h->n_nodes + j * c->p_num + i];
+        mesh[3 * h->n_nodes + i] = pn[i] * pn[i];
+        mesh[3 * h->n_nodes + n_iso + i] = csum;
+    }
+
     DeviceConfig& dc = h->host_cfg;
     std::memset(&dc, 0, sizeof(dc));
+    dc.n_iso = n_iso;
     dc.m.hbarc = c->hbarc; dc.m.Lambda = c->Lambda; dc.m.m_ud0 = c->m_ud0; dc.m.m_s0 = c->m_s0; dc.m.G = c->G; dc.m.K = c->K;
     dc.m.T0 = c->T0; dc.m.a0 = c->a0; dc.m.a1 = c->a1; dc.m.a2 = c->a2; dc.m.b3 = c->b3; dc.m.rho0 = c->rho0; dc.m.Nc = c->Nc;
     dc.sp.xtol = c->xtol; dc.sp.ftol = c->ftol; dc.sp.residual_norm_max = c->residual_norm_max; dc.sp.phi_tol = c->phi_tol;
@@ -1176,9 +1215,10 @@ int pnjl_create(const pnjl_config* c, pnjl_handle** out) {
         if (getenv("PNJL_WS_WORKERS")) h->ws_workers = atoi(getenv("PNJL_WS_WORKERS"));
         if (getenv("PNJL_WS_CTRL")) h->ws_ctrl_warps = atoi(getenv("PNJL_WS_CTRL"));
         if (getenv("PNJL_WS_SPW")) h->ws_spw = atoi(getenv("PNJL_WS_SPW"));
+        if (getenv("PNJL_WS_SLOTS")) h->ws_slots = atoi(getenv("PNJL_WS_SLOTS"));
         if (h->ws_spw < 1 || h->ws_spw > 8) h->ws_spw = 4;
-        if (h->ws_workers < 1 || h->ws_workers > 15) h->ws_workers = 15;
-        if (h->ws_ctrl_warps < 1 || h->ws_workers + h->ws_ctrl_warps > 16) h->ws_ctrl_warps = 16 - h->ws_workers;
+        if (h->ws_workers < 1 || h->ws_workers > kWsMaxWarps - 1) h->ws_workers = kWsMaxWarps - 1;
+        if (h->ws_ctrl_warps < 1 || h->ws_workers + h->ws_ctrl_warps > kWsMaxWarps) h->ws_ctrl_warps = kWsMaxWarps - h->ws_workers;
     }
     dc.n_nodes = h->n_nodes;
     dc.p2max = 0.0;

@@ -28,8 +28,16 @@
 #define PNJL_HD_NOINL
 #endif
 
+#ifndef PNJL_FJ_UNROLL
+#define PNJL_FJ_UNROLL 1
+#endif
+#ifndef PNJL_SWP
+#define PNJL_SWP 0
+#endif
+
 namespace pnjl {
 
+constexpr int kFjUnroll = PNJL_FJ_UNROLL;   // unroll factor of the paired FJ loop (experiments; 1 in the product build)
 constexpr double kPi = 3.14159265358979323846;
 constexpr double kPolyakovEps = 1e-16;  // Integrals.jl:152
 
@@ -518,12 +526,10 @@ PNJL_HD void pair_front(const FastCtx& fc, double M2u, double M2s, double k2, do
     for (int j = 0; j < 2; ++j) { Y[2 * j] = e1[j] * fc.kapP; Y[2 * j + 1] = e1[j] * fc.kapM; }
 }
 
-// FJ pass, u and s flavour of one node.  fu/fs: per-flavour sums as in fj_node_fast; sh: flavour-summed sums with
-// the u contribution counted twice (u and d are the same flavour here).
-PNJL_HD void fj_pair_fast(const FastCtx& fc, double M2u, double M2s, double k2, double coef, double fu[5], double fs[5],
+// FJ pass, u and s flavour of one node, after the front end.  fu/fs: per-flavour sums as in fj_node_fast; sh:
+// flavour-summed sums with the u contribution counted twice (u and d are the same flavour here).
+PNJL_HD void fj_pair_back(const FastCtx& fc, const double rE[2], const double Y[4], double coef, double fu[5], double fs[5],
                           double sh[5]) {
-    double rE[2], E[2], Y[4];
-    pair_front(fc, M2u, M2s, k2, rE, E, Y);
     Species4 sp;
     species4_fast(fc, Y, sp, true);
     double nsum[2], Q[2], crE[2], crE2[2], m3[4], s3[2], s4[2], gp[2], gpb[2], hpp[2], hppb[2], hpbpb[2];
@@ -554,6 +560,113 @@ PNJL_HD void fj_pair_fast(const FastCtx& fc, double M2u, double M2s, double k2, 
     sh[2] = f_fma(coef, f_fma(2.0, hpp[0], hpp[1]), sh[2]);
     sh[3] = f_fma(coef, f_fma(2.0, hppb[0], hppb[1]), sh[3]);
     sh[4] = f_fma(coef, f_fma(2.0, hpbpb[0], hpbpb[1]), sh[4]);
+}
+
+#if defined(__CUDA_ARCH__)
+// Software-pipelined step of the paired FJ loop: the back end of the CURRENT node (species, sums; inputs rE, Y, coef)
+// written level by level in between the levels of the front end of the NEXT node (k2n -> rEn, Yn), so that the two long
+// serial chains of the front end (rsqrt refinement, exp polynomial) are spread over the whole step and the warp always
+// has an independent instruction to issue.  Arithmetic identical, operation by operation, to pair_front + fj_pair_back.
+__device__ __forceinline__ void fj_pair_swp(const FastCtx& fc, double M2u, double M2s, double k2n, const double rE[2],
+                                            const double Y[4], double coef, double rEn[2], double Yn[4], double fu[5],
+                                            double fs[5], double sh[5]) {
+    const double P1[4] = {fc.Phi, fc.Phib, fc.Phi, fc.Phib}, P2[4] = {fc.Phib, fc.Phi, fc.Phib, fc.Phi};
+    const double P13[4] = {fc.Phi3, fc.Phib3, fc.Phi3, fc.Phib3}, P24[4] = {fc.Phib4, fc.Phi4, fc.Phib4, fc.Phi4};
+    double E2[2], y0[2], t[2], e[2], pp[2], kd[2], r[2], tt[2], po[2];
+    int ke[2];
+    double a[4], f[4], inv0[4], g[4], q[4], ee[4], inv[4], r1[4], r2[4], n[4], qf[4], m3[4];
+#define PNJL_F2(expr) _Pragma("unroll") for (int j = 0; j < 2; ++j) { expr; }
+#define PNJL_B4(expr) _Pragma("unroll") for (int s = 0; s < 4; ++s) { expr; }
+    PNJL_F2(E2[j] = k2n + (j == 0 ? M2u : M2s))
+    PNJL_B4(a[s] = fma(3.0, P2[s], Y[s]))
+    PNJL_F2(asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0[j]) : "d"(E2[j])))
+    PNJL_B4(a[s] = fma(Y[s], a[s], P13[s]))
+    PNJL_F2(t[j] = E2[j] * y0[j])
+    PNJL_B4(f[s] = fma(Y[s], a[s], 1.0))
+    PNJL_F2(e[j] = fma(-t[j], y0[j], 1.0))
+    PNJL_B4(asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(inv0[s]) : "d"(f[s])))
+    PNJL_F2(pp[j] = fma(0.375, e[j], 0.5))
+    PNJL_B4(g[s] = fma(2.0, P2[s], Y[s]))
+    PNJL_F2(t[j] = y0[j] * e[j])
+    PNJL_B4(q[s] = fma(3.0, Y[s], P24[s]))
+    PNJL_F2(rEn[j] = fma(t[j], pp[j], y0[j]))
+    PNJL_B4(g[s] = fma(Y[s], g[s], P1[s]))
+    PNJL_F2(t[j] = E2[j] * rEn[j])
+    PNJL_B4(q[s] = fma(Y[s], q[s], P1[s]))
+    PNJL_F2(tt[j] = t[j] * fc.nInvT)
+    PNJL_B4(ee[s] = fma(-f[s], inv0[s], 1.0))
+    PNJL_F2(kd[j] = fma(tt[j], kExpR[0], kExpR[1]))
+    PNJL_B4(ee[s] = fma(ee[s], ee[s], ee[s]))
+    PNJL_F2(ke[j] = __double2loint(kd[j]))
+    PNJL_F2(kd[j] -= kExpR[1])
+    PNJL_B4(inv[s] = fma(inv0[s], ee[s], inv0[s]))
+    PNJL_F2(r[j] = fma(kd[j], kExpR[2], tt[j]))
+    PNJL_B4(r1[s] = Y[s] * inv[s])
+    PNJL_F2(r[j] = fma(kd[j], kExpR[3], r[j]))
+    PNJL_B4(r2[s] = r1[s] * Y[s])
+    PNJL_F2(po[j] = fma(kExpC[0], r[j], kExpC[1]))
+    PNJL_B4(n[s] = g[s] * r1[s])
+    PNJL_F2(po[j] = fma(po[j], r[j], kExpC[2]))
+    PNJL_B4(qf[s] = q[s] * r1[s])
+    PNJL_F2(po[j] = fma(po[j], r[j], kExpC[3]))
+    PNJL_B4(m3[s] = -3.0 * n[s])
+    PNJL_F2(po[j] = fma(po[j], r[j], kExpC[4]))
+    double nsum[2], Q[2], Qb[2], crE[2], crE2[2], crE3[2], u1a[2], u2a[2], u1b[2], u2b[2], s3[2], s4[2], gp[2], gpb[2];
+    double hpp[2], hppb[2], hpbpb[2];
+    PNJL_F2(nsum[j] = n[2 * j] + n[2 * j + 1])
+    PNJL_F2(crE[j] = coef * rE[j])
+    PNJL_F2(po[j] = fma(po[j], r[j], kExpC[5]))
+    PNJL_F2(Q[j] = fma(m3[2 * j], n[2 * j], qf[2 * j]))
+    PNJL_F2(Qb[j] = fma(m3[2 * j + 1], n[2 * j + 1], qf[2 * j + 1]))
+    PNJL_F2(po[j] = fma(po[j], r[j], kExpC[6]))
+    PNJL_F2(crE2[j] = crE[j] * rE[j])
+    PNJL_F2(Q[j] = Q[j] + Qb[j])
+    PNJL_F2(po[j] = fma(po[j], r[j], kExpC[7]))
+    PNJL_F2(u1a[j] = 1.0 + m3[2 * j])
+    PNJL_F2(u2b[j] = 2.0 + m3[2 * j + 1])
+    PNJL_F2(po[j] = fma(po[j], r[j], kExpC[8]))
+    PNJL_F2(u2a[j] = 2.0 + m3[2 * j])
+    PNJL_F2(u1b[j] = 1.0 + m3[2 * j + 1])
+    PNJL_F2(po[j] = fma(po[j], r[j], kExpC[9]))
+    PNJL_F2(s3[j] = r2[2 * j + 1] * u2b[j])
+    PNJL_F2(s4[j] = r1[2 * j + 1] * u1b[j])
+    PNJL_F2(po[j] = fma(po[j], r[j], kExpC[10]))
+    PNJL_F2(s3[j] = fma(r1[2 * j], u1a[j], s3[j]))
+    PNJL_F2(s4[j] = fma(r2[2 * j], u2a[j], s4[j]))
+    PNJL_F2(po[j] = fma(po[j], r[j], kExpC[11]))
+    PNJL_F2(gp[j] = r1[2 * j] + r2[2 * j + 1])
+    PNJL_F2(gpb[j] = r2[2 * j] + r1[2 * j + 1])
+    double e1[2];
+    PNJL_F2(e1[j] = __hiloint2double(__double2hiint(po[j]) + (ke[j] << 20), __double2loint(po[j])))
+    PNJL_F2(hpp[j] = r2[2 * j + 1] * r2[2 * j + 1])
+    PNJL_F2(hppb[j] = r2[2 * j + 1] * r1[2 * j + 1])
+    PNJL_F2(Yn[2 * j] = e1[j] * fc.kapP)
+    PNJL_F2(hpbpb[j] = r1[2 * j + 1] * r1[2 * j + 1])
+    PNJL_F2(hpp[j] = fma(r1[2 * j], r1[2 * j], hpp[j]))
+    PNJL_F2(Yn[2 * j + 1] = e1[j] * fc.kapM)
+    PNJL_F2(hppb[j] = fma(r1[2 * j], r2[2 * j], hppb[j]))
+    PNJL_F2(hpbpb[j] = fma(r2[2 * j], r2[2 * j], hpbpb[j]))
+    PNJL_F2(crE3[j] = crE2[j] * rE[j])
+    fu[0] = fma(crE[0], nsum[0], fu[0]);   fs[0] = fma(crE[1], nsum[1], fs[0]);
+    fu[1] = fma(crE2[0], Q[0], fu[1]);     fs[1] = fma(crE2[1], Q[1], fs[1]);
+    fu[2] = fma(crE3[0], nsum[0], fu[2]);  fs[2] = fma(crE3[1], nsum[1], fs[2]);
+    fu[3] = fma(crE[0], s3[0], fu[3]);     fs[3] = fma(crE[1], s3[1], fs[3]);
+    fu[4] = fma(crE[0], s4[0], fu[4]);     fs[4] = fma(crE[1], s4[1], fs[4]);
+    sh[0] = fma(coef, fma(2.0, gp[0], gp[1]), sh[0]);
+    sh[1] = fma(coef, fma(2.0, gpb[0], gpb[1]), sh[1]);
+    sh[2] = fma(coef, fma(2.0, hpp[0], hpp[1]), sh[2]);
+    sh[3] = fma(coef, fma(2.0, hppb[0], hppb[1]), sh[3]);
+    sh[4] = fma(coef, fma(2.0, hpbpb[0], hpbpb[1]), sh[4]);
+#undef PNJL_F2
+#undef PNJL_B4
+}
+#endif
+
+PNJL_HD void fj_pair_fast(const FastCtx& fc, double M2u, double M2s, double k2, double coef, double fu[5], double fs[5],
+                          double sh[5]) {
+    double rE[2], E[2], Y[4];
+    pair_front(fc, M2u, M2s, k2, rE, E, Y);
+    fj_pair_back(fc, rE, Y, coef, fu, fs, sh);
 }
 
 // Thermo pass / fused final pass, u and s flavour of one node.  tu/ts: {sum c n+, sum c n-, sum c ln(f+ f-),
@@ -588,7 +701,26 @@ struct MeshView {
     const double* coef;   // w_p * 2 w_c * p^2 / (2 pi)^2
     int n;
     double p2max, pc2max;
+    // Isotropic collapse (n_iso > 0 enables it): for xi == 0 the integrand does not depend on cos(theta), so
+    //   sum_ij coef_ij g(p_i) = sum_i (sum_j coef_ij) g(p_i)
+    // and a pass needs p_num nodes instead of p_num * t_num.  p2_iso[i] = p_i^2, coef_iso[i] = sum_j coef_ij (summed on
+    // the host in j order).  Same value up to the summation order (<= a few ulp of the sums).
+    const double* p2_iso;
+    const double* coef_iso;
+    int n_iso;
 };
+
+// The mesh a pass sweeps for anisotropy xi (group-uniform choice).
+PNJL_HD MeshView select_mesh(const MeshView& mv, double xi) {
+    MeshView r = mv;
+    if (xi == 0.0 && mv.n_iso > 0) {
+        r.p2 = mv.p2_iso;
+        r.pc2 = mv.p2_iso;     // multiplied by xi == 0
+        r.coef = mv.coef_iso;
+        r.n = mv.n_iso;
+    }
+    return r;
+}
 
 // Per-lane partial sums of one FJ pass in the canonical 20-slot layout (to be summed over the lanes of
 // the group, then finish_fj).  Chooses, uniformly for the whole group, between
@@ -596,19 +728,47 @@ struct MeshView {
 //   fast, three flavours,
 //   general path (floors / rescaling live).
 // Returns true when the fast-path slot convention (S2B') is in use.
-PNJL_HD bool fj_partial(const Model& m, bool isospin, const PointCtx& c, const double x[5], const MeshView& mv, int lane,
+PNJL_HD bool fj_partial(const Model& m, bool isospin, const PointCtx& c, const double x[5], const MeshView& mv_in, int lane,
                         int stride, double acc[kFJAcc]) {
+    const MeshView mv = select_mesh(mv_in, c.xi);
     const double k2max = mv.p2max + (c.xi > 0.0 ? c.xi * mv.pc2max : 0.0);
     if (fast_path_ok(c.T, c.mu, c.Phi, c.Phib, k2max, c.M2)) {
         FastCtx fc;
         make_fast_ctx(c, fc);
         if (isospin && x[0] == x[1]) {
             double fu[5] = {0, 0, 0, 0, 0}, fs[5] = {0, 0, 0, 0, 0}, sh[5] = {0, 0, 0, 0, 0};
+#if PNJL_SWP
+            // Software pipeline: the front end of the next node (sqrt, exp: two long serial chains) is issued
+            // together with the back end of the current one (four species chains, the sums), so that the warp has
+            // independent work while the exp chains wait on the 8-cycle DFMA latency.
+            if (lane < mv.n) {
+                double rE[2], E[2], Y[4];
+                double cf = mv.coef[lane];
+                pair_front(fc, c.M2[0], c.M2[2], f_fma(c.xi, mv.pc2[lane], mv.p2[lane]), rE, E, Y);
 #pragma unroll 1
+                for (int k = lane + stride; k < mv.n; k += stride) {
+                    double rEn[2], Yn[4];
+                    const double cfn = mv.coef[k];
+#if defined(__CUDA_ARCH__)
+                    fj_pair_swp(fc, c.M2[0], c.M2[2], f_fma(c.xi, mv.pc2[k], mv.p2[k]), rE, Y, cf, rEn, Yn, fu, fs, sh);
+#else
+                    double En[2];
+                    pair_front(fc, c.M2[0], c.M2[2], f_fma(c.xi, mv.pc2[k], mv.p2[k]), rEn, En, Yn);
+                    fj_pair_back(fc, rE, Y, cf, fu, fs, sh);
+#endif
+                    rE[0] = rEn[0]; rE[1] = rEn[1];
+                    Y[0] = Yn[0]; Y[1] = Yn[1]; Y[2] = Yn[2]; Y[3] = Yn[3];
+                    cf = cfn;
+                }
+                fj_pair_back(fc, rE, Y, cf, fu, fs, sh);
+            }
+#else
+#pragma unroll kFjUnroll
             for (int k = lane; k < mv.n; k += stride) {
                 const double k2 = f_fma(c.xi, mv.pc2[k], mv.p2[k]);
                 fj_pair_fast(fc, c.M2[0], c.M2[2], k2, mv.coef[k], fu, fs, sh);
             }
+#endif
 #pragma unroll
             for (int q = 0; q < 5; ++q) {
                 acc[3 * q + 0] = fu[q];
@@ -808,8 +968,9 @@ PNJL_HD void thermo_node(const PointCtx& c, double k2, double coef, double acc[k
 }
 
 // Per-lane partial sums of one thermo pass in the canonical 8-slot layout.
-PNJL_HD void thermo_partial(const Model& m, bool isospin, const PointCtx& c, const double x[5], const MeshView& mv, int lane,
+PNJL_HD void thermo_partial(const Model& m, bool isospin, const PointCtx& c, const double x[5], const MeshView& mv_in, int lane,
                             int stride, double acc[kThAcc]) {
+    const MeshView mv = select_mesh(mv_in, c.xi);
     const double k2max = mv.p2max + (c.xi > 0.0 ? c.xi * mv.pc2max : 0.0);
     if (fast_path_ok(c.T, c.mu, c.Phi, c.Phib, k2max, c.M2)) {
         FastCtx fc;
@@ -855,8 +1016,9 @@ PNJL_HD void thermo_partial(const Model& m, bool isospin, const PointCtx& c, con
 // sums), tacc[8] in the thermo layout.  Returns false when the state is not on the fast path (the caller then
 // runs the two ordinary passes).
 constexpr int kFtAcc = 5;
-PNJL_HD bool ft_partial(const Model& m, bool isospin, const PointCtx& c, const double x[5], const MeshView& mv, int lane,
+PNJL_HD bool ft_partial(const Model& m, bool isospin, const PointCtx& c, const double x[5], const MeshView& mv_in, int lane,
                         int stride, double facc[kFtAcc], double tacc[kThAcc]) {
+    const MeshView mv = select_mesh(mv_in, c.xi);
     const double k2max = mv.p2max + (c.xi > 0.0 ? c.xi * mv.pc2max : 0.0);
     if (!fast_path_ok(c.T, c.mu, c.Phi, c.Phib, k2max, c.M2)) return false;
     FastCtx fc;

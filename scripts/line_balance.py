@@ -28,3 +28,9 @@ for per_sm in (56,):
 st = rec[..., A.REC_STATUS].astype(int)
 print("TR attempted points", ((st & 4) != 0).sum(), "multiseed points", ((st & 8) != 0).sum(), "phase switch", ((st & 128) != 0).sum())
 print("kernel ms", e.stats()["kernel_ms"])
+# per-line cost in FP64 loop instructions (paired loops: FJ 177, fused final 265, thermo 153 per node) for offline analysis
+cost = 177.0 * rec[..., A.REC_NEVAL].sum(axis=1) + 265.0 * rec[..., A.REC_NFUSED].sum(axis=1) + 153.0 * rec[..., A.REC_NTHERMO].sum(axis=1)
+os.makedirs("gpurun_out", exist_ok=True)
+np.save("gpurun_out/line_cost.npy", np.stack([rec[..., A.REC_NEVAL].sum(axis=1), rec[..., A.REC_NFUSED].sum(axis=1), rec[..., A.REC_NTHERMO].sum(axis=1)]))
+print("per-line loop cost: max/mean %.3f p90/mean %.3f p10/mean %.3f min/mean %.3f" % (
+    cost.max() / cost.mean(), np.percentile(cost, 90) / cost.mean(), np.percentile(cost, 10) / cost.mean(), cost.min() / cost.mean()))

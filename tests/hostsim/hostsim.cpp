@@ -17,6 +17,7 @@ namespace {
 struct HostMesh {
     int n;
     std::vector<double> p2, pc2, coef;
+    std::vector<double> p2_iso, coef_iso;   // isotropic collapse (empty: disabled), as in pnjl_create
 };
 
 struct HostEval {
@@ -31,6 +32,7 @@ struct HostEval {
             mv.p2max = mesh->p2[k] > mv.p2max ? mesh->p2[k] : mv.p2max;
             mv.pc2max = mesh->pc2[k] > mv.pc2max ? mesh->pc2[k] : mv.pc2max;
         }
+        mv.p2_iso = mesh->p2_iso.data(); mv.coef_iso = mesh->coef_iso.data(); mv.n_iso = (int)mesh->p2_iso.size();
         return mv;
     }
     void fj(double T, double mu, double xi, const double x[5], double F[5], double J[25]) {
@@ -92,6 +94,14 @@ HostMesh mesh_of(const pnjl_config* c) {
             h.pc2[k] = (p * t) * (p * t);
             h.coef[k] = (c->p_w[i] * (c->c_w[j] * 2.0)) * (p * p) / (two_pi * two_pi);
         }
+    if (c->isotropic_collapse) {
+        for (int i = 0; i < c->p_num; ++i) {
+            double csum = 0.0;
+            for (int j = 0; j < c->t_num; ++j) csum += h.coef[j * c->p_num + i];
+            h.p2_iso.push_back(c->p_nodes[i] * c->p_nodes[i]);
+            h.coef_iso.push_back(csum);
+        }
+    }
     return h;
 }
 

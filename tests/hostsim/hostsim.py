@@ -25,7 +25,7 @@ def build():
 
 class HostSim:
     def __init__(self, p_nodes, p_w, c_nodes, c_w, max_iter=1000, tr_fallback=True, auto_multiseed_fallback=True,
-                 omega_tie_rel=1e-12, isospin_symmetric=True, predict_tol=1e-4, consts=DEFAULT):
+                 omega_tie_rel=1e-12, isospin_symmetric=True, predict_tol=1e-4, isotropic_collapse=True, consts=DEFAULT):
         self.lib = C.CDLL(build())
         self.keep = [np.ascontiguousarray(a, dtype=np.float64) for a in (p_nodes, p_w, c_nodes, c_w)]
         k = consts
@@ -37,7 +37,7 @@ class HostSim:
             xtol=1e-9, ftol=1e-9, residual_norm_max=1e-6, phi_tol=1e-8, max_iter=max_iter,
             tr_fallback=int(tr_fallback), auto_multiseed_fallback=int(auto_multiseed_fallback),
             omega_tie_rel=omega_tie_rel, device=-1, lanes_per_solve=0, predict_tol=predict_tol,
-            isospin_symmetric=int(isospin_symmetric), schedule=0)
+            isospin_symmetric=int(isospin_symmetric), schedule=0, isotropic_collapse=int(isotropic_collapse))
 
     def fj(self, x, T, mu, xi):
         x = _abi.as_f64(x)

@@ -271,6 +271,49 @@ def test_isospin_fast_path_equals_three_flavour_path():
     assert (a[:, 0] == a[:, 1]).all() and (a[:, 5] == a[:, 6]).all()      # phi_u == phi_d, M_u == M_d exactly
 
 
+@pytest.mark.parametrize("p_num,t_num", [(12, 6), (64, 16)])
+def test_isotropic_collapse_equals_full_mesh(p_num, t_num):
+    """xi == 0: summing over the p_num momentum nodes with pre-summed cos(theta) weights (isotropic_collapse, default)
+    gives the same F, J and the same scan as sweeping all p_num * t_num nodes like the reference (round-off only), and
+    both agree with the oracle's full-mesh evaluation; xi != 0 is untouched (bit-identical)."""
+    o = Oracle(p_num=p_num, t_num=t_num, max_iter=40)
+    nodes = (o.p_nodes, o.p_w, o.c_nodes, o.c_w)
+    ec = engine(p_num=p_num, t_num=t_num, max_iter=40, nodes=nodes, isotropic_collapse=True)
+    ef = engine(p_num=p_num, t_num=t_num, max_iter=40, nodes=nodes, isotropic_collapse=False)
+    rng = np.random.default_rng(21)
+    n = 32
+    T, mu = rng.uniform(30, 400, n) / HBARC, rng.uniform(0, 400, n) / HBARC
+    xi = np.where(np.arange(n) % 2 == 0, 0.0, rng.uniform(-0.6, 0.8, n))
+    x = np.stack([rng.uniform(-2.2, 0.3, n), rng.uniform(-2.2, 0.3, n), rng.uniform(-2.4, -0.3, n),
+                  rng.uniform(-0.05, 1.02, n), rng.uniform(-0.05, 1.02, n)], axis=1)
+    Fc, Jc = ec.eval_fj(T, mu, xi, x)
+    Ff, Jf = ef.eval_fj(T, mu, xi, x)
+    aniso = xi != 0.0
+    assert (Fc[aniso] == Ff[aniso]).all() and (Jc[aniso] == Jf[aniso]).all()
+    assert np.abs(Fc - Ff).max() <= 2e-13 * np.abs(Ff).max() and np.abs(Jc - Jf).max() <= 2e-13 * np.abs(Jf).max()
+    for i in range(0, n, 2):
+        F0, J0 = o.FJ(x[i], T[i], mu[i], 0.0)
+        assert np.abs(Fc[i] - F0).max() <= 2e-12 * (np.abs(F0).max() + 1e-3)
+        assert np.abs(Jc[i] - J0).max() <= 2e-12 * np.abs(J0).max()
+    tables, index = load_phase_tables(os.path.join(GOLDEN, "boundary.csv"), os.path.join(GOLDEN, "cep.csv"), [0.0])
+    Tg = np.linspace(50, 300, 48)
+    muq = np.linspace(0, 400, 16)
+    tidx = np.full(16, index[0.0], dtype=np.int32)
+    recs = []
+    for e in (ec, ef):
+        e.set_boundaries(tables)
+        recs.append(e.scan_lines(muq, np.zeros(16), Tg, tidx).reshape(-1, A.REC_DOUBLES))
+    a, b = recs
+    assert (a[:, A.REC_STATUS] == b[:, A.REC_STATUS]).all() and (a[:, A.REC_ITER] == b[:, A.REC_ITER]).mean() > 0.99
+    for q in range(13):
+        # state, masses, Omega, P relative; rho_norm / s / epsilon vanish at low T and mu = 0: absolute floor
+        scale = np.maximum(np.abs(b[:, q]), 1e-3 if q in (3, 4) else (1e-2 if q >= A.REC_RHO_NORM else 1e-300))
+        err = np.abs(a[:, q] - b[:, q]) / scale
+        assert err.max() <= 1e-9, (q, err.max(), int(err.argmax()), a[err.argmax(), q], b[err.argmax(), q])
+    res = o.scan_lines(muq, np.zeros(16), Tg, tables, tidx)
+    assert_state_parity(a, res, label="collapse-lines")
+
+
 @pytest.mark.parametrize("schedule,parts", [(0, 1), (0, 2), (0, 4), (1, 1)])
 def test_kernel_organisations_agree(schedule, parts, monkeypatch):
     """Warp-specialised kernel (passes whole or split over 2/4 workers) and the one-warp-per-line kernel against the

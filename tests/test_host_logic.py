@@ -233,3 +233,29 @@ def test_solver_cascade_matches_oracle_on_lines_and_points(sim_and_oracle):
         ok = res.converged
         for q in range(3):
             assert rel(rec[ok, 5 + q], res.mass[q][ok]).max() <= 1e-9
+
+
+def test_isotropic_collapse_host_build_matches_full_mesh(sim_and_oracle):
+    """xi == 0 with the cos(theta) weights pre-summed (p_num nodes per pass) vs the full p_num * t_num mesh of the
+    reference: F, J and the thermo sums agree to round-off, and so does the oracle's full-mesh AD evaluation."""
+    from tests.hostsim.hostsim import HostSim
+    hs, o = sim_and_oracle
+    full = HostSim(o.p_nodes, o.p_w, o.c_nodes, o.c_w, max_iter=40, isotropic_collapse=False)
+    rng = np.random.default_rng(8)
+    for _ in range(30):
+        T, mu = rng.uniform(30, 400) / HBARC, rng.uniform(0, 400) / HBARC
+        x = np.array([rng.uniform(-2.2, 0.3), rng.uniform(-2.2, 0.3), rng.uniform(-2.4, -0.3),
+                      rng.uniform(-0.05, 1.02), rng.uniform(-0.05, 1.02)])
+        F1, J1 = hs.fj(x, T, mu, 0.0)
+        F2, J2 = full.fj(x, T, mu, 0.0)
+        F0, J0 = o.FJ(x, T, mu, 0.0)
+        assert np.abs(F1 - F2).max() <= 2e-13 * (np.abs(F2).max() + 1e-3) and np.abs(J1 - J2).max() <= 2e-13 * np.abs(J2).max()
+        assert np.abs(F1 - F0).max() <= 2e-12 * (np.abs(F0).max() + 1e-3) and np.abs(J1 - J0).max() <= 2e-12 * np.abs(J0).max()
+        t1, t2 = hs.thermo(x, T, mu, 0.0), full.thermo(x, T, mu, 0.0)
+        for k in t1:
+            a, b = np.asarray(t1[k]), np.asarray(t2[k])
+            assert np.abs(a - b).max() <= 1e-12 * (np.abs(b).max() + 1e-9), k
+        # xi != 0 never takes the collapsed mesh
+        F3, J3 = hs.fj(x, T, mu, 0.3)
+        F4, J4 = full.fj(x, T, mu, 0.3)
+        assert (F3 == F4).all() and (J3 == J4).all()
