@@ -572,8 +572,11 @@ __global__ void __launch_bounds__(PNJL_WS_MAX_THREADS, 1) k_solve_ws(const Devic
     WsSlot* s_slots = reinterpret_cast<WsSlot*>(s_dyn + n_mesh);
     double* s_part = reinterpret_cast<double*>(s_slots + n_slots);
     for (int i = threadIdx.x; i < n_mesh; i += blockDim.x) s_mesh[i] = g_mesh[i];
-    const int per = (n_slots + n_ctrl_warps - 1) / n_ctrl_warps;
-    if (threadIdx.x < n_ctrl_warps) {
+    // One request group per controller warp.  (Two independent groups per warp — divergent half-warps with shorter rounds —
+    // were measured 16 % slower on cfg5: the halves serialise their scalar phases.)
+    const int n_groups = n_ctrl_warps;
+    const int per = (n_slots + n_groups - 1) / n_groups;
+    if (threadIdx.x < n_groups) {
         const int cw = threadIdx.x;
         int cnt = n_slots - cw * per;
         cnt = cnt < 0 ? 0 : (cnt > per ? per : cnt);
@@ -609,7 +612,7 @@ __global__ void __launch_bounds__(PNJL_WS_MAX_THREADS, 1) k_solve_ws(const Devic
             // group's scalar phase hides behind another group's round.
             bool any_live = false, did = false;
             int best = -1, best_ticket = 0;
-            for (int g = 0; g < n_ctrl_warps; ++g) {
+            for (int g = 0; g < n_groups; ++g) {
                 WsGroup* gr = &s_groups[g];
                 if (gr->exit_flag) continue;
                 any_live = true;
@@ -876,7 +879,10 @@ struct pnjl_handle {
     int sm_count = 0;
     int n_nodes = 0;
     int G = 32;
+    int G_user = 0;               // lanes_per_solve given by the caller (0 = automatic)
+    int G_next = 0;               // layout for the next launch only (host entry points: all-isotropic batches), 0 = G
     int block_threads = 128;
+    bool block_threads_forced = false;   // PNJL_BLOCK_THREADS given
     int schedule = 0;             // 0: every warp owns a line (phase-aligned CTAs); 1: worker/controller warps
     int ws_workers = 14, ws_ctrl_warps = 2, ws_spw = 4, ws_slots = 0;
     DeviceConfig host_cfg;
@@ -907,7 +913,7 @@ template <class K>
 int launch_geometry(pnjl_handle* h, K kernel, size_t smem, long long n_groups_needed, int G, int* blocks, int* threads) {
     // CTA size: h->block_threads when there is enough work to fill every SM with such CTAs, otherwise the
     // largest warp count per CTA that still gives every SM a CTA (few lines per GPU in multi-GPU runs).
-    int block = h->block_threads;
+    int block = (G == 32 || h->block_threads_forced) ? h->block_threads : 128;   // small CTAs for the 8/16-lane layouts
     {
         const long long warps_needed = (n_groups_needed * G + 31) / 32;
         long long per_sm = (warps_needed + h->sm_count - 1) / h->sm_count;
@@ -1055,9 +1061,27 @@ int launch_fj(pnjl_handle* h, long long n, const double* T, const double* mu, co
         }                                        \
     } while (0)
 
+int take_layout(pnjl_handle* h) {
+    const int g = h->G_next ? h->G_next : h->G;
+    h->G_next = 0;
+    return g;
+}
+
+// Host entry points know xi: when the whole batch is isotropic (xi == 0 everywhere) and the collapse is on, a pass sweeps
+// p_num nodes only, so the layout is chosen for that mesh (8 or 16 lanes per solve) instead of the full one — the
+// warp-specialised kernel would be bound by its controller warps there.
+void choose_layout_for_batch(pnjl_handle* h, long long n, const double* xi) {
+    h->G_next = 0;
+    if (h->G_user != 0 || h->host_cfg.n_iso == 0) return;
+    for (long long i = 0; i < n; ++i)
+        if (xi[i] != 0.0) return;
+    const int n_eff = h->host_cfg.n_iso;
+    h->G_next = n_eff <= 96 ? 8 : (n_eff <= 256 ? 16 : 32);
+}
+
 int dispatch_points(pnjl_handle* h, long long n, const double* T, const double* mu, const double* xi, int seed_mode,
                     int n_seeds, const double* seeds, double* rec, cudaStream_t st) {
-    switch (h->G) {
+    switch (take_layout(h)) {
         case 8: return launch_points<8>(h, n, T, mu, xi, seed_mode, n_seeds, seeds, rec, st);
         case 16: return launch_points<16>(h, n, T, mu, xi, seed_mode, n_seeds, seeds, rec, st);
         default:
@@ -1067,7 +1091,7 @@ int dispatch_points(pnjl_handle* h, long long n, const double* T, const double* 
 }
 int dispatch_lines(pnjl_handle* h, long long n_lines, const double* muq, const double* xi, const int* tidx, int n_T,
                    const double* T, double* rec, cudaStream_t st, int mode = 0) {
-    switch (h->G) {
+    switch (take_layout(h)) {
         case 8: return launch_lines<8>(h, n_lines, muq, xi, tidx, n_T, T, rec, st, mode);
         case 16: return launch_lines<16>(h, n_lines, muq, xi, tidx, n_T, T, rec, st, mode);
         default:
@@ -1153,6 +1177,7 @@ int pnjl_create(const pnjl_config* c, pnjl_handle** out) {
     h->sm_count = prop.multiProcessorCount;
     h->n_nodes = c->p_num * c->t_num;
     std::memset(&h->stats, 0, sizeof(h->stats));
+    h->G_user = c->lanes_per_solve;
     if (c->lanes_per_solve == 8 || c->lanes_per_solve == 16 || c->lanes_per_solve == 32) h->G = c->lanes_per_solve;
     else if (c->lanes_per_solve == 0) h->G = h->n_nodes <= 96 ? 8 : (h->n_nodes <= 256 ? 16 : 32);
     else { delete h; return fail(PNJL_ERR_ARG, "lanes_per_solve must be 0, 8, 16 or 32"); }
@@ -1208,6 +1233,7 @@ int pnjl_create(const pnjl_config* c, pnjl_handle** out) {
         const char* el = getenv("PNJL_LOCKSTEP");
         dc.lockstep = el ? atoi(el) : (h->G == 32 ? 1 : 0);   // 0 off, 1 align loop entry, 3 align entry and exit
         h->block_threads = eb ? atoi(eb) : (h->G == 32 ? 512 : 128);
+        h->block_threads_forced = eb != nullptr;
         if (h->block_threads < 32 || h->block_threads > 512 || (h->block_threads & 31)) h->block_threads = 128;
         // internal numbering: 1 = warp-specialised, 0 = one warp per line; PNJL_SCHEDULE overrides for experiments
         const char* es = getenv("PNJL_SCHEDULE");
@@ -1353,6 +1379,7 @@ int pnjl_solve_points_host(pnjl_handle* h, int64_t n, const double* T, const dou
         d_seeds = (const double*)h->in_seeds.p;
     }
     CUDA_TRY(cudaEventRecord(h->ev0, st));
+    choose_layout_for_batch(h, n, xi);
     int rc = pnjl_solve_points_device(h, n, (const double*)h->in_T.p, (const double*)h->in_mu.p, (const double*)h->in_xi.p,
                                       seed_mode, n_seeds, d_seeds, (double*)h->out_rec.p, st);
     if (rc) return rc;
@@ -1389,6 +1416,7 @@ int pnjl_scan_lines_host(pnjl_handle* h, int64_t n_lines, const double* muq, con
         d_idx = (const int32_t*)h->in_idx.p;
     }
     CUDA_TRY(cudaEventRecord(h->ev0, st));
+    choose_layout_for_batch(h, n_lines, xi);
     int rc = pnjl_scan_lines_device(h, n_lines, (const double*)h->in_mu.p, (const double*)h->in_xi.p, d_idx, n_T,
                                     (const double*)h->in_T.p, (double*)h->out_rec.p, st);
     if (rc) return rc;
@@ -1436,6 +1464,7 @@ int pnjl_tmu_scan_host(pnjl_handle* h, int64_t n_lines, const double* T_MeV, con
         d_idx = (const int32_t*)h->in_idx.p;
     }
     CUDA_TRY(cudaEventRecord(h->ev0, st));
+    choose_layout_for_batch(h, n_lines, xi);
     int rc = pnjl_tmu_scan_device(h, n_lines, (const double*)h->in_mu.p, (const double*)h->in_xi.p, d_idx, n_mu,
                                   (const double*)h->in_T.p, (double*)h->out_rec.p, st);
     if (rc) return rc;

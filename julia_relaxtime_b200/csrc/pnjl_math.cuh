@@ -31,9 +31,6 @@
 #ifndef PNJL_FJ_UNROLL
 #define PNJL_FJ_UNROLL 1
 #endif
-#ifndef PNJL_SWP
-#define PNJL_SWP 0
-#endif
 
 namespace pnjl {
 
@@ -300,6 +297,9 @@ PNJL_HD bool fast_path_ok(double T, double mu, double Phi, double Phib, double k
     return (Phi >= 0.0) && (Phib >= 0.0) && (T > 1e-300) && (r > 0.0) && (k2max + m2 <= r * r);
 }
 
+// |mu|/T <= 60: the product (f_u+ f_u-)^2 f_s+ f_s- of one node stays far below DBL_MAX (see th_pair_fast).
+PNJL_HD bool one_log_ok(double T, double mu) { return fabs(mu) <= 60.0 * T; }
+
 PNJL_HD void make_fast_ctx(const PointCtx& c, FastCtx& f) {
     f.nInvT = -c.invT;
     // |mu|/T <= 200 here, so e^{-|mu|/T} is a normal number and its reciprocal is safe
@@ -403,6 +403,11 @@ PNJL_HD void ft_node_fast(const FastCtx& fc, double mu, double M2, double k2, do
 }
 
 // ------------------------------------------------------------------------------------------------
+// Note on the FP64 pipe: a DFMA whose three sources are three different vector registers occupies the pipe for 3 cycles
+// instead of 2 (register-file operand bandwidth; scripts/microbench_dfma_operands*.cu measure 0.333 instead of 0.5 warp
+// instructions per cycle per scheduler), while immediates, constant-bank / uniform-register operands, a repeated register
+// or a reuse-cache hit are free.  44 of the 177 FP64 instructions of the paired FJ loop are of the slow kind
+// (accumulations, mixed products), which puts the loop's own ceiling at 354 / 398 = 89 % of the DFMA peak.
 // Paired fast path (isospin case): the u and the s flavour of one node are advanced step by step together, so
 // that two (four, inside the species block) independent dependency chains are adjacent in program order.  A
 // DFMA result is available after 8 cycles and a warp can issue one every 2, so a lone chain leaves the FP64 pipe
@@ -447,6 +452,8 @@ PNJL_HD void v_rcp(const double x[W], double y[W]) {
 #endif
 }
 
+// (A table-driven exp — 32-entry 2^(j/32) table in shared memory + degree-6 polynomial, 11 FP64 instructions instead of
+// 15 — was measured 3 % SLOWER on cfg5: the LDS and the index arithmetic sit on the critical chain of the front end.)
 template <int W>
 PNJL_HD void v_exp_nonpos(const double t[W], double out[W]) {
 #if defined(__CUDA_ARCH__)
@@ -562,106 +569,6 @@ PNJL_HD void fj_pair_back(const FastCtx& fc, const double rE[2], const double Y[
     sh[4] = f_fma(coef, f_fma(2.0, hpbpb[0], hpbpb[1]), sh[4]);
 }
 
-#if defined(__CUDA_ARCH__)
-// Software-pipelined step of the paired FJ loop: the back end of the CURRENT node (species, sums; inputs rE, Y, coef)
-// written level by level in between the levels of the front end of the NEXT node (k2n -> rEn, Yn), so that the two long
-// serial chains of the front end (rsqrt refinement, exp polynomial) are spread over the whole step and the warp always
-// has an independent instruction to issue.  Arithmetic identical, operation by operation, to pair_front + fj_pair_back.
-__device__ __forceinline__ void fj_pair_swp(const FastCtx& fc, double M2u, double M2s, double k2n, const double rE[2],
-                                            const double Y[4], double coef, double rEn[2], double Yn[4], double fu[5],
-                                            double fs[5], double sh[5]) {
-    const double P1[4] = {fc.Phi, fc.Phib, fc.Phi, fc.Phib}, P2[4] = {fc.Phib, fc.Phi, fc.Phib, fc.Phi};
-    const double P13[4] = {fc.Phi3, fc.Phib3, fc.Phi3, fc.Phib3}, P24[4] = {fc.Phib4, fc.Phi4, fc.Phib4, fc.Phi4};
-    double E2[2], y0[2], t[2], e[2], pp[2], kd[2], r[2], tt[2], po[2];
-    int ke[2];
-    double a[4], f[4], inv0[4], g[4], q[4], ee[4], inv[4], r1[4], r2[4], n[4], qf[4], m3[4];
-#define PNJL_F2(expr) _Pragma("unroll") for (int j = 0; j < 2; ++j) { expr; }
-#define PNJL_B4(expr) _Pragma("unroll") for (int s = 0; s < 4; ++s) { expr; }
-    PNJL_F2(E2[j] = k2n + (j == 0 ? M2u : M2s))
-    PNJL_B4(a[s] = fma(3.0, P2[s], Y[s]))
-    PNJL_F2(asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0[j]) : "d"(E2[j])))
-    PNJL_B4(a[s] = fma(Y[s], a[s], P13[s]))
-    PNJL_F2(t[j] = E2[j] * y0[j])
-    PNJL_B4(f[s] = fma(Y[s], a[s], 1.0))
-    PNJL_F2(e[j] = fma(-t[j], y0[j], 1.0))
-    PNJL_B4(asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(inv0[s]) : "d"(f[s])))
-    PNJL_F2(pp[j] = fma(0.375, e[j], 0.5))
-    PNJL_B4(g[s] = fma(2.0, P2[s], Y[s]))
-    PNJL_F2(t[j] = y0[j] * e[j])
-    PNJL_B4(q[s] = fma(3.0, Y[s], P24[s]))
-    PNJL_F2(rEn[j] = fma(t[j], pp[j], y0[j]))
-    PNJL_B4(g[s] = fma(Y[s], g[s], P1[s]))
-    PNJL_F2(t[j] = E2[j] * rEn[j])
-    PNJL_B4(q[s] = fma(Y[s], q[s], P1[s]))
-    PNJL_F2(tt[j] = t[j] * fc.nInvT)
-    PNJL_B4(ee[s] = fma(-f[s], inv0[s], 1.0))
-    PNJL_F2(kd[j] = fma(tt[j], kExpR[0], kExpR[1]))
-    PNJL_B4(ee[s] = fma(ee[s], ee[s], ee[s]))
-    PNJL_F2(ke[j] = __double2loint(kd[j]))
-    PNJL_F2(kd[j] -= kExpR[1])
-    PNJL_B4(inv[s] = fma(inv0[s], ee[s], inv0[s]))
-    PNJL_F2(r[j] = fma(kd[j], kExpR[2], tt[j]))
-    PNJL_B4(r1[s] = Y[s] * inv[s])
-    PNJL_F2(r[j] = fma(kd[j], kExpR[3], r[j]))
-    PNJL_B4(r2[s] = r1[s] * Y[s])
-    PNJL_F2(po[j] = fma(kExpC[0], r[j], kExpC[1]))
-    PNJL_B4(n[s] = g[s] * r1[s])
-    PNJL_F2(po[j] = fma(po[j], r[j], kExpC[2]))
-    PNJL_B4(qf[s] = q[s] * r1[s])
-    PNJL_F2(po[j] = fma(po[j], r[j], kExpC[3]))
-    PNJL_B4(m3[s] = -3.0 * n[s])
-    PNJL_F2(po[j] = fma(po[j], r[j], kExpC[4]))
-    double nsum[2], Q[2], Qb[2], crE[2], crE2[2], crE3[2], u1a[2], u2a[2], u1b[2], u2b[2], s3[2], s4[2], gp[2], gpb[2];
-    double hpp[2], hppb[2], hpbpb[2];
-    PNJL_F2(nsum[j] = n[2 * j] + n[2 * j + 1])
-    PNJL_F2(crE[j] = coef * rE[j])
-    PNJL_F2(po[j] = fma(po[j], r[j], kExpC[5]))
-    PNJL_F2(Q[j] = fma(m3[2 * j], n[2 * j], qf[2 * j]))
-    PNJL_F2(Qb[j] = fma(m3[2 * j + 1], n[2 * j + 1], qf[2 * j + 1]))
-    PNJL_F2(po[j] = fma(po[j], r[j], kExpC[6]))
-    PNJL_F2(crE2[j] = crE[j] * rE[j])
-    PNJL_F2(Q[j] = Q[j] + Qb[j])
-    PNJL_F2(po[j] = fma(po[j], r[j], kExpC[7]))
-    PNJL_F2(u1a[j] = 1.0 + m3[2 * j])
-    PNJL_F2(u2b[j] = 2.0 + m3[2 * j + 1])
-    PNJL_F2(po[j] = fma(po[j], r[j], kExpC[8]))
-    PNJL_F2(u2a[j] = 2.0 + m3[2 * j])
-    PNJL_F2(u1b[j] = 1.0 + m3[2 * j + 1])
-    PNJL_F2(po[j] = fma(po[j], r[j], kExpC[9]))
-    PNJL_F2(s3[j] = r2[2 * j + 1] * u2b[j])
-    PNJL_F2(s4[j] = r1[2 * j + 1] * u1b[j])
-    PNJL_F2(po[j] = fma(po[j], r[j], kExpC[10]))
-    PNJL_F2(s3[j] = fma(r1[2 * j], u1a[j], s3[j]))
-    PNJL_F2(s4[j] = fma(r2[2 * j], u2a[j], s4[j]))
-    PNJL_F2(po[j] = fma(po[j], r[j], kExpC[11]))
-    PNJL_F2(gp[j] = r1[2 * j] + r2[2 * j + 1])
-    PNJL_F2(gpb[j] = r2[2 * j] + r1[2 * j + 1])
-    double e1[2];
-    PNJL_F2(e1[j] = __hiloint2double(__double2hiint(po[j]) + (ke[j] << 20), __double2loint(po[j])))
-    PNJL_F2(hpp[j] = r2[2 * j + 1] * r2[2 * j + 1])
-    PNJL_F2(hppb[j] = r2[2 * j + 1] * r1[2 * j + 1])
-    PNJL_F2(Yn[2 * j] = e1[j] * fc.kapP)
-    PNJL_F2(hpbpb[j] = r1[2 * j + 1] * r1[2 * j + 1])
-    PNJL_F2(hpp[j] = fma(r1[2 * j], r1[2 * j], hpp[j]))
-    PNJL_F2(Yn[2 * j + 1] = e1[j] * fc.kapM)
-    PNJL_F2(hppb[j] = fma(r1[2 * j], r2[2 * j], hppb[j]))
-    PNJL_F2(hpbpb[j] = fma(r2[2 * j], r2[2 * j], hpbpb[j]))
-    PNJL_F2(crE3[j] = crE2[j] * rE[j])
-    fu[0] = fma(crE[0], nsum[0], fu[0]);   fs[0] = fma(crE[1], nsum[1], fs[0]);
-    fu[1] = fma(crE2[0], Q[0], fu[1]);     fs[1] = fma(crE2[1], Q[1], fs[1]);
-    fu[2] = fma(crE3[0], nsum[0], fu[2]);  fs[2] = fma(crE3[1], nsum[1], fs[2]);
-    fu[3] = fma(crE[0], s3[0], fu[3]);     fs[3] = fma(crE[1], s3[1], fs[3]);
-    fu[4] = fma(crE[0], s4[0], fu[4]);     fs[4] = fma(crE[1], s4[1], fs[4]);
-    sh[0] = fma(coef, fma(2.0, gp[0], gp[1]), sh[0]);
-    sh[1] = fma(coef, fma(2.0, gpb[0], gpb[1]), sh[1]);
-    sh[2] = fma(coef, fma(2.0, hpp[0], hpp[1]), sh[2]);
-    sh[3] = fma(coef, fma(2.0, hppb[0], hppb[1]), sh[3]);
-    sh[4] = fma(coef, fma(2.0, hpbpb[0], hpbpb[1]), sh[4]);
-#undef PNJL_F2
-#undef PNJL_B4
-}
-#endif
-
 PNJL_HD void fj_pair_fast(const FastCtx& fc, double M2u, double M2s, double k2, double coef, double fu[5], double fs[5],
                           double sh[5]) {
     double rE[2], E[2], Y[4];
@@ -672,18 +579,29 @@ PNJL_HD void fj_pair_fast(const FastCtx& fc, double M2u, double M2s, double k2, 
 // Thermo pass / fused final pass, u and s flavour of one node.  tu/ts: {sum c n+, sum c n-, sum c ln(f+ f-),
 // sum c [n+ (E-mu) + n- (E+mu)]} per flavour; when WITH_F also s1u/s1s (sum c (n+ + n-)/E) and the flavour-summed
 // gsh[2] = {GP, GPB} (u counted twice).
-template <bool WITH_F>
+// ONE_LOG: the u flavour counts twice (u == d), so the log sum of a node is 2 ln(f_u+ f_u-) + ln(f_s+ f_s-) =
+// ln((f_u+ f_u-)^2 f_s+ f_s-): one logarithm per node instead of two, accumulated in ts[2] alone (tu[2] stays 0).
+// The caller selects it (uniformly) only when the product cannot overflow: every f is <= 8 max(1, e^{3|mu|/T}), so
+// |mu|/T <= 60 bounds the product by 2^18 e^{540}.
+template <bool WITH_F, bool ONE_LOG>
 PNJL_HD void th_pair_fast(const FastCtx& fc, double mu, double M2u, double M2s, double k2, double coef, double tu[4],
                           double ts[4], double& s1u, double& s1s, double gsh[2]) {
     double rE[2], E[2], Y[4];
     pair_front(fc, M2u, M2s, k2, rE, E, Y);
     Species4 sp;
     species4_fast(fc, Y, sp, false);
-    const double Lu = fast_log_pos(sp.f[0] * sp.f[1]);
-    const double Ls = fast_log_pos(sp.f[2] * sp.f[3]);
     tu[0] = f_fma(coef, sp.n[0], tu[0]);  ts[0] = f_fma(coef, sp.n[2], ts[0]);
     tu[1] = f_fma(coef, sp.n[1], tu[1]);  ts[1] = f_fma(coef, sp.n[3], ts[1]);
-    tu[2] = f_fma(coef, Lu, tu[2]);       ts[2] = f_fma(coef, Ls, ts[2]);
+    if (ONE_LOG) {
+        const double fu = sp.f[0] * sp.f[1];
+        const double L = fast_log_pos((fu * fu) * (sp.f[2] * sp.f[3]));
+        ts[2] = f_fma(coef, L, ts[2]);
+    } else {
+        const double Lu = fast_log_pos(sp.f[0] * sp.f[1]);
+        const double Ls = fast_log_pos(sp.f[2] * sp.f[3]);
+        tu[2] = f_fma(coef, Lu, tu[2]);
+        ts[2] = f_fma(coef, Ls, ts[2]);
+    }
     tu[3] = f_fma(coef, f_fma(sp.n[0], E[0] - mu, sp.n[1] * (E[0] + mu)), tu[3]);
     ts[3] = f_fma(coef, f_fma(sp.n[2], E[1] - mu, sp.n[3] * (E[1] + mu)), ts[3]);
     if (WITH_F) {
@@ -737,38 +655,11 @@ PNJL_HD bool fj_partial(const Model& m, bool isospin, const PointCtx& c, const d
         make_fast_ctx(c, fc);
         if (isospin && x[0] == x[1]) {
             double fu[5] = {0, 0, 0, 0, 0}, fs[5] = {0, 0, 0, 0, 0}, sh[5] = {0, 0, 0, 0, 0};
-#if PNJL_SWP
-            // Software pipeline: the front end of the next node (sqrt, exp: two long serial chains) is issued
-            // together with the back end of the current one (four species chains, the sums), so that the warp has
-            // independent work while the exp chains wait on the 8-cycle DFMA latency.
-            if (lane < mv.n) {
-                double rE[2], E[2], Y[4];
-                double cf = mv.coef[lane];
-                pair_front(fc, c.M2[0], c.M2[2], f_fma(c.xi, mv.pc2[lane], mv.p2[lane]), rE, E, Y);
-#pragma unroll 1
-                for (int k = lane + stride; k < mv.n; k += stride) {
-                    double rEn[2], Yn[4];
-                    const double cfn = mv.coef[k];
-#if defined(__CUDA_ARCH__)
-                    fj_pair_swp(fc, c.M2[0], c.M2[2], f_fma(c.xi, mv.pc2[k], mv.p2[k]), rE, Y, cf, rEn, Yn, fu, fs, sh);
-#else
-                    double En[2];
-                    pair_front(fc, c.M2[0], c.M2[2], f_fma(c.xi, mv.pc2[k], mv.p2[k]), rEn, En, Yn);
-                    fj_pair_back(fc, rE, Y, cf, fu, fs, sh);
-#endif
-                    rE[0] = rEn[0]; rE[1] = rEn[1];
-                    Y[0] = Yn[0]; Y[1] = Yn[1]; Y[2] = Yn[2]; Y[3] = Yn[3];
-                    cf = cfn;
-                }
-                fj_pair_back(fc, rE, Y, cf, fu, fs, sh);
-            }
-#else
 #pragma unroll kFjUnroll
             for (int k = lane; k < mv.n; k += stride) {
                 const double k2 = f_fma(c.xi, mv.pc2[k], mv.p2[k]);
                 fj_pair_fast(fc, c.M2[0], c.M2[2], k2, mv.coef[k], fu, fs, sh);
             }
-#endif
 #pragma unroll
             for (int q = 0; q < 5; ++q) {
                 acc[3 * q + 0] = fu[q];
@@ -979,13 +870,25 @@ PNJL_HD void thermo_partial(const Model& m, bool isospin, const PointCtx& c, con
         const bool iso = isospin && x[0] == x[1];
         if (iso) {
             double d0 = 0, d1 = 0, dg[2] = {0, 0};
+            if (one_log_ok(c.T, c.mu)) {
 #pragma unroll 1
-            for (int k = lane; k < mv.n; k += stride) {
-                const double k2 = f_fma(c.xi, mv.pc2[k], mv.p2[k]);
-                th_pair_fast<false>(fc, c.mu, c.M2[0], c.M2[2], k2, mv.coef[k], t0, t2, d0, d1, dg);
-            }
+                for (int k = lane; k < mv.n; k += stride) {
+                    const double k2 = f_fma(c.xi, mv.pc2[k], mv.p2[k]);
+                    th_pair_fast<false, true>(fc, c.mu, c.M2[0], c.M2[2], k2, mv.coef[k], t0, t2, d0, d1, dg);
+                }
+                // t2[2] already holds 2 L_u + L_s; the combination below expects (L_u, L_d, L_s) = (t0, t1, t2)
 #pragma unroll
-            for (int q = 0; q < 4; ++q) t1[q] = t0[q];
+                for (int q = 0; q < 4; ++q) t1[q] = t0[q];
+                t0[2] = 0.0; t1[2] = 0.0;
+            } else {
+#pragma unroll 1
+                for (int k = lane; k < mv.n; k += stride) {
+                    const double k2 = f_fma(c.xi, mv.pc2[k], mv.p2[k]);
+                    th_pair_fast<false, false>(fc, c.mu, c.M2[0], c.M2[2], k2, mv.coef[k], t0, t2, d0, d1, dg);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) t1[q] = t0[q];
+            }
         } else {
             for (int k = lane; k < mv.n; k += stride) {
                 const double k2 = f_fma(c.xi, mv.pc2[k], mv.p2[k]);
@@ -1027,10 +930,18 @@ PNJL_HD bool ft_partial(const Model& m, bool isospin, const PointCtx& c, const d
     const bool iso = isospin && x[0] == x[1];
     if (iso) {
         double tu[4] = {0, 0, 0, 0}, ts[4] = {0, 0, 0, 0}, s1u = 0, s1s = 0, gsh[2] = {0, 0};
+        if (one_log_ok(c.T, c.mu)) {
 #pragma unroll 1
-        for (int k = lane; k < mv.n; k += stride) {
-            const double k2 = f_fma(c.xi, mv.pc2[k], mv.p2[k]);
-            th_pair_fast<true>(fc, c.mu, c.M2[0], c.M2[2], k2, mv.coef[k], tu, ts, s1u, s1s, gsh);
+            for (int k = lane; k < mv.n; k += stride) {
+                const double k2 = f_fma(c.xi, mv.pc2[k], mv.p2[k]);
+                th_pair_fast<true, true>(fc, c.mu, c.M2[0], c.M2[2], k2, mv.coef[k], tu, ts, s1u, s1s, gsh);
+            }
+        } else {
+#pragma unroll 1
+            for (int k = lane; k < mv.n; k += stride) {
+                const double k2 = f_fma(c.xi, mv.pc2[k], mv.p2[k]);
+                th_pair_fast<true, false>(fc, c.mu, c.M2[0], c.M2[2], k2, mv.coef[k], tu, ts, s1u, s1s, gsh);
+            }
         }
         facc[0] = s1u; facc[1] = s1u; facc[2] = s1s;
         facc[3] = gsh[0]; facc[4] = gsh[1];

@@ -312,6 +312,12 @@ def test_isotropic_collapse_equals_full_mesh(p_num, t_num):
         assert err.max() <= 1e-9, (q, err.max(), int(err.argmax()), a[err.argmax(), q], b[err.argmax(), q])
     res = o.scan_lines(muq, np.zeros(16), Tg, tables, tidx)
     assert_state_parity(a, res, label="collapse-lines")
+    # an all-isotropic host batch is run in the layout that fits p_num nodes; a mixed batch keeps the handle's layout
+    # (the warp-specialised kernel reports 32 x parts lanes when it splits passes over several workers)
+    full_layout = (lambda v: v == 8) if p_num * t_num <= 96 else (lambda v: v >= 32)
+    assert ec.stats()["lanes_per_solve"] == 8 and full_layout(ef.stats()["lanes_per_solve"])
+    ec.scan_lines(muq[:4], np.array([0.0, 0.0, 0.2, 0.0]), Tg[:4], tidx[:4])
+    assert full_layout(ec.stats()["lanes_per_solve"])
 
 
 @pytest.mark.parametrize("schedule,parts", [(0, 1), (0, 2), (0, 4), (1, 1)])
