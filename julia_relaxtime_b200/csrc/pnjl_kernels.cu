@@ -498,6 +498,42 @@ struct CtrlSink {
     }
 };
 
+// Warp sum of N per-lane values with N/2 + N/4 + ... shuffles instead of 5 N ("transposed" butterfly): at the step
+// with lane offset OFF the lanes whose OFF bit is clear keep the first half of the values and the others the second
+// half; each lane sends the half it gives up and adds what it receives to the half it keeps.  Every kept value is
+// a(l) + a(l ^ OFF) exactly as in the plain xor butterfly (v += shfl_xor(v, off), off = 16 .. 1), so after five steps
+// the sums are bit-identical to that butterfly's; they end up spread over the lanes: `idx` is the index of the one
+// sum this lane holds in v[0], `valid` is false for the lanes that hold padding.
+template <int N, int OFF>
+struct WarpSumT {
+    static __device__ __forceinline__ void run(double* v, int lane, int& idx, bool& valid) {
+        constexpr int H = (N + 1) / 2;
+        const bool up = (lane & OFF) != 0;
+#pragma unroll
+        for (int j = 0; j < H; ++j) {
+            const double hi = (H + j < N) ? v[H + j] : 0.0;
+            const double keep = up ? hi : v[j];
+            const double send = up ? v[j] : hi;
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+        }
+        WarpSumT<H, OFF / 2>::run(v, lane, idx, valid);
+        idx += up ? H : 0;
+        valid = valid && idx < N;
+    }
+};
+template <int N>
+struct WarpSumT<N, 0> {
+    static_assert(N == 1, "at most 32 values");
+    static __device__ __forceinline__ void run(double*, int, int& idx, bool& valid) { idx = 0; valid = true; }
+};
+template <int N>
+__device__ __forceinline__ void warp_sum_store(double (&v)[N], int lane, double* out) {
+    int idx;
+    bool valid;
+    WarpSumT<N, 16>::run(v, lane, idx, valid);
+    if (valid) out[idx] = v[0];
+}
+
 // One quadrature pass (or one part of it: nodes lane + 32 part, stride 32 parts) of a worker warp for mailbox `sl`;
 // the warp-reduced sums go to out[0..20].
 __device__ __noinline__ void ws_worker_pass(const DeviceConfig* cfg, const MeshView& mv, const WsSlot* sl, int type, int lane,
@@ -513,41 +549,16 @@ __device__ __noinline__ void ws_worker_pass(const DeviceConfig* cfg, const MeshV
     if (type == WS_FJ) {
         double acc[kFJAcc];
         const bool fast = fj_partial(cfg->m, iso, c, x, mv, l0, stride, acc);
-#pragma unroll
-        for (int i = 0; i < kFJAcc; ++i) {
-            double v = acc[i];
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-            if (lane == 0) out[i] = v;
-        }
+        warp_sum_store(acc, lane, out);
         if (lane == 0) out[20] = fast ? 1.0 : 0.0;
     } else if (type == WS_FT) {
-        double facc[kFtAcc], tacc[kThAcc];
-        ft_partial(cfg->m, iso, c, x, mv, l0, stride, facc, tacc);
-#pragma unroll
-        for (int i = 0; i < kFtAcc; ++i) {
-            double v = facc[i];
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-            if (lane == 0) out[i] = v;
-        }
-#pragma unroll
-        for (int i = 0; i < kThAcc; ++i) {
-            double v = tacc[i];
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-            if (lane == 0) out[kFtAcc + i] = v;
-        }
+        double acc[kFtAcc + kThAcc];
+        ft_partial(cfg->m, iso, c, x, mv, l0, stride, acc, acc + kFtAcc);
+        warp_sum_store(acc, lane, out);
     } else {
         double tacc[kThAcc];
         thermo_partial(cfg->m, iso, c, x, mv, l0, stride, tacc);
-#pragma unroll
-        for (int i = 0; i < kThAcc; ++i) {
-            double v = tacc[i];
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-            if (lane == 0) out[i] = v;
-        }
+        warp_sum_store(tacc, lane, out);
     }
 }
 

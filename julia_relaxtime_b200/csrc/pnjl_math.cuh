@@ -501,10 +501,11 @@ PNJL_HD void species4_fast(const FastCtx& fc, const double Y[4], Species4& o, bo
         g[s] = f_fma(Y[s], f_fma(2.0, P2, Y[s]), P1);
     }
     if (need_q) {
+        // q - g = 2 y (P2 + y) in these (y-stripped) forms, so q/f = n + r2 (2 P2 + 2 y): two instructions instead of three
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
-            const double P1 = (s & 1) ? fc.Phib : fc.Phi, P24 = (s & 1) ? fc.Phi4 : fc.Phib4;
-            q[s] = f_fma(Y[s], f_fma(3.0, Y[s], P24), P1);
+            const double P22 = (s & 1) ? fc.Phi2 : fc.Phib2;
+            q[s] = f_fma(2.0, Y[s], P22);
         }
     }
     v_rcp<4>(o.f, inv);
@@ -516,7 +517,7 @@ PNJL_HD void species4_fast(const FastCtx& fc, const double Y[4], Species4& o, bo
     for (int s = 0; s < 4; ++s) o.n[s] = g[s] * o.r1[s];
     if (need_q) {
 #pragma unroll
-        for (int s = 0; s < 4; ++s) o.qf[s] = q[s] * o.r1[s];
+        for (int s = 0; s < 4; ++s) o.qf[s] = f_fma(q[s], o.r2[s], o.n[s]);
     }
 }
 
