@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define PNJL_ABI_VERSION 6
+#define PNJL_ABI_VERSION 7
 
 /* ---- result record layout (doubles) --------------------------------------------------------- */
 #define PNJL_REC_DOUBLES 32
@@ -174,6 +174,44 @@ int pnjl_tmu_scan_host(pnjl_handle* h, int64_t n_lines, const double* T_MeV, con
 int pnjl_tmu_scan_device(pnjl_handle* h, int64_t n_lines, const double* d_T_MeV, const double* d_xi,
                          const int32_t* d_table_idx, int32_t n_mu, const double* d_mu_MeV, double* d_records,
                          void* stream);
+
+/* ---- one-loop integral A and effective couplings (the per-point step after the gap solve) ------------------------
+ * build_K_data of scripts/relaxtime/run_gap_transport_scan.jl:297-305:
+ *     A_f = OneLoopIntegrals.A(m_f, mu, T, Phi, Phibar, nodes, weights)            src/relaxtime/OneLoopIntegrals.jl:531-543
+ *     G_f = calculate_G_from_A(A_f, m_f)                                           src/relaxtime/EffectiveCouplings.jl:56-60
+ *     K   = calculate_effective_couplings(G_fm2, K_fm5, G_u, G_s)                  EffectiveCouplings.jl:232-279
+ * One 16-double AUX record per point (a Julia Matrix{Float64}(16, n)), offsets PNJL_AUX_* below.  The quadrature rule is
+ * the handle's one-loop rule: gauleg(0, 10, 64) = DEFAULT_MOMENTUM_NODES/WEIGHTS (src/integration/GaussLegendre.jl:170)
+ * unless replaced with pnjl_set_oneloop_rule (the reference's A takes the rule as an argument). */
+#define PNJL_AUX_DOUBLES 16
+#define PNJL_AUX_A_U 0
+#define PNJL_AUX_A_S 1
+#define PNJL_AUX_G_U 2
+#define PNJL_AUX_G_S 3
+#define PNJL_AUX_K0_PLUS 4
+#define PNJL_AUX_K0_MINUS 5
+#define PNJL_AUX_K123_PLUS 6
+#define PNJL_AUX_K123_MINUS 7
+#define PNJL_AUX_K4567_PLUS 8
+#define PNJL_AUX_K4567_MINUS 9
+#define PNJL_AUX_K8_PLUS 10
+#define PNJL_AUX_K8_MINUS 11
+#define PNJL_AUX_K08_PLUS 12
+#define PNJL_AUX_K08_MINUS 13
+#define PNJL_AUX_DETK_PLUS 14
+#define PNJL_AUX_DETK_MINUS 15
+#define PNJL_MAX_ONELOOP_NODES 512
+int pnjl_set_oneloop_rule(pnjl_handle* h, int32_t n_nodes, const double* nodes, const double* weights);
+/* n independent states given as arrays (what a caller of A(m, mu, T, Phi, Phibar, ...) has at hand). */
+int pnjl_effective_couplings_host(pnjl_handle* h, int64_t n, const double* T_fm, const double* mu_fm, const double* m_u,
+                                  const double* m_s, const double* Phi, const double* Phibar, double* aux);
+/* From result records on the device (masses, Phi, Phibar, T, mu are read from each record): d_aux [n][16]. */
+int pnjl_effective_couplings_device(pnjl_handle* h, int64_t n, const double* d_records, double* d_aux, void* stream);
+/* pnjl_scan_lines_host followed by the couplings of every point, one call and one round trip: records [n_lines][n_T][32],
+ * aux [n_lines][n_T][16]. */
+int pnjl_scan_lines_couplings_host(pnjl_handle* h, int64_t n_lines, const double* muq_MeV, const double* xi,
+                                   const int32_t* table_idx, int32_t n_T, const double* T_MeV, double* records,
+                                   double* aux);
 
 /* Single Omega-gradient/Jacobian evaluation at given states (test hook for per-iterate parity):
  * FJ: [n][30] = F[5] then J[5][5] row-major. */

@@ -3,7 +3,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 REC_DOUBLES = 32
 REC_X, REC_MASS, REC_OMEGA, REC_PRESSURE, REC_RHO_NORM, REC_ENTROPY, REC_ENERGY = 0, 5, 8, 9, 10, 11, 12
 REC_NQ, REC_NQBAR, REC_RESNORM, REC_ITER, REC_STATUS, REC_NEVAL, REC_RHO, REC_NTHERMO = 13, 16, 19, 20, 21, 22, 23, 26
@@ -12,6 +12,11 @@ REC_T, REC_MU, REC_XI, REC_NFUSED = 27, 28, 29, 30
 ST_CONVERGED, ST_USED_TR, ST_TR_ATTEMPTED, ST_USED_MULTISEED = 1, 2, 4, 8
 ST_SEED_SHIFT, ST_SEED_MASK, ST_PHASE_SWITCH, ST_NONFINITE, ST_ALL_SEEDS_FAILED = 4, 0x70, 128, 256, 512
 ST_PROMOTED, ST_REFINED, ST_CAND_SHIFT, ST_CAND_MASK, ST_NO_RESULT = 1024, 2048, 12, 0x3000, 16384
+
+AUX_DOUBLES = 16
+AUX_NAMES = ("A_u", "A_s", "G_u", "G_s", "K0_plus", "K0_minus", "K123_plus", "K123_minus", "K4567_plus", "K4567_minus",
+             "K8_plus", "K8_minus", "K08_plus", "K08_minus", "det_K_plus", "det_K_minus")
+AUX = {name: i for i, name in enumerate(AUX_NAMES)}
 
 SEED_EXPLICIT, SEED_AUTO, SEED_MULTI = 0, 1, 2
 MAX_TABLES, MAX_TABLE_ROWS = 8, 64

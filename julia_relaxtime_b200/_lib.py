@@ -78,6 +78,10 @@ def load():
     L.pnjl_tmu_scan_host.argtypes = [H, C.c_int64, dp, dp, ip, C.c_int32, dp, dp]
     L.pnjl_tmu_scan_device.argtypes = [H, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                        C.c_void_p, C.c_void_p]
+    L.pnjl_set_oneloop_rule.argtypes = [H, C.c_int32, dp, dp]
+    L.pnjl_effective_couplings_host.argtypes = [H, C.c_int64, dp, dp, dp, dp, dp, dp, dp]
+    L.pnjl_effective_couplings_device.argtypes = [H, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pnjl_scan_lines_couplings_host.argtypes = [H, C.c_int64, dp, dp, ip, C.c_int32, dp, dp, dp]
     L.pnjl_eval_fj_host.argtypes = [H, C.c_int64, dp, dp, dp, dp, dp]
     L.pnjl_selftest_math.argtypes = [H, C.c_int64, dp, C.c_int32, dp]
     L.pnjl_get_stats.argtypes = [H, C.POINTER(_abi.PnjlStats)]
@@ -91,7 +95,8 @@ def load():
 EXPORTED_SYMBOLS = [
     "pnjl_default_config", "pnjl_abi_version", "pnjl_last_error", "pnjl_create", "pnjl_destroy", "pnjl_gauleg",
     "pnjl_solve_points_host", "pnjl_solve_points_device", "pnjl_set_boundaries", "pnjl_scan_lines_host",
-    "pnjl_scan_lines_device", "pnjl_tmu_scan_host", "pnjl_tmu_scan_device", "pnjl_eval_fj_host", "pnjl_selftest_math", "pnjl_get_stats", "pnjl_measure_fp64_peak"]
+    "pnjl_scan_lines_device", "pnjl_set_oneloop_rule", "pnjl_effective_couplings_host",
+    "pnjl_effective_couplings_device", "pnjl_scan_lines_couplings_host", "pnjl_tmu_scan_host", "pnjl_tmu_scan_device", "pnjl_eval_fj_host", "pnjl_selftest_math", "pnjl_get_stats", "pnjl_measure_fp64_peak"]
 
 
 def gauleg(a, b, n):
@@ -196,6 +201,46 @@ class Engine:
                                                 int(T_MeV.size), _abi.dptr(T_MeV), _abi.dptr(rec)),
                     "pnjl_scan_lines_host")
         return rec
+
+    def scan_lines_couplings(self, muq_MeV, xi, T_MeV, table_idx=None):
+        """scan_lines plus build_K_data of every point in the same call: (records [L][T][32], aux [L][T][16])."""
+        muq_MeV = _abi.as_f64(muq_MeV)
+        n_lines = muq_MeV.size
+        xi = _abi.as_f64(xi, n_lines)
+        T_MeV = _abi.as_f64(T_MeV)
+        ti = None
+        if table_idx is not None:
+            table_idx = np.ascontiguousarray(table_idx, dtype=np.int32)
+            ti = _abi.iptr(table_idx)
+        rec = np.empty((n_lines, T_MeV.size, _abi.REC_DOUBLES))
+        aux = np.empty((n_lines, T_MeV.size, _abi.AUX_DOUBLES))
+        self._check(self.L.pnjl_scan_lines_couplings_host(self.h, n_lines, _abi.dptr(muq_MeV), _abi.dptr(xi), ti,
+                                                          int(T_MeV.size), _abi.dptr(T_MeV), _abi.dptr(rec), _abi.dptr(aux)),
+                    "pnjl_scan_lines_couplings_host")
+        return rec, aux
+
+    def set_oneloop_rule(self, nodes, weights):
+        """Quadrature rule of the one-loop integral A (default gauleg(0, 10, 64) = DEFAULT_MOMENTUM_NODES/WEIGHTS)."""
+        nodes, weights = _abi.as_f64(nodes), _abi.as_f64(weights)
+        if nodes.size != weights.size:
+            raise ValueError("nodes and weights differ in length")
+        self._check(self.L.pnjl_set_oneloop_rule(self.h, int(nodes.size), _abi.dptr(nodes), _abi.dptr(weights)),
+                    "pnjl_set_oneloop_rule")
+
+    def effective_couplings(self, T_fm, mu_fm, m_u, m_s, Phi, Phibar):
+        """A_u, A_s, G_u, G_s and the 12 effective couplings of n states: aux [n][16] (columns _abi.AUX_NAMES)."""
+        T_fm = _abi.as_f64(T_fm)
+        n = T_fm.size
+        arrs = [T_fm] + [_abi.as_f64(a, n) for a in (mu_fm, m_u, m_s, Phi, Phibar)]
+        aux = np.empty((n, _abi.AUX_DOUBLES))
+        self._check(self.L.pnjl_effective_couplings_host(self.h, n, *[_abi.dptr(a) for a in arrs], _abi.dptr(aux)),
+                    "pnjl_effective_couplings_host")
+        return aux
+
+    def effective_couplings_device(self, d_records, d_aux, stream=0):
+        n = d_records.numel() // _abi.REC_DOUBLES
+        self._check(self.L.pnjl_effective_couplings_device(self.h, n, d_records.data_ptr(), d_aux.data_ptr(),
+                                                           C.c_void_p(stream)), "pnjl_effective_couplings_device")
 
     def tmu_scan(self, T_MeV, xi, mu_MeV, table_idx=None, out=None):
         """TmuScan semantics: line l = (xi[l], T_MeV[l]) marches mu_MeV; records [n_lines][n_mu][32]."""

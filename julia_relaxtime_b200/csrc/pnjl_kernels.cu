@@ -778,6 +778,32 @@ __global__ void __launch_bounds__(512, 1) k_eval_fj(const DeviceConfig* __restri
     ev.drain();
 }
 
+// ---- one-loop integral A + effective couplings (build_K_data step of the scan script) ---------------------------
+// One thread per point: n_rule nodes x 2 flavours in a register loop, rule (p^2, w p^2) in shared memory.  Inputs are
+// strided so that the same kernel reads either result records (stride 32) or plain arrays (stride 1).
+struct CouplingsIn {
+    const double* T; const double* mu; const double* m_u; const double* m_s; const double* Phi; const double* Phib;
+    int stride;
+};
+__global__ void __launch_bounds__(128) k_couplings(const DeviceConfig* __restrict__ cfg, const double* __restrict__ g_rule, int n_rule,
+                                                   long long n, CouplingsIn in, double* __restrict__ aux) {
+    extern __shared__ double s_rule[];
+    for (int i = threadIdx.x; i < 2 * n_rule; i += blockDim.x) s_rule[i] = g_rule[i];
+    __syncthreads();
+    const Model& m = cfg->m;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long o = i * in.stride;
+        const double T = in.T[o], mu = in.mu[o], mq = in.m_u[o], ms = in.m_s[o], P = in.Phi[o], Pb = in.Phib[o];
+        const double A_u = oneloop_A(m.Lambda, mq, mu, T, P, Pb, n_rule, s_rule, s_rule + n_rule);
+        const double A_s = oneloop_A(m.Lambda, ms, mu, T, P, Pb, n_rule, s_rule, s_rule + n_rule);
+        double a[kAuxDoubles];
+        effective_couplings(m.G, m.K, m.Nc, mq, ms, A_u, A_s, a);
+        double* out = aux + i * kAuxDoubles;
+#pragma unroll
+        for (int q = 0; q < kAuxDoubles; q += 2) *reinterpret_cast<double2*>(out + q) = make_double2(a[q], a[q + 1]);
+    }
+}
+
 // ---- FP64 FMA peak microbenchmark ----------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double seed) {
     double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
@@ -902,7 +928,9 @@ struct pnjl_handle {
     unsigned long long* d_counter = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    DevBuf in_T, in_mu, in_xi, in_seeds, in_idx, in_x, out_rec;
+    DevBuf in_T, in_mu, in_xi, in_seeds, in_idx, in_x, out_rec, out_aux, in_c[6];
+    double* d_rule = nullptr;      // one-loop rule: p^2 [n] | w p^2 [n]
+    int n_rule = 0;
     pnjl_stats stats;
 };
 
@@ -1288,6 +1316,13 @@ int pnjl_create(const pnjl_config* c, pnjl_handle** out) {
     CREATE_TRY(cudaMemcpy(h->d_mesh, mesh.data(), sizeof(double) * mesh.size(), cudaMemcpyHostToDevice));
 #undef CREATE_TRY
     *out = h;
+    {
+        // default one-loop rule = DEFAULT_MOMENTUM_NODES / WEIGHTS = gauleg(0, 10, 64)   (GaussLegendre.jl:121,170)
+        std::vector<double> x(64), w(64);
+        int rc = pnjl_gauleg(0.0, 10.0, 64, x.data(), w.data());
+        if (!rc) rc = pnjl_set_oneloop_rule(h, 64, x.data(), w.data());
+        if (rc) { *out = nullptr; pnjl_destroy(h); return rc; }
+    }
     return PNJL_OK;
 }
 
@@ -1309,7 +1344,9 @@ void pnjl_destroy(pnjl_handle* h) {
     }
 #endif
     h->in_T.release(); h->in_mu.release(); h->in_xi.release(); h->in_seeds.release(); h->in_idx.release();
-    h->in_x.release(); h->out_rec.release();
+    h->in_x.release(); h->out_rec.release(); h->out_aux.release();
+    for (auto& b : h->in_c) b.release();
+    if (h->d_rule) cudaFree(h->d_rule);
     if (h->d_cfg) cudaFree(h->d_cfg);
     if (h->d_mesh) cudaFree(h->d_mesh);
     if (h->d_counter) cudaFree(h->d_counter);
@@ -1437,6 +1474,99 @@ int pnjl_scan_lines_host(pnjl_handle* h, int64_t n_lines, const double* muq, con
     float ms = 0;
     CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     h->stats.kernel_ms = ms;
+    return PNJL_OK;
+}
+
+int pnjl_set_oneloop_rule(pnjl_handle* h, int32_t n_nodes, const double* nodes, const double* weights) {
+    if (!h) return fail(PNJL_ERR_ARG, "null handle");
+    if (n_nodes < 1 || n_nodes > PNJL_MAX_ONELOOP_NODES) return fail(PNJL_ERR_ARG, "one-loop rule: need 1 <= n_nodes <= 512");
+    if (!nodes || !weights) return fail(PNJL_ERR_ARG, "null buffer");
+    DeviceGuard guard(h->device);
+    std::vector<double> r(2 * (size_t)n_nodes);
+    for (int i = 0; i < n_nodes; ++i) {
+        r[i] = nodes[i] * nodes[i];
+        r[n_nodes + i] = weights[i] * (nodes[i] * nodes[i]);     // weight_p * node_p^2   OneLoopIntegrals.jl:540
+    }
+    if (h->stream) CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (h->d_rule) cudaFree(h->d_rule);
+    h->d_rule = nullptr;
+    CUDA_TRY(cudaMalloc(&h->d_rule, sizeof(double) * r.size()));
+    CUDA_TRY(cudaMemcpy(h->d_rule, r.data(), sizeof(double) * r.size(), cudaMemcpyHostToDevice));
+    h->n_rule = n_nodes;
+    return PNJL_OK;
+}
+
+namespace {
+int launch_couplings(pnjl_handle* h, long long n, const CouplingsIn& in, double* d_aux, cudaStream_t st) {
+    const int threads = 128;
+    long long blocks = (n + threads - 1) / threads;
+    const long long cap = (long long)h->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    k_couplings<<<(int)blocks, threads, sizeof(double) * 2 * h->n_rule, st>>>(h->d_cfg, h->d_rule, h->n_rule, n, in, d_aux);
+    CUDA_TRY(cudaGetLastError());
+    h->stats.kernel_launches += 1;
+    return PNJL_OK;
+}
+}  // namespace
+
+int pnjl_effective_couplings_device(pnjl_handle* h, int64_t n, const double* d_records, double* d_aux, void* stream) {
+    if (!h) return fail(PNJL_ERR_ARG, "null handle");
+    if (n < 0) return fail(PNJL_ERR_ARG, "negative size");
+    h->stats.kernel_launches = 0;
+    if (n == 0) return PNJL_OK;
+    if (!d_records || !d_aux) return fail(PNJL_ERR_ARG, "null buffer");
+    DeviceGuard guard(h->device);
+    CouplingsIn in{d_records + PNJL_REC_T, d_records + PNJL_REC_MU, d_records + PNJL_REC_MASS, d_records + PNJL_REC_MASS + 2,
+                   d_records + PNJL_REC_X + 3, d_records + PNJL_REC_X + 4, PNJL_REC_DOUBLES};
+    return launch_couplings(h, n, in, d_aux, (cudaStream_t)stream);
+}
+
+int pnjl_effective_couplings_host(pnjl_handle* h, int64_t n, const double* T_fm, const double* mu_fm, const double* m_u,
+                                  const double* m_s, const double* Phi, const double* Phibar, double* aux) {
+    if (!h) return fail(PNJL_ERR_ARG, "null handle");
+    if (n < 0) return fail(PNJL_ERR_ARG, "negative size");
+    h->stats.kernel_launches = 0;
+    if (n == 0) return PNJL_OK;
+    if (!T_fm || !mu_fm || !m_u || !m_s || !Phi || !Phibar || !aux) return fail(PNJL_ERR_ARG, "null buffer");
+    DeviceGuard guard(h->device);
+    const double* src[6] = {T_fm, mu_fm, m_u, m_s, Phi, Phibar};
+    const size_t nb = sizeof(double) * (size_t)n;
+    cudaStream_t st = h->stream;
+    for (int q = 0; q < 6; ++q) {
+        CUDA_TRY(h->in_c[q].reserve(nb));
+        CUDA_TRY(cudaMemcpyAsync(h->in_c[q].p, src[q], nb, cudaMemcpyHostToDevice, st));
+    }
+    CUDA_TRY(h->out_aux.reserve(nb * PNJL_AUX_DOUBLES));
+    CouplingsIn in{(const double*)h->in_c[0].p, (const double*)h->in_c[1].p, (const double*)h->in_c[2].p,
+                   (const double*)h->in_c[3].p, (const double*)h->in_c[4].p, (const double*)h->in_c[5].p, 1};
+    CUDA_TRY(cudaEventRecord(h->ev0, st));
+    int rc = launch_couplings(h, n, in, (double*)h->out_aux.p, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(h->ev1, st));
+    CUDA_TRY(cudaMemcpyAsync(aux, h->out_aux.p, nb * PNJL_AUX_DOUBLES, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->stats.kernel_ms = ms;
+    return PNJL_OK;
+}
+
+int pnjl_scan_lines_couplings_host(pnjl_handle* h, int64_t n_lines, const double* muq, const double* xi, const int32_t* tidx,
+                                   int32_t n_T, const double* T_MeV, double* records, double* aux) {
+    if (!aux) return fail(PNJL_ERR_ARG, "null buffer");
+    // the scan itself (records stay resident in out_rec), then the couplings of every record on the same stream
+    int rc = pnjl_scan_lines_host(h, n_lines, muq, xi, tidx, n_T, T_MeV, records);
+    if (rc || n_lines == 0 || n_T == 0) return rc;
+    DeviceGuard guard(h->device);
+    const long long n = (long long)n_lines * n_T;
+    const size_t nb = sizeof(double) * (size_t)n * PNJL_AUX_DOUBLES;
+    CUDA_TRY(h->out_aux.reserve(nb));
+    const long long scan_launches = h->stats.kernel_launches;
+    rc = pnjl_effective_couplings_device(h, n, (const double*)h->out_rec.p, (double*)h->out_aux.p, h->stream);
+    if (rc) return rc;
+    h->stats.kernel_launches += scan_launches;
+    CUDA_TRY(cudaMemcpyAsync(aux, h->out_aux.p, nb, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
     return PNJL_OK;
 }
 

@@ -1133,4 +1133,76 @@ PNJL_HD double wnorm5(const double d[5], const double v[5]) {
     return sqrt(s);
 }
 
+// ------------------------------------------------------------------------------------------------
+// One-loop integral A and the effective couplings K_alpha^+- (the per-point step that follows the gap solve in
+// scripts/relaxtime/run_gap_transport_scan.jl:297-305 `build_K_data`).
+//   A(m, mu, T, Phi, Phibar) = 4 [ -C(m) + sum_i w_i p_i^2 / E_i (f+(E_i) + f-(E_i)) ]     src/relaxtime/OneLoopIntegrals.jl:531-543
+//   C(m) = (Lambda sqrt(Lambda^2 + m^2) - m^2 ln((Lambda + sqrt(Lambda^2 + m^2)) / m)) / 2,  m -> max(m, 0); Lambda^2 / 2 below 1e-14   :507-517
+//   f+-  = PNJL occupation numbers (isotropic)                                                src/QuarkDistribution.jl:14-51
+//   G_f  = -Nc / (4 pi^2) m_f A_f                                                             src/relaxtime/EffectiveCouplings.jl:56-60
+//   K_alpha^+-, det K^+-                                                                      EffectiveCouplings.jl:232-279
+// The occupation number is written in the scale-free form (divide through by the largest power of y when y > 1), which
+// equals the reference's expression wherever that one is finite (its clamp(exp, 1e-200, 1e200) overflows in y^2 beyond
+// |a| > 354; this form does not).
+// ------------------------------------------------------------------------------------------------
+enum { AUX_A_U = 0, AUX_A_S, AUX_G_U, AUX_G_S, AUX_K0_P, AUX_K0_M, AUX_K123_P, AUX_K123_M, AUX_K4567_P, AUX_K4567_M,
+       AUX_K8_P, AUX_K8_M, AUX_K08_P, AUX_K08_M, AUX_DETK_P, AUX_DETK_M, kAuxDoubles };
+
+// n = (P1 y + 2 P2 y^2 + y^3) / (1 + 3 P1 y + 3 P2 y^2 + y^3), y = e^a
+PNJL_HD double pnjl_occupation(double a, double P1, double P2) {
+    const bool tame = (a >= -708.0) && (a <= 708.0);
+    const double na = -fabs(a);
+    const double w = tame ? fast_exp_nonpos(na) : exp(na);
+    double num, den;
+    if (a <= 0.0) {
+        num = w * (P1 + w * (2.0 * P2 + w));
+        den = 1.0 + w * (3.0 * P1 + w * (3.0 * P2 + w));
+    } else {
+        num = 1.0 + w * (2.0 * P2 + w * P1);
+        den = 1.0 + w * (3.0 * P2 + w * (3.0 * P1 + w));
+    }
+    return num / den;
+}
+
+PNJL_HD double oneloop_const_term_A(double Lam, double m) {
+    const double mp = m > 0.0 ? m : 0.0;
+    if (mp < 1e-14) return 0.5 * (Lam * Lam);
+    const double s = sqrt(Lam * Lam + mp * mp);
+    return 0.5 * (Lam * s - (mp * mp) * log((Lam + s) / mp));
+}
+
+// rule: p2[i] = p_i^2, wp2[i] = w_i p_i^2
+PNJL_HD double oneloop_A(double Lam, double m, double mu, double T, double Phi, double Phib, int n, const double* p2,
+                         const double* wp2) {
+    double acc = -oneloop_const_term_A(Lam, m);
+    const double iT = 1.0 / T;
+    const double m2 = m * m;
+    for (int i = 0; i < n; ++i) {
+        const double E = sqrt(p2[i] + m2);
+        const double fq = pnjl_occupation(-(E - mu) * iT, Phi, Phib);
+        const double fa = pnjl_occupation(-(E + mu) * iT, Phib, Phi);
+        acc += wp2[i] / E * (fq + fa);
+    }
+    return 4.0 * acc;
+}
+
+PNJL_HD void effective_couplings(double G, double K, double Nc, double m_u, double m_s, double A_u, double A_s,
+                                 double aux[kAuxDoubles]) {
+    const double pref = -Nc / (4.0 * (kPi * kPi));
+    const double G_u = pref * (m_u * A_u), G_s = pref * (m_s * A_s);
+    aux[AUX_A_U] = A_u; aux[AUX_A_S] = A_s; aux[AUX_G_U] = G_u; aux[AUX_G_S] = G_s;
+    const double t0 = (1.0 / 3.0) * K * (2.0 * G_u + G_s);
+    const double t123 = 0.5 * K * G_s;
+    const double t4567 = 0.5 * K * G_u;
+    const double t8 = (1.0 / 6.0) * K * (4.0 * G_u - G_s);
+    const double t08 = (1.0 / 6.0) * 1.4142135623730951 * K * (G_u - G_s);
+    aux[AUX_K0_P] = G - t0;         aux[AUX_K0_M] = G + t0;
+    aux[AUX_K123_P] = G + t123;     aux[AUX_K123_M] = G - t123;
+    aux[AUX_K4567_P] = G + t4567;   aux[AUX_K4567_M] = G - t4567;
+    aux[AUX_K8_P] = G + t8;         aux[AUX_K8_M] = G - t8;
+    aux[AUX_K08_P] = t08;           aux[AUX_K08_M] = -t08;
+    aux[AUX_DETK_P] = aux[AUX_K0_P] * aux[AUX_K8_P] - aux[AUX_K08_P] * aux[AUX_K08_P];
+    aux[AUX_DETK_M] = aux[AUX_K0_M] * aux[AUX_K8_M] - aux[AUX_K08_M] * aux[AUX_K08_M];
+}
+
 }  // namespace pnjl

@@ -280,3 +280,41 @@ def load_phase_tables(boundary_csv, cep_csv, xis):
         index[xi] = len(tables)
         tables.append((np.array([s[0] for s in sel]), np.array([s[1] for s in sel]), tcep))
     return tables, index
+
+
+def _oneloop_A(self, m, mu, T, Phi, Phib, nodes=None, weights=None):
+    """OneLoopIntegrals.A(m, mu, T, Phi, Phibar, nodes, weights); default rule = gauleg(0, 10, 64)."""
+    if nodes is None:
+        nodes, weights = self.gauleg(0.0, 10.0, 64)
+    nodes = np.ascontiguousarray(nodes, dtype=np.float64)
+    weights = np.ascontiguousarray(weights, dtype=np.float64)
+    self.lib.oracle_oneloop_A.restype = C.c_double
+    return self.lib.oracle_oneloop_A(C.byref(self.cfg), C.c_double(m), C.c_double(mu), C.c_double(T), C.c_double(Phi),
+                                     C.c_double(Phib), C.c_int32(nodes.size), _dp(nodes), _dp(weights))
+
+
+def _effective_couplings(self, G, K, G_u, G_s):
+    out = np.zeros(12)
+    self.lib.oracle_effective_couplings.restype = None
+    self.lib.oracle_effective_couplings(C.c_double(G), C.c_double(K), C.c_double(G_u), C.c_double(G_s), _dp(out))
+    return out
+
+
+def _couplings_batch(self, T, mu, m_u, m_s, Phi, Phib, nodes=None, weights=None):
+    """build_K_data for arrays of states: [n, 16] = A_u, A_s, G_u, G_s, K0+-, K123+-, K4567+-, K8+-, K08+-, detK+-."""
+    if nodes is None:
+        nodes, weights = self.gauleg(0.0, 10.0, 64)
+    arrs = [np.ascontiguousarray(np.atleast_1d(a), dtype=np.float64) for a in (T, mu, m_u, m_s, Phi, Phib)]
+    n = arrs[0].size
+    nodes = np.ascontiguousarray(nodes, dtype=np.float64)
+    weights = np.ascontiguousarray(weights, dtype=np.float64)
+    aux = np.zeros((n, 16))
+    self.lib.oracle_couplings_batch.restype = None
+    self.lib.oracle_couplings_batch(C.byref(self.cfg), C.c_int64(n), *[_dp(a) for a in arrs], C.c_int32(nodes.size),
+                                    _dp(nodes), _dp(weights), _dp(aux))
+    return aux
+
+
+Oracle.oneloop_A = _oneloop_A
+Oracle.effective_couplings = _effective_couplings
+Oracle.couplings_batch = _couplings_batch

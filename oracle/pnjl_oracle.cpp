@@ -1327,4 +1327,75 @@ int32_t oracle_num_threads(void) {
 #endif
 }
 
+// ---- one-loop integral A and effective couplings -------------------------------------------------------------------
+// Restated literally from the reference (clamped exponential, un-rescaled ratio):
+//   quark_distribution / antiquark_distribution          src/QuarkDistribution.jl:14-51
+//   const_integral_term_A, A                              src/relaxtime/OneLoopIntegrals.jl:507-543
+//   calculate_G_from_A, calculate_effective_couplings     src/relaxtime/EffectiveCouplings.jl:56-60, 232-279
+static double ref_clamp(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
+static double ref_quark_distribution(double E, double mu, double T, double Phi, double Phib) {
+    const double beta = 1.0 / T;
+    const double e1 = ref_clamp(std::exp(-(E - mu) * beta), 1e-200, 1e200);
+    const double e2 = e1 * e1, e3 = e2 * e1;
+    return (Phi * e1 + 2 * Phib * e2 + e3) / (1 + 3 * Phi * e1 + 3 * Phib * e2 + e3);
+}
+static double ref_antiquark_distribution(double E, double mu, double T, double Phi, double Phib) {
+    const double beta = 1.0 / T;
+    const double e1 = ref_clamp(std::exp(-(E + mu) * beta), 1e-200, 1e200);
+    const double e2 = e1 * e1, e3 = e2 * e1;
+    return (Phib * e1 + 2 * Phi * e2 + e3) / (1 + 3 * Phib * e1 + 3 * Phi * e2 + e3);
+}
+static double ref_const_integral_term_A(double Lam, double m) {
+    const double mp = std::max(m, 0.0);
+    if (mp < 1e-14) return (Lam * Lam) / 2.0;
+    const double term1 = Lam * std::sqrt(Lam * Lam + mp * mp);
+    const double term2 = mp * mp * std::log((Lam + std::sqrt(Lam * Lam + mp * mp)) / mp);
+    return (term1 - term2) / 2.0;
+}
+
+double oracle_oneloop_A(const oracle_config* c, double m, double mu, double T, double Phi, double Phib, int32_t n,
+                        const double* nodes, const double* weights) {
+    double integral = -ref_const_integral_term_A(c->Lambda, m);
+    for (int i = 0; i < n; ++i) {
+        const double p = nodes[i], w = weights[i];
+        const double E = std::sqrt(p * p + m * m);
+        const double dq = ref_quark_distribution(E, mu, T, Phi, Phib);
+        const double da = ref_antiquark_distribution(E, mu, T, Phi, Phib);
+        integral += w * (p * p) / E * (dq + da);
+    }
+    return 4.0 * integral;
+}
+
+// out[12] = K0+, K0-, K123+, K123-, K4567+, K4567-, K8+, K8-, K08+, K08-, detK+, detK-
+void oracle_effective_couplings(double G, double K, double G_u, double G_s, double* out) {
+    const double term_0 = (1.0 / 3.0) * K * (2.0 * G_u + G_s);
+    out[0] = G - term_0; out[1] = G + term_0;
+    const double term_123 = 0.5 * K * G_s;
+    out[2] = G + term_123; out[3] = G - term_123;
+    const double term_4567 = 0.5 * K * G_u;
+    out[4] = G + term_4567; out[5] = G - term_4567;
+    const double term_8 = (1.0 / 6.0) * K * (4.0 * G_u - G_s);
+    out[6] = G + term_8; out[7] = G - term_8;
+    const double term_08 = (1.0 / 6.0) * std::sqrt(2.0) * K * (G_u - G_s);
+    out[8] = term_08; out[9] = -term_08;
+    out[10] = out[0] * out[6] - out[8] * out[8];
+    out[11] = out[1] * out[7] - out[9] * out[9];
+}
+
+// build_K_data (run_gap_transport_scan.jl:297-305) for n states: aux [n][16] = A_u, A_s, G_u, G_s, then the 12 couplings.
+void oracle_couplings_batch(const oracle_config* c, int64_t n, const double* T, const double* mu, const double* m_u,
+                            const double* m_s, const double* Phi, const double* Phib, int32_t n_rule, const double* nodes,
+                            const double* weights, double* aux) {
+    const double pi = 3.14159265358979323846;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        double* a = aux + 16 * i;
+        a[0] = oracle_oneloop_A(c, m_u[i], mu[i], T[i], Phi[i], Phib[i], n_rule, nodes, weights);
+        a[1] = oracle_oneloop_A(c, m_s[i], mu[i], T[i], Phi[i], Phib[i], n_rule, nodes, weights);
+        a[2] = -c->Nc / (4.0 * pi * pi) * (m_u[i] * a[0]);
+        a[3] = -c->Nc / (4.0 * pi * pi) * (m_s[i] * a[1]);
+        oracle_effective_couplings(c->G, c->K, a[2], a[3], a + 4);
+    }
+}
+
 }  // extern "C"

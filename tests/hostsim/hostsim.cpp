@@ -188,4 +188,18 @@ void hostsim_scan_lines_mode(const pnjl_config* c, int64_t n_lines, const double
     delete pt;
 }
 
+// build_K_data through the product's header (oneloop_A + effective_couplings): aux [n][16]
+void hostsim_couplings(const pnjl_config* c, int64_t n, const double* T, const double* mu, const double* m_u, const double* m_s,
+                       const double* Phi, const double* Phib, int32_t n_rule, const double* nodes, const double* weights,
+                       double* aux) {
+    Model m = model_of(c);
+    std::vector<double> p2(n_rule), wp2(n_rule);
+    for (int i = 0; i < n_rule; ++i) { p2[i] = nodes[i] * nodes[i]; wp2[i] = weights[i] * (nodes[i] * nodes[i]); }
+    for (int64_t i = 0; i < n; ++i) {
+        const double A_u = oneloop_A(m.Lambda, m_u[i], mu[i], T[i], Phi[i], Phib[i], n_rule, p2.data(), wp2.data());
+        const double A_s = oneloop_A(m.Lambda, m_s[i], mu[i], T[i], Phi[i], Phib[i], n_rule, p2.data(), wp2.data());
+        effective_couplings(m.G, m.K, m.Nc, m_u[i], m_s[i], A_u, A_s, aux + 16 * i);
+    }
+}
+
 }  // extern "C"

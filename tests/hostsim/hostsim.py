@@ -94,3 +94,12 @@ class HostSim:
                                          _abi.iptr(table_idx), C.c_int32(T_MeV.size), _abi.dptr(T_MeV),
                                          C.c_int32(len(tables)), ctabs, _abi.dptr(rec), C.c_int32(mode))
         return rec
+
+    def couplings(self, T, mu, m_u, m_s, Phi, Phib, nodes, weights):
+        arrs = [_abi.as_f64(a) for a in (T, mu, m_u, m_s, Phi, Phib)]
+        n = arrs[0].size
+        nodes, weights = _abi.as_f64(nodes), _abi.as_f64(weights)
+        aux = np.zeros((n, 16))
+        self.lib.hostsim_couplings(C.byref(self.cfg), C.c_int64(n), *[_abi.dptr(a) for a in arrs], C.c_int32(nodes.size),
+                                   _abi.dptr(nodes), _abi.dptr(weights), _abi.dptr(aux))
+        return aux
