@@ -17,6 +17,7 @@ using StaticArrays
 const LIB = get(ENV, "PNJL_B200_LIB", joinpath(@__DIR__, "..", "julia_relaxtime_b200", "csrc", "_build", "libpnjl_b200.so"))
 
 const REC = 32                       # doubles per result record (PNJL_REC_DOUBLES)
+const AUX = 16                       # doubles per couplings record (PNJL_AUX_DOUBLES)
 const ST_CONVERGED = 1
 const ST_ALL_SEEDS_FAILED = 512
 const SEED_EXPLICIT, SEED_AUTO, SEED_MULTI = Int32(0), Int32(1), Int32(2)
@@ -34,6 +35,7 @@ struct Config
     predict_tol::Cdouble
     isospin_symmetric::Int32
     schedule::Int32
+    isotropic_collapse::Int32
 end
 
 struct Boundary                      # struct pnjl_boundary
@@ -65,7 +67,7 @@ function Engine(; p_num::Int=64, t_num::Int=8, iterations::Int=1000, trust_regio
                  C.a0, C.a1, C.a2, C.b3, C.ρ0_inv_fm3, Int32(C.N_color), Int32(p_num), Int32(t_num),
                  pointer(pn), pointer(pw), pointer(cn), pointer(cw),
                  1e-9, 1e-9, residual_norm_max, 1e-8, Int32(iterations), Int32(trust_region_fallback),
-                 Int32(auto_multiseed_fallback), 1e-12, Int32(device), Int32(0), 1e-4, Int32(1), Int32(0))
+                 Int32(auto_multiseed_fallback), 1e-12, Int32(device), Int32(0), 1e-4, Int32(1), Int32(0), Int32(1))
     h = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve pn pw cn cw begin
         check(ccall((:pnjl_create, LIB), Cint, (Ref{Config}, Ref{Ptr{Cvoid}}), cfg, h), "pnjl_create")
@@ -108,6 +110,55 @@ function scan_lines(e::Engine, muq_MeV::Vector{Float64}, xi::Vector{Float64}, ta
                 (Ptr{Cvoid}, Int64, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Int32}, Int32, Ptr{Cdouble}, Ptr{Cdouble}),
                 e.handle, nl, muq_MeV, xi, table_idx, Int32(nT), T_MeV, rec), "pnjl_scan_lines_host")
     return rec
+end
+
+"""T-mu scan with TmuScan.run_tmu_scan semantics (src/pnjl/scans/TmuScan.jl:120-234): line l = (xi[l], T_MeV[l]) marches
+`mu_MeV` in the given order.  Returns `Array{Float64}(32, n_mu, n_lines)`; rows with `PNJL_ST_NO_RESULT` (bit 16384) are
+the reference's all-NaN rows."""
+function tmu_scan(e::Engine, T_MeV::Vector{Float64}, xi::Vector{Float64}, table_idx::Vector{Int32}, mu_MeV::Vector{Float64})
+    nl, nmu = length(T_MeV), length(mu_MeV)
+    rec = Array{Float64}(undef, REC, nmu, nl)
+    check(ccall((:pnjl_tmu_scan_host, LIB), Cint,
+                (Ptr{Cvoid}, Int64, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Int32}, Int32, Ptr{Cdouble}, Ptr{Cdouble}),
+                e.handle, nl, T_MeV, xi, table_idx, Int32(nmu), mu_MeV, rec), "pnjl_tmu_scan_host")
+    return rec
+end
+
+# ---- one-loop integral A and effective couplings (build_K_data, run_gap_transport_scan.jl:297-305) -----------------
+"""Replace the rule of A (default: DEFAULT_MOMENTUM_NODES / DEFAULT_MOMENTUM_WEIGHTS)."""
+function set_oneloop_rule!(e::Engine, nodes::Vector{Float64}, weights::Vector{Float64})
+    check(ccall((:pnjl_set_oneloop_rule, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Cdouble}, Ptr{Cdouble}),
+                e.handle, Int32(length(nodes)), nodes, weights), "pnjl_set_oneloop_rule")
+end
+
+"""`Matrix{Float64}(16, n)`: rows A_u, A_s, G_u, G_s, K0±, K123±, K4567±, K8±, K08±, det K± (PNJL_AUX_*)."""
+function effective_couplings(e::Engine, T_fm::Vector{Float64}, mu_fm::Vector{Float64}, m_u::Vector{Float64},
+                             m_s::Vector{Float64}, Phi::Vector{Float64}, Phibar::Vector{Float64})
+    n = length(T_fm)
+    aux = Matrix{Float64}(undef, AUX, n)
+    check(ccall((:pnjl_effective_couplings_host, LIB), Cint,
+                (Ptr{Cvoid}, Int64, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+                e.handle, n, T_fm, mu_fm, m_u, m_s, Phi, Phibar, aux), "pnjl_effective_couplings_host")
+    return aux
+end
+
+"""`scan_lines` plus the couplings of every point in one call: `(rec(32, n_T, n_lines), aux(16, n_T, n_lines))`."""
+function scan_lines_couplings(e::Engine, muq_MeV::Vector{Float64}, xi::Vector{Float64}, table_idx::Vector{Int32},
+                              T_MeV::Vector{Float64})
+    nl, nT = length(muq_MeV), length(T_MeV)
+    rec = Array{Float64}(undef, REC, nT, nl)
+    aux = Array{Float64}(undef, AUX, nT, nl)
+    check(ccall((:pnjl_scan_lines_couplings_host, LIB), Cint,
+                (Ptr{Cvoid}, Int64, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Int32}, Int32, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+                e.handle, nl, muq_MeV, xi, table_idx, Int32(nT), T_MeV, rec, aux), "pnjl_scan_lines_couplings_host")
+    return rec, aux
+end
+
+"""The script's `build_K_data` NamedTuple from one couplings record."""
+function k_data(a::AbstractVector{Float64})
+    K = (K0_plus=a[5], K0_minus=a[6], K123_plus=a[7], K123_minus=a[8], K4567_plus=a[9], K4567_minus=a[10],
+         K8_plus=a[11], K8_minus=a[12], K08_plus=a[13], K08_minus=a[14], det_K_plus=a[15], det_K_minus=a[16])
+    return (K_coeffs=K, A_vals=(u=a[1], d=a[1], s=a[2]))
 end
 
 """Rebuild the reference's `SolverResult` (ImplicitSolver.jl:178-193) from one record."""
