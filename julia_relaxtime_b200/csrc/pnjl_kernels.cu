@@ -1014,11 +1014,14 @@ int launch_ws(pnjl_handle* h, const WsTask& task_in, cudaStream_t st) {
         // several workers so that all workers stay busy
         n_slots = per_sm < 1 ? 1 : per_sm;
         while (parts < 4 && n_slots * parts * 2 <= 2LL * nw) parts *= 2;
+        // measured on cfg5 slabs (scripts/strong_slab_variants.sh): with 7 lines per SM two parts beat four (9.8 vs 9.2 M
+        // points/s; 8 and 16 parts are slower still) — the per-part prologue/reduction costs more than the shorter sweep saves
+        if (n_slots >= 4 && parts > 2) parts = 2;
         if (n_slots * parts < nw) nw = (int)(n_slots * parts);
     }
     if (getenv("PNJL_WS_PARTS")) parts = atoi(getenv("PNJL_WS_PARTS"));
     if (parts < 1) parts = 1;
-    if (parts > 4) parts = 4;
+    if (parts > 16) parts = 16;
     while ((n_slots + nc - 1) / nc > 32 && nc < kWsMaxGroups) ++nc;
     if (nc > (int)n_slots) nc = (int)n_slots;
     if (nw + nc > kWsMaxWarps) nw = kWsMaxWarps - nc;
