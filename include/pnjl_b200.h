@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define PNJL_ABI_VERSION 7
+#define PNJL_ABI_VERSION 8
 
 /* ---- result record layout (doubles) --------------------------------------------------------- */
 #define PNJL_REC_DOUBLES 32
@@ -174,6 +174,17 @@ int pnjl_tmu_scan_host(pnjl_handle* h, int64_t n_lines, const double* T_MeV, con
 int pnjl_tmu_scan_device(pnjl_handle* h, int64_t n_lines, const double* d_T_MeV, const double* d_xi,
                          const int32_t* d_table_idx, int32_t n_mu, const double* d_mu_MeV, double* d_records,
                          void* stream);
+
+/* Dual-branch scan, DualBranchScan.run_dual_branch_scan (src/pnjl/scans/DualBranchScan.jl:104-182): for line l = (xi[l],
+ * T_MeV[l]) the hadron branch marches mu_MeV ascending from the hadron seed and the quark branch marches it descending
+ * from the quark seed, each with plain continuity seeding and each stopping at its first non-converged or jumping point
+ * (:420-429).  records: [n_lines][2][n_mu][32], branch 0 = hadron, 1 = quark, indexed by the position in mu_MeV; points a
+ * branch does not reach carry PNJL_ST_NO_RESULT and NaNs.  Physical-branch selection, the Omega crossing and the merged
+ * CSV are host arithmetic (julia_relaxtime_b200/dual_branch.py; DualBranchScan.jl:190-330). */
+int pnjl_dual_branch_host(pnjl_handle* h, int64_t n_lines, const double* T_MeV, const double* xi, int32_t n_mu,
+                          const double* mu_MeV, double* records);
+int pnjl_dual_branch_device(pnjl_handle* h, int64_t n_lines, const double* d_T_MeV, const double* d_xi, int32_t n_mu,
+                            const double* d_mu_MeV, double* d_records, void* stream);
 
 /* ---- one-loop integral A and effective couplings (the per-point step after the gap solve) ------------------------
  * build_K_data of scripts/relaxtime/run_gap_transport_scan.jl:297-305:

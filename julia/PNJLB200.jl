@@ -124,6 +124,18 @@ function tmu_scan(e::Engine, T_MeV::Vector{Float64}, xi::Vector{Float64}, table_
     return rec
 end
 
+"""Both branches of `DualBranchScan.run_dual_branch_scan` (src/pnjl/scans/DualBranchScan.jl:104-182) for the lines
+(xi[l], T_MeV[l]).  Returns `Array{Float64}(32, n_mu, 2, n_lines)`: branch 1 = hadron (mu ascending), 2 = quark (mu descending);
+entries with status bit 16384 (`PNJL_ST_NO_RESULT`) are the `nothing`s of the reference's branch vectors."""
+function dual_branch(e::Engine, T_MeV::Vector{Float64}, xi::Vector{Float64}, mu_MeV::Vector{Float64})
+    nl, nmu = length(T_MeV), length(mu_MeV)
+    rec = Array{Float64}(undef, REC, nmu, 2, nl)
+    check(ccall((:pnjl_dual_branch_host, LIB), Cint,
+                (Ptr{Cvoid}, Int64, Ptr{Cdouble}, Ptr{Cdouble}, Int32, Ptr{Cdouble}, Ptr{Cdouble}),
+                e.handle, nl, T_MeV, xi, Int32(nmu), mu_MeV, rec), "pnjl_dual_branch_host")
+    return rec
+end
+
 # ---- one-loop integral A and effective couplings (build_K_data, run_gap_transport_scan.jl:297-305) -----------------
 """Replace the rule of A (default: DEFAULT_MOMENTUM_NODES / DEFAULT_MOMENTUM_WEIGHTS)."""
 function set_oneloop_rule!(e::Engine, nodes::Vector{Float64}, weights::Vector{Float64})

@@ -78,6 +78,8 @@ def load():
     L.pnjl_tmu_scan_host.argtypes = [H, C.c_int64, dp, dp, ip, C.c_int32, dp, dp]
     L.pnjl_tmu_scan_device.argtypes = [H, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                        C.c_void_p, C.c_void_p]
+    L.pnjl_dual_branch_host.argtypes = [H, C.c_int64, dp, dp, C.c_int32, dp, dp]
+    L.pnjl_dual_branch_device.argtypes = [H, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pnjl_set_oneloop_rule.argtypes = [H, C.c_int32, dp, dp]
     L.pnjl_effective_couplings_host.argtypes = [H, C.c_int64, dp, dp, dp, dp, dp, dp, dp]
     L.pnjl_effective_couplings_device.argtypes = [H, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -96,7 +98,7 @@ EXPORTED_SYMBOLS = [
     "pnjl_default_config", "pnjl_abi_version", "pnjl_last_error", "pnjl_create", "pnjl_destroy", "pnjl_gauleg",
     "pnjl_solve_points_host", "pnjl_solve_points_device", "pnjl_set_boundaries", "pnjl_scan_lines_host",
     "pnjl_scan_lines_device", "pnjl_set_oneloop_rule", "pnjl_effective_couplings_host",
-    "pnjl_effective_couplings_device", "pnjl_scan_lines_couplings_host", "pnjl_tmu_scan_host", "pnjl_tmu_scan_device", "pnjl_eval_fj_host", "pnjl_selftest_math", "pnjl_get_stats", "pnjl_measure_fp64_peak"]
+    "pnjl_effective_couplings_device", "pnjl_scan_lines_couplings_host", "pnjl_dual_branch_host", "pnjl_dual_branch_device", "pnjl_tmu_scan_host", "pnjl_tmu_scan_device", "pnjl_eval_fj_host", "pnjl_selftest_math", "pnjl_get_stats", "pnjl_measure_fp64_peak"]
 
 
 def gauleg(a, b, n):
@@ -255,6 +257,17 @@ class Engine:
         rec = out if out is not None else np.empty((n_lines, mu_MeV.size, _abi.REC_DOUBLES))
         self._check(self.L.pnjl_tmu_scan_host(self.h, n_lines, _abi.dptr(T_MeV), _abi.dptr(xi), ti, int(mu_MeV.size),
                                               _abi.dptr(mu_MeV), _abi.dptr(rec)), "pnjl_tmu_scan_host")
+        return rec
+
+    def dual_branch(self, T_MeV, xi, mu_MeV):
+        """DualBranchScan: records [n_lines][2][n_mu][32] (branch 0 hadron / mu ascending, 1 quark / mu descending)."""
+        T_MeV = _abi.as_f64(T_MeV)
+        n_lines = T_MeV.size
+        xi = _abi.as_f64(xi, n_lines)
+        mu_MeV = _abi.as_f64(mu_MeV)
+        rec = np.empty((n_lines, 2, mu_MeV.size, _abi.REC_DOUBLES))
+        self._check(self.L.pnjl_dual_branch_host(self.h, n_lines, _abi.dptr(T_MeV), _abi.dptr(xi), int(mu_MeV.size),
+                                                 _abi.dptr(mu_MeV), _abi.dptr(rec)), "pnjl_dual_branch_host")
         return rec
 
     def eval_fj(self, T_fm, mu_fm, xi, x):

@@ -313,10 +313,13 @@ __global__ void __launch_bounds__(512, 1) k_scan_lines(const DeviceConfig* __res
     for (;;) {
         const long long l = next_task<G>(counter, ev);
         if (l >= n_lines) break;
-        LineSink<G> sink{&ev, records + (long long)PNJL_REC_DOUBLES * n_T * l, xi[l]};
-        // mode 0: (xi, mu) line marching T (run_gap_transport_scan.jl); mode 1: (xi, T) line marching mu (TmuScan.jl)
+        // mode 0: (xi, mu) line marching T (run_gap_transport_scan.jl); mode 1: (xi, T) line marching mu (TmuScan.jl);
+        // mode 2: task l = branch (l & 1) of the (xi, T) line l >> 1 (DualBranchScan.jl), records [line][branch][mu]
+        const long long li = mode == 2 ? (l >> 1) : l;
+        LineSink<G> sink{&ev, records + (long long)PNJL_REC_DOUBLES * n_T * l, xi[li]};
         if (mode == 0) scan_line(sv, &cfg->pt, table_idx ? table_idx[l] : -1, muq_MeV[l], xi[l], n_T, T_MeV, sink);
-        else scan_tmu_line(sv, &cfg->pt, table_idx ? table_idx[l] : -1, muq_MeV[l], xi[l], n_T, T_MeV, sink);
+        else if (mode == 1) scan_tmu_line(sv, &cfg->pt, table_idx ? table_idx[l] : -1, muq_MeV[l], xi[l], n_T, T_MeV, sink);
+        else scan_branch_line(sv, muq_MeV[li], xi[li], n_T, T_MeV, (int)(l & 1), sink);
     }
     ev.drain();
 }
@@ -359,7 +362,7 @@ struct WsGroup {
 
 // What the controller lanes work on: whole continuity lines or independent points.
 struct WsTask {
-    int mode;                // 0: lines (scan_line), 1: points (solve / solve_multi), 2: TmuScan lines (scan_tmu_line)
+    int mode;                // 0: lines (scan_line), 1: points (solve / solve_multi), 2: TmuScan lines (scan_tmu_line), 3: dual-branch lines
     long long n_tasks;
     long long perm_mult;     // tasks are handed out in the order (k * perm_mult) mod n_tasks (coprime multiplier): neighbouring
                              // lines cost alike, so a contiguous hand-out loads the SMs unevenly (measured 1.12 vs 1.02 max/mean)
@@ -728,6 +731,11 @@ __global__ void __launch_bounds__(PNJL_WS_MAX_THREADS, 1) k_solve_ws(const Devic
             CtrlSink sink{task.records + (long long)PNJL_REC_DOUBLES * task.n_T * t, task.xi[t]};
             scan_tmu_line(sv, &cfg->pt, task.table_idx ? task.table_idx[t] : -1, task.muq_MeV[t], task.xi[t], task.n_T,
                           task.T_MeV, sink);
+        } else if (task.mode == 3) {
+            // dual-branch scan: task t = branch (t & 1) of line t >> 1; muq_MeV holds the lines' T_MeV, T_MeV the mu grid
+            const long long li = t >> 1;
+            CtrlSink sink{task.records + (long long)PNJL_REC_DOUBLES * task.n_T * t, task.xi[li]};
+            scan_branch_line(sv, task.muq_MeV[li], task.xi[li], task.n_T, task.T_MeV, (int)(t & 1), sink);
         } else {
             const double T = task.T_fm[t], mu = task.mu_fm[t], x_i = task.xi[t];
             sv.set_point(T, mu, x_i);
@@ -1053,7 +1061,7 @@ int launch_lines_ws(pnjl_handle* h, long long n_lines, const double* muq, const 
                     const double* T, double* rec, cudaStream_t st, int mode) {
     WsTask t;
     std::memset(&t, 0, sizeof(t));
-    t.mode = mode == 0 ? 0 : 2; t.n_tasks = n_lines; t.muq_MeV = muq; t.xi = xi; t.table_idx = tidx; t.n_T = n_T; t.T_MeV = T; t.records = rec;
+    t.mode = mode == 0 ? 0 : (mode == 1 ? 2 : 3); t.n_tasks = n_lines; t.muq_MeV = muq; t.xi = xi; t.table_idx = tidx; t.n_T = n_T; t.T_MeV = T; t.records = rec;
     return launch_ws(h, t, st);
 }
 
@@ -1611,6 +1619,47 @@ int pnjl_tmu_scan_host(pnjl_handle* h, int64_t n_lines, const double* T_MeV, con
     choose_layout_for_batch(h, n_lines, xi);
     int rc = pnjl_tmu_scan_device(h, n_lines, (const double*)h->in_mu.p, (const double*)h->in_xi.p, d_idx, n_mu,
                                   (const double*)h->in_T.p, (double*)h->out_rec.p, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(h->ev1, st));
+    CUDA_TRY(cudaMemcpyAsync(records, h->out_rec.p, nrec, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->stats.kernel_ms = ms;
+    return PNJL_OK;
+}
+
+int pnjl_dual_branch_device(pnjl_handle* h, int64_t n_lines, const double* d_T, const double* d_xi, int32_t n_mu,
+                            const double* d_mu, double* d_records, void* stream) {
+    if (!h) return fail(PNJL_ERR_ARG, "null handle");
+    if (n_lines < 0 || n_mu < 0) return fail(PNJL_ERR_ARG, "negative size");
+    h->stats.kernel_launches = 0;
+    if (n_lines == 0 || n_mu == 0) return PNJL_OK;
+    if (!d_T || !d_xi || !d_mu || !d_records) return fail(PNJL_ERR_ARG, "null buffer");
+    DeviceGuard guard(h->device);
+    return dispatch_lines(h, 2 * n_lines, d_T, d_xi, nullptr, n_mu, d_mu, d_records, (cudaStream_t)stream, 2);
+}
+int pnjl_dual_branch_host(pnjl_handle* h, int64_t n_lines, const double* T_MeV, const double* xi, int32_t n_mu,
+                          const double* mu_MeV, double* records) {
+    if (!h) return fail(PNJL_ERR_ARG, "null handle");
+    if (n_lines < 0 || n_mu < 0) return fail(PNJL_ERR_ARG, "negative size");
+    if (n_lines == 0 || n_mu == 0) { h->stats.kernel_launches = 0; return PNJL_OK; }
+    if (!T_MeV || !xi || !mu_MeV || !records) return fail(PNJL_ERR_ARG, "null buffer");
+    DeviceGuard guard(h->device);
+    const size_t nl = sizeof(double) * (size_t)n_lines;
+    const size_t nrec = sizeof(double) * (size_t)n_lines * 2 * n_mu * PNJL_REC_DOUBLES;
+    CUDA_TRY(h->in_mu.reserve(nl));
+    CUDA_TRY(h->in_xi.reserve(nl));
+    CUDA_TRY(h->in_T.reserve(sizeof(double) * n_mu));
+    CUDA_TRY(h->out_rec.reserve(nrec));
+    cudaStream_t st = h->stream;
+    CUDA_TRY(cudaMemcpyAsync(h->in_mu.p, T_MeV, nl, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(h->in_xi.p, xi, nl, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(h->in_T.p, mu_MeV, sizeof(double) * n_mu, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaEventRecord(h->ev0, st));
+    choose_layout_for_batch(h, n_lines, xi);
+    int rc = pnjl_dual_branch_device(h, n_lines, (const double*)h->in_mu.p, (const double*)h->in_xi.p, n_mu,
+                                     (const double*)h->in_T.p, (double*)h->out_rec.p, st);
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(h->ev1, st));
     CUDA_TRY(cudaMemcpyAsync(records, h->out_rec.p, nrec, cudaMemcpyDeviceToHost, st));

@@ -640,4 +640,58 @@ PNJL_HD_NOINL void scan_tmu_line(Solver<Ev>& sv, const PhaseTables* pt, int ti, 
     }
 }
 
+// One branch of DualBranchScan.run_dual_branch_scan (src/pnjl/scans/DualBranchScan.jl:104-182) for one (T, xi) line:
+//   branch 0 "hadron": mu ascending,  ContinuitySeed(fallback = DefaultSeed(phase_hint = :hadron))   :121-146
+//   branch 1 "quark":  mu descending, ContinuitySeed(fallback = DefaultSeed(phase_hint = :quark))    :148-174
+// Every point is solve(FixedMu(), T, mu; seed_strategy = fixed seed) with its automatic fallbacks (_solve_point :334-351;
+// any exception = no result).  The branch stops at the first point that does not converge or that jumps
+// (|d phi_u| > 0.5 or |d M_u| > 50 MeV against the last accepted point, _is_solution_jump :420-429); that point and
+// everything after it carry PNJL_ST_NO_RESULT and NaNs ("nothing" in the reference's branch vectors).
+template <class Ev, class Sink>
+PNJL_HD_NOINL void scan_branch_line(Solver<Ev>& sv, double T_MeV, double xi, int n_mu, const double* mu_MeV, int branch,
+                                    Sink& sink) {
+    const double T_fm = T_MeV / sv.m.hbarc;
+    bool has_prev = false, alive = true;
+    double prev[5] = {0, 0, 0, 0, 0};
+    double prev_Mu = 0.0;
+    PointRes r;
+    for (int k = 0; k < n_mu; ++k) {
+        const int im = branch == 0 ? k : n_mu - 1 - k;
+        const double mu_fm = mu_MeV[im] / sv.m.hbarc;
+        sv.set_point(T_fm, mu_fm, xi);
+        sv.n_fj = 0;
+        sv.n_th = 0;
+        sv.n_ft = 0;
+        bool keep = false;
+        if (alive) {
+            double x0[5];
+            if (has_prev) copy5(x0, prev);
+            else default_seed(branch == 0 ? 0 : 1, T_fm, mu_fm, x0);
+            sv.solve_with_fallback(x0, r);
+            if (r.converged && !(r.status & PNJL_ST_NONFINITE)) {
+                const bool jump = has_prev && (fabs(prev[0] - r.x[0]) > 0.5 || fabs(prev_Mu - r.th.M[0]) * 197.327 > 50.0);
+                if (!jump) {
+                    keep = true;
+                    copy5(prev, r.x);
+                    prev_Mu = r.th.M[0];
+                    has_prev = true;
+                }
+            }
+            if (!keep) alive = false;
+        }
+        if (!keep) {
+#pragma unroll
+            for (int q = 0; q < 5; ++q) r.x[q] = NAN;
+            sv.nan_thermo(r);
+#pragma unroll
+            for (int q = 0; q < 3; ++q) r.th.M[q] = NAN;
+            r.res = NAN;
+            r.it = -1;
+            r.converged = false;
+            r.status = PNJL_ST_NO_RESULT;
+        }
+        sink(im, r, T_fm, mu_fm, sv.n_fj, sv.n_th, sv.n_ft);
+    }
+}
+
 }  // namespace pnjl

@@ -318,3 +318,20 @@ def _couplings_batch(self, T, mu, m_u, m_s, Phi, Phib, nodes=None, weights=None)
 Oracle.oneloop_A = _oneloop_A
 Oracle.effective_couplings = _effective_couplings
 Oracle.couplings_batch = _couplings_batch
+
+
+def _dual_branch(self, T_MeV, xi, mu_MeV):
+    """DualBranchScan semantics: Result of n_lines * 2 * n_mu entries, index (line * 2 + branch) * n_mu + imu."""
+    T_MeV = np.ascontiguousarray(np.atleast_1d(T_MeV), dtype=np.float64)
+    n_lines = T_MeV.size
+    xi = np.ascontiguousarray(np.broadcast_to(np.atleast_1d(xi), (n_lines,)), dtype=np.float64)
+    mu_MeV = np.ascontiguousarray(mu_MeV, dtype=np.float64)
+    out = Result(n_lines * 2 * mu_MeV.size)
+    cs = out.c_struct()
+    self.lib.oracle_dual_branch(C.byref(self.cfg), C.c_int64(n_lines), _dp(T_MeV), _dp(xi), C.c_int32(mu_MeV.size), _dp(mu_MeV),
+                                C.byref(cs))
+    out.n_lines, out.n_mu = n_lines, mu_MeV.size
+    return out
+
+
+Oracle.dual_branch = _dual_branch

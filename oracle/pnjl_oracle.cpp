@@ -1319,6 +1319,69 @@ int32_t oracle_tmu_scan(const oracle_config* c, int64_t n_lines, const double* T
     return 0;
 }
 
+// DualBranchScan.run_dual_branch_scan (src/pnjl/scans/DualBranchScan.jl:104-182).  Output index = (line * 2 + branch) * n_mu
+// + imu, branch 0 = hadron (mu ascending, ContinuitySeed(fallback = DefaultSeed(:hadron))), 1 = quark (mu descending,
+// fallback DefaultSeed(:quark)); every point is solve() from the fixed seed with its automatic fallbacks (:334-351); a
+// branch ends at its first non-converged or jumping point (:420-429) and the rest carries ST_NO_RESULT / NaN.
+int32_t oracle_dual_branch(const oracle_config* c, int64_t n_lines, const double* T_MeV, const double* xi, int32_t n_mu,
+                           const double* mu_MeV, const oracle_out* out) {
+    Consts k = consts_of(c);
+    Mesh m = mesh_of(c);
+    SolverOpts o = opts_of(c);
+    const int64_t n = n_lines * 2 * (int64_t)n_mu;
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+#ifdef _OPENMP
+    int nt = c->n_threads > 0 ? c->n_threads : omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nt)
+#endif
+    for (int64_t task = 0; task < 2 * n_lines; ++task) {
+        const int64_t l = task / 2;
+        const int branch = (int)(task % 2);
+        const double T_fm = T_MeV[l] / k.hbarc;
+        bool has_prev = false, alive = true;
+        double prev[5] = {0, 0, 0, 0, 0}, prev_Mu = 0;
+        for (int kk = 0; kk < n_mu; ++kk) {
+            const int im = branch == 0 ? kk : n_mu - 1 - kk;
+            const double mu_fm = mu_MeV[im] / k.hbarc;
+            Problem pb{&k, &m, T_fm, mu_fm, xi[l]};
+            const int64_t i = task * n_mu + im;
+            bool keep = false;
+            PointResult r;
+            int n_fj = 0;
+            if (alive) {
+                double x0[5];
+                if (has_prev) std::memcpy(x0, prev, 40);
+                else default_seed(branch == 0 ? 0 : 1, T_fm, mu_fm, x0);
+                r = solve_with_fallback(pb, x0, o);
+                n_fj = r.n_fj;
+                if (r.converged && !(r.status & ST_NONFINITE)) {
+                    const bool jump = has_prev && (std::fabs(prev[0] - r.x[0]) > 0.5 ||
+                                                   std::fabs(prev_Mu - r.th.masses[0]) * 197.327 > 50.0);
+                    if (!jump) {
+                        keep = true;
+                        std::memcpy(prev, r.x, 40);
+                        prev_Mu = r.th.masses[0];
+                        has_prev = true;
+                    }
+                }
+                if (!keep) alive = false;
+            }
+            if (keep) {
+                store(out, n, i, pb, r);
+            } else {
+                for (int q = 0; q < 5; ++q) out->x[q * n + i] = nan;
+                for (int q = 0; q < 3; ++q) { out->mass[q * n + i] = nan; out->n_q[q * n + i] = nan; out->n_qbar[q * n + i] = nan; }
+                out->omega[i] = out->pressure[i] = out->rho_norm[i] = out->entropy[i] = out->energy[i] = nan;
+                out->residual_norm[i] = nan;
+                out->iterations[i] = -1;
+                out->status[i] = ST_NO_RESULT;
+                if (out->n_fj) out->n_fj[i] = n_fj;
+            }
+        }
+    }
+    return 0;
+}
+
 int32_t oracle_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

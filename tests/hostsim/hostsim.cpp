@@ -181,9 +181,16 @@ void hostsim_scan_lines_mode(const pnjl_config* c, int64_t n_lines, const double
     for (int64_t l = 0; l < n_lines; ++l) {
         HostEval ev{&m, &mesh, c->isospin_symmetric};
         Solver<HostEval> sv(m, sp, ev);
-        Sink sink{records + PNJL_REC_DOUBLES * n_T * l, xi[l]};
+        Sink sink{records + PNJL_REC_DOUBLES * n_T * (mode == 2 ? 0 : l), xi[l]};
         if (mode == 0) scan_line(sv, pt, table_idx ? table_idx[l] : -1, muq_MeV[l], xi[l], n_T, T_MeV, sink);
-        else scan_tmu_line(sv, pt, table_idx ? table_idx[l] : -1, muq_MeV[l], xi[l], n_T, T_MeV, sink);
+        else if (mode == 1) scan_tmu_line(sv, pt, table_idx ? table_idx[l] : -1, muq_MeV[l], xi[l], n_T, T_MeV, sink);
+        else {
+            // dual-branch: records [line][2][n_mu]
+            for (int b = 0; b < 2; ++b) {
+                Sink sb{records + PNJL_REC_DOUBLES * n_T * (2 * l + b), xi[l]};
+                scan_branch_line(sv, muq_MeV[l], xi[l], n_T, T_MeV, b, sb);
+            }
+        }
     }
     delete pt;
 }

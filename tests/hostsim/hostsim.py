@@ -71,6 +71,10 @@ class HostSim:
                                       C.c_int32(seed_mode), C.c_int32(n_seeds), sp, _abi.dptr(rec))
         return rec
 
+    def dual_branch(self, T_MeV, xi, mu_MeV):
+        r = self.scan_lines(T_MeV, xi, mu_MeV, (), None, mode=2)
+        return r.reshape(-1, 2, r.shape[1], _abi.REC_DOUBLES)
+
     def tmu_scan(self, T_MeV, xi, mu_MeV, tables=(), table_idx=None):
         return self.scan_lines(T_MeV, xi, mu_MeV, tables, table_idx, mode=1)
 
@@ -89,7 +93,7 @@ class HostSim:
         if table_idx is None:
             table_idx = np.full(n_lines, -1, dtype=np.int32)
         table_idx = np.ascontiguousarray(table_idx, dtype=np.int32)
-        rec = np.zeros((n_lines, T_MeV.size, _abi.REC_DOUBLES))
+        rec = np.zeros((n_lines * (2 if mode == 2 else 1), T_MeV.size, _abi.REC_DOUBLES))
         self.lib.hostsim_scan_lines_mode(C.byref(self.cfg), C.c_int64(n_lines), _abi.dptr(muq_MeV), _abi.dptr(xi),
                                          _abi.iptr(table_idx), C.c_int32(T_MeV.size), _abi.dptr(T_MeV),
                                          C.c_int32(len(tables)), ctabs, _abi.dptr(rec), C.c_int32(mode))
