@@ -101,11 +101,20 @@ function solve_points(e::Engine, T_fm::Vector{Float64}, mu_fm::Vector{Float64}, 
     return rec
 end
 
+"""Page-locked result buffer: the kernels write into it while they run (no device->host copy afterwards).  Free with
+`free_pinned(a)`; pass it as `out` to the `*!` variants or let `scan_lines(...; pinned=true)` do it."""
+function alloc_pinned(dims::Int...)
+    p = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:pnjl_alloc_pinned, LIB), Cint, (UInt64, Ref{Ptr{Cvoid}}), UInt64(8 * prod(dims)), p), "pnjl_alloc_pinned")
+    return unsafe_wrap(Array, Ptr{Float64}(p[]), dims; own=false)
+end
+free_pinned(a::Array{Float64}) = ccall((:pnjl_free_pinned, LIB), Cint, (Ptr{Cvoid},), pointer(a))
+
 """Continuity lines in run_gap_transport_scan.jl order.  Returns `Array{Float64}(32, n_T, n_lines)`."""
 function scan_lines(e::Engine, muq_MeV::Vector{Float64}, xi::Vector{Float64}, table_idx::Vector{Int32},
-                    T_MeV::Vector{Float64})
+                    T_MeV::Vector{Float64}; pinned::Bool=false)
     nl, nT = length(muq_MeV), length(T_MeV)
-    rec = Array{Float64}(undef, REC, nT, nl)
+    rec = pinned ? alloc_pinned(REC, nT, nl) : Array{Float64}(undef, REC, nT, nl)
     check(ccall((:pnjl_scan_lines_host, LIB), Cint,
                 (Ptr{Cvoid}, Int64, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Int32}, Int32, Ptr{Cdouble}, Ptr{Cdouble}),
                 e.handle, nl, muq_MeV, xi, table_idx, Int32(nT), T_MeV, rec), "pnjl_scan_lines_host")

@@ -67,6 +67,8 @@ def load():
     L.pnjl_create.argtypes = [C.POINTER(_abi.PnjlConfig), C.POINTER(H)]
     L.pnjl_destroy.argtypes = [H]
     L.pnjl_destroy.restype = None
+    L.pnjl_alloc_pinned.argtypes = [C.c_uint64, C.POINTER(C.c_void_p)]
+    L.pnjl_free_pinned.argtypes = [C.c_void_p]
     L.pnjl_gauleg.argtypes = [C.c_double, C.c_double, C.c_int32, dp, dp]
     L.pnjl_solve_points_host.argtypes = [H, C.c_int64, dp, dp, dp, C.c_int32, C.c_int32, dp, dp]
     L.pnjl_solve_points_device.argtypes = [H, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
@@ -95,10 +97,37 @@ def load():
 
 
 EXPORTED_SYMBOLS = [
-    "pnjl_default_config", "pnjl_abi_version", "pnjl_last_error", "pnjl_create", "pnjl_destroy", "pnjl_gauleg",
+    "pnjl_default_config", "pnjl_alloc_pinned", "pnjl_free_pinned", "pnjl_abi_version", "pnjl_last_error", "pnjl_create", "pnjl_destroy", "pnjl_gauleg",
     "pnjl_solve_points_host", "pnjl_solve_points_device", "pnjl_set_boundaries", "pnjl_scan_lines_host",
     "pnjl_scan_lines_device", "pnjl_set_oneloop_rule", "pnjl_effective_couplings_host",
     "pnjl_effective_couplings_device", "pnjl_scan_lines_couplings_host", "pnjl_dual_branch_host", "pnjl_dual_branch_device", "pnjl_tmu_scan_host", "pnjl_tmu_scan_device", "pnjl_eval_fj_host", "pnjl_selftest_math", "pnjl_get_stats", "pnjl_measure_fp64_peak"]
+
+
+class PinnedArray:
+    """numpy view of page-locked host memory from pnjl_alloc_pinned: result buffers the kernels write in place."""
+
+    def __init__(self, shape):
+        L = load()
+        self.shape = tuple(int(x) for x in shape)
+        n = int(np.prod(self.shape))
+        self._p = C.c_void_p()
+        rc = L.pnjl_alloc_pinned(C.c_uint64(8 * n), C.byref(self._p))
+        if rc != 0:
+            raise PnjlError("pnjl_alloc_pinned failed (%d): %s" % (rc, L.pnjl_last_error().decode()))
+        buf = (C.c_double * n).from_address(self._p.value)
+        self.array = np.frombuffer(buf, dtype=np.float64).reshape(self.shape)
+
+    def close(self):
+        if getattr(self, "_p", None) and self._p.value:
+            self.array = None
+            load().pnjl_free_pinned(self._p)
+            self._p = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def gauleg(a, b, n):

@@ -1158,6 +1158,19 @@ int dispatch_fj(pnjl_handle* h, long long n, const double* T, const double* mu, 
     }
 }
 
+// If `host_ptr` is page-locked host memory that the device can address (cudaHostAlloc / cudaHostRegister under UVA), return
+// its device alias: the solve kernels then write their 256-byte records straight into the caller's buffer over PCIe while
+// they run (2.1 GB in 340 ms on cfg5 is 6 GB/s) and the device->host copy after the kernel disappears.  nullptr otherwise
+// (pageable memory: staged through a device buffer and copied).  PNJL_ZERO_COPY=0 turns it off.
+double* device_alias_of_pinned(void* host_ptr) {
+    static const bool enabled = !(getenv("PNJL_ZERO_COPY") && atoi(getenv("PNJL_ZERO_COPY")) == 0);
+    if (!enabled) return nullptr;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, host_ptr) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (a.type != cudaMemoryTypeHost || !a.devicePointer) return nullptr;
+    return (double*)a.devicePointer;
+}
+
 }  // namespace
 
 extern "C" {
@@ -1201,6 +1214,20 @@ int pnjl_gauleg(double a, double b, int32_t n, double* nodes, double* weights) {
         nodes[i] = scale * x[i] + shift;
         weights[i] = scale * w[i];
     }
+    return PNJL_OK;
+}
+
+int pnjl_alloc_pinned(uint64_t bytes, void** out) {
+    if (!out) return fail(PNJL_ERR_ARG, "null buffer");
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocMapped);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(e == cudaErrorMemoryAllocation ? PNJL_ERR_NOMEM : PNJL_ERR_CUDA, cudaGetErrorString(e)); }
+    return PNJL_OK;
+}
+int pnjl_free_pinned(void* p) {
+    if (!p) return PNJL_OK;
+    cudaError_t e = cudaFreeHost(p);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(PNJL_ERR_CUDA, cudaGetErrorString(e)); }
     return PNJL_OK;
 }
 
@@ -1425,7 +1452,8 @@ int pnjl_solve_points_host(pnjl_handle* h, int64_t n, const double* T, const dou
     CUDA_TRY(h->in_T.reserve(nb));
     CUDA_TRY(h->in_mu.reserve(nb));
     CUDA_TRY(h->in_xi.reserve(nb));
-    CUDA_TRY(h->out_rec.reserve(nb * PNJL_REC_DOUBLES));
+    double* alias = device_alias_of_pinned(records);
+    if (!alias) CUDA_TRY(h->out_rec.reserve(nb * PNJL_REC_DOUBLES));
     cudaStream_t st = h->stream;
     CUDA_TRY(cudaMemcpyAsync(h->in_T.p, T, nb, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(h->in_mu.p, mu, nb, cudaMemcpyHostToDevice, st));
@@ -1440,10 +1468,10 @@ int pnjl_solve_points_host(pnjl_handle* h, int64_t n, const double* T, const dou
     CUDA_TRY(cudaEventRecord(h->ev0, st));
     choose_layout_for_batch(h, n, xi);
     int rc = pnjl_solve_points_device(h, n, (const double*)h->in_T.p, (const double*)h->in_mu.p, (const double*)h->in_xi.p,
-                                      seed_mode, n_seeds, d_seeds, (double*)h->out_rec.p, st);
+                                      seed_mode, n_seeds, d_seeds, alias ? alias : (double*)h->out_rec.p, st);
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(h->ev1, st));
-    CUDA_TRY(cudaMemcpyAsync(records, h->out_rec.p, nb * PNJL_REC_DOUBLES, cudaMemcpyDeviceToHost, st));
+    if (!alias) CUDA_TRY(cudaMemcpyAsync(records, h->out_rec.p, nb * PNJL_REC_DOUBLES, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     float ms = 0;
     CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
@@ -1451,8 +1479,8 @@ int pnjl_solve_points_host(pnjl_handle* h, int64_t n, const double* T, const dou
     return PNJL_OK;
 }
 
-int pnjl_scan_lines_host(pnjl_handle* h, int64_t n_lines, const double* muq, const double* xi, const int32_t* tidx,
-                         int32_t n_T, const double* T_MeV, double* records) {
+static int scan_lines_host_impl(pnjl_handle* h, int64_t n_lines, const double* muq, const double* xi, const int32_t* tidx,
+                                int32_t n_T, const double* T_MeV, double* records, bool keep_device_copy) {
     if (!h) return fail(PNJL_ERR_ARG, "null handle");
     if (n_lines < 0 || n_T < 0) return fail(PNJL_ERR_ARG, "negative size");
     if (n_lines == 0 || n_T == 0) { h->stats.kernel_launches = 0; return PNJL_OK; }
@@ -1464,7 +1492,8 @@ int pnjl_scan_lines_host(pnjl_handle* h, int64_t n_lines, const double* muq, con
     CUDA_TRY(h->in_xi.reserve(nl));
     CUDA_TRY(h->in_T.reserve(sizeof(double) * n_T));
     CUDA_TRY(h->in_idx.reserve(sizeof(int32_t) * (size_t)n_lines));
-    CUDA_TRY(h->out_rec.reserve(nrec));
+    double* alias = keep_device_copy ? nullptr : device_alias_of_pinned(records);
+    if (!alias) CUDA_TRY(h->out_rec.reserve(nrec));
     cudaStream_t st = h->stream;
     CUDA_TRY(cudaMemcpyAsync(h->in_mu.p, muq, nl, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(h->in_xi.p, xi, nl, cudaMemcpyHostToDevice, st));
@@ -1477,15 +1506,19 @@ int pnjl_scan_lines_host(pnjl_handle* h, int64_t n_lines, const double* muq, con
     CUDA_TRY(cudaEventRecord(h->ev0, st));
     choose_layout_for_batch(h, n_lines, xi);
     int rc = pnjl_scan_lines_device(h, n_lines, (const double*)h->in_mu.p, (const double*)h->in_xi.p, d_idx, n_T,
-                                    (const double*)h->in_T.p, (double*)h->out_rec.p, st);
+                                    (const double*)h->in_T.p, alias ? alias : (double*)h->out_rec.p, st);
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(h->ev1, st));
-    CUDA_TRY(cudaMemcpyAsync(records, h->out_rec.p, nrec, cudaMemcpyDeviceToHost, st));
+    if (!alias) CUDA_TRY(cudaMemcpyAsync(records, h->out_rec.p, nrec, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     float ms = 0;
     CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     h->stats.kernel_ms = ms;
     return PNJL_OK;
+}
+int pnjl_scan_lines_host(pnjl_handle* h, int64_t n_lines, const double* muq, const double* xi, const int32_t* tidx,
+                         int32_t n_T, const double* T_MeV, double* records) {
+    return scan_lines_host_impl(h, n_lines, muq, xi, tidx, n_T, T_MeV, records, false);
 }
 
 int pnjl_set_oneloop_rule(pnjl_handle* h, int32_t n_nodes, const double* nodes, const double* weights) {
@@ -1566,7 +1599,7 @@ int pnjl_scan_lines_couplings_host(pnjl_handle* h, int64_t n_lines, const double
                                    int32_t n_T, const double* T_MeV, double* records, double* aux) {
     if (!aux) return fail(PNJL_ERR_ARG, "null buffer");
     // the scan itself (records stay resident in out_rec), then the couplings of every record on the same stream
-    int rc = pnjl_scan_lines_host(h, n_lines, muq, xi, tidx, n_T, T_MeV, records);
+    int rc = scan_lines_host_impl(h, n_lines, muq, xi, tidx, n_T, T_MeV, records, true);
     if (rc || n_lines == 0 || n_T == 0) return rc;
     DeviceGuard guard(h->device);
     const long long n = (long long)n_lines * n_T;
@@ -1605,7 +1638,8 @@ int pnjl_tmu_scan_host(pnjl_handle* h, int64_t n_lines, const double* T_MeV, con
     CUDA_TRY(h->in_xi.reserve(nl));
     CUDA_TRY(h->in_T.reserve(sizeof(double) * n_mu));
     CUDA_TRY(h->in_idx.reserve(sizeof(int32_t) * (size_t)n_lines));
-    CUDA_TRY(h->out_rec.reserve(nrec));
+    double* alias = device_alias_of_pinned(records);
+    if (!alias) CUDA_TRY(h->out_rec.reserve(nrec));
     cudaStream_t st = h->stream;
     CUDA_TRY(cudaMemcpyAsync(h->in_mu.p, T_MeV, nl, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(h->in_xi.p, xi, nl, cudaMemcpyHostToDevice, st));
@@ -1618,10 +1652,10 @@ int pnjl_tmu_scan_host(pnjl_handle* h, int64_t n_lines, const double* T_MeV, con
     CUDA_TRY(cudaEventRecord(h->ev0, st));
     choose_layout_for_batch(h, n_lines, xi);
     int rc = pnjl_tmu_scan_device(h, n_lines, (const double*)h->in_mu.p, (const double*)h->in_xi.p, d_idx, n_mu,
-                                  (const double*)h->in_T.p, (double*)h->out_rec.p, st);
+                                  (const double*)h->in_T.p, alias ? alias : (double*)h->out_rec.p, st);
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(h->ev1, st));
-    CUDA_TRY(cudaMemcpyAsync(records, h->out_rec.p, nrec, cudaMemcpyDeviceToHost, st));
+    if (!alias) CUDA_TRY(cudaMemcpyAsync(records, h->out_rec.p, nrec, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     float ms = 0;
     CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
@@ -1651,7 +1685,8 @@ int pnjl_dual_branch_host(pnjl_handle* h, int64_t n_lines, const double* T_MeV, 
     CUDA_TRY(h->in_mu.reserve(nl));
     CUDA_TRY(h->in_xi.reserve(nl));
     CUDA_TRY(h->in_T.reserve(sizeof(double) * n_mu));
-    CUDA_TRY(h->out_rec.reserve(nrec));
+    double* alias = device_alias_of_pinned(records);
+    if (!alias) CUDA_TRY(h->out_rec.reserve(nrec));
     cudaStream_t st = h->stream;
     CUDA_TRY(cudaMemcpyAsync(h->in_mu.p, T_MeV, nl, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(h->in_xi.p, xi, nl, cudaMemcpyHostToDevice, st));
@@ -1659,10 +1694,10 @@ int pnjl_dual_branch_host(pnjl_handle* h, int64_t n_lines, const double* T_MeV, 
     CUDA_TRY(cudaEventRecord(h->ev0, st));
     choose_layout_for_batch(h, n_lines, xi);
     int rc = pnjl_dual_branch_device(h, n_lines, (const double*)h->in_mu.p, (const double*)h->in_xi.p, n_mu,
-                                     (const double*)h->in_T.p, (double*)h->out_rec.p, st);
+                                     (const double*)h->in_T.p, alias ? alias : (double*)h->out_rec.p, st);
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(h->ev1, st));
-    CUDA_TRY(cudaMemcpyAsync(records, h->out_rec.p, nrec, cudaMemcpyDeviceToHost, st));
+    if (!alias) CUDA_TRY(cudaMemcpyAsync(records, h->out_rec.p, nrec, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     float ms = 0;
     CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
