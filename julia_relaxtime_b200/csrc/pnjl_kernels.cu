@@ -718,8 +718,18 @@ __global__ void __launch_bounds__(PNJL_WS_MAX_THREADS, 1) k_solve_ws(const Devic
     ev.t_ret = 0;
 #endif
     Solver<CtrlEval> sv(cfg->m, cfg->sp, ev);
+    // First task of every mailbox: CTA b, mailbox j -> ticket b + gridDim.x * j, so that a grid that holds all tasks in one
+    // wave spreads them evenly over ALL its CTAs (8192 lines on 148 SMs: 55 or 56 per SM instead of 147 x 56 and one idle
+    // SM); later tasks come from the global counter.
+    bool first_task = true;
     for (;;) {
-        const long long tk = (long long)atomicAdd(counter, 1ULL);
+        long long tk;
+        if (first_task) {
+            tk = (long long)blockIdx.x + (long long)gridDim.x * (gr->first_slot + lane);
+            first_task = false;
+        } else {
+            tk = (long long)gridDim.x * n_slots + (long long)atomicAdd(counter, 1ULL);
+        }
         if (tk >= task.n_tasks) break;
         const long long t = (long long)(((unsigned long long)tk * (unsigned long long)task.perm_mult) % (unsigned long long)task.n_tasks);
         if (task.mode == 0) {
@@ -1044,7 +1054,8 @@ int launch_ws(pnjl_handle* h, const WsTask& task_in, cudaStream_t st) {
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_ctas, k_solve_ws, threads, smem));
     if (per_sm_ctas < 1) return fail(PNJL_ERR_CUDA, "warp-specialised kernel does not fit on an SM");
     const long long cap = (long long)per_sm_ctas * h->sm_count;
-    const int blocks = (int)(need < cap ? need : cap);
+    // with at least one task per SM every SM gets a CTA (the tasks are dealt out round-robin, see k_solve_ws)
+    const int blocks = (int)(task.n_tasks >= cap ? cap : (need < cap ? need : cap));
     h->stats.regs_per_thread = fa.numRegs;
     h->stats.smem_bytes = (int)smem;
     h->stats.blocks = blocks;
