@@ -516,8 +516,9 @@ PNJL_HD void species4_fast(const FastCtx& fc, const double Y[4], Species4& o, bo
 #pragma unroll
     for (int s = 0; s < 4; ++s) o.n[s] = g[s] * o.r1[s];
     if (need_q) {
+        // qf here is (q - g)/f = r2 (2 P2 + 2 y); the caller forms (q - 3 g n)/f = u n + qf with u = 1 - 3 n
 #pragma unroll
-        for (int s = 0; s < 4; ++s) o.qf[s] = f_fma(q[s], o.r2[s], o.n[s]);
+        for (int s = 0; s < 4; ++s) o.qf[s] = q[s] * o.r2[s];
     }
 }
 
@@ -540,18 +541,21 @@ PNJL_HD void fj_pair_back(const FastCtx& fc, const double rE[2], const double Y[
                           double sh[5]) {
     Species4 sp;
     species4_fast(fc, Y, sp, true);
-    double nsum[2], Q[2], crE[2], crE2[2], m3[4], s3[2], s4[2], gp[2], gpb[2], hpp[2], hppb[2], hpbpb[2];
+    double nsum[2], Q[2], crE[2], crE2[2], u[4], v[4], s3[2], s4[2], gp[2], gpb[2], hpp[2], hppb[2], hpbpb[2];
+    // u = 1 - 3 n, v = 2 - 3 n = u + 1;  (q - 3 g n)/f = q/f - 3 n^2 = u n + (q - g)/f
 #pragma unroll
-    for (int s = 0; s < 4; ++s) m3[s] = -3.0 * sp.n[s];
+    for (int s = 0; s < 4; ++s) u[s] = f_fma(-3.0, sp.n[s], 1.0);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) v[s] = u[s] + 1.0;
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
         const int a = 2 * j, b = 2 * j + 1;   // quark, antiquark
         nsum[j] = sp.n[a] + sp.n[b];
-        Q[j] = f_fma(m3[a], sp.n[a], sp.qf[a]) + f_fma(m3[b], sp.n[b], sp.qf[b]);
+        Q[j] = f_fma(u[a], sp.n[a], sp.qf[a]) + f_fma(u[b], sp.n[b], sp.qf[b]);
         crE[j] = coef * rE[j];
         crE2[j] = crE[j] * rE[j];
-        s3[j] = f_fma(sp.r1[a], 1.0 + m3[a], sp.r2[b] * (2.0 + m3[b]));
-        s4[j] = f_fma(sp.r2[a], 2.0 + m3[a], sp.r1[b] * (1.0 + m3[b]));
+        s3[j] = f_fma(sp.r1[a], u[a], sp.r2[b] * v[b]);
+        s4[j] = f_fma(sp.r2[a], v[a], sp.r1[b] * u[b]);
         gp[j] = sp.r1[a] + sp.r2[b];
         gpb[j] = sp.r2[a] + sp.r1[b];
         hpp[j] = f_fma(sp.r1[a], sp.r1[a], sp.r2[b] * sp.r2[b]);
@@ -603,14 +607,24 @@ PNJL_HD void th_pair_fast(const FastCtx& fc, double mu, double M2u, double M2s, 
         tu[2] = f_fma(coef, Lu, tu[2]);
         ts[2] = f_fma(coef, Ls, ts[2]);
     }
-    tu[3] = f_fma(coef, f_fma(sp.n[0], E[0] - mu, sp.n[1] * (E[0] + mu)), tu[3]);
-    ts[3] = f_fma(coef, f_fma(sp.n[2], E[1] - mu, sp.n[3] * (E[1] + mu)), ts[3]);
+    // n+ (E - mu) + n- (E + mu) = E (n+ + n-) - mu (n+ - n-): the loop accumulates sum c E (n+ + n-) only, the caller
+    // subtracts mu (sum c n+ - sum c n-) from the slots it has anyway (th_pair_finish)
+    const double nsu = sp.n[0] + sp.n[1], nss = sp.n[2] + sp.n[3];
+    tu[3] = f_fma(coef, E[0] * nsu, tu[3]);
+    ts[3] = f_fma(coef, E[1] * nss, ts[3]);
     if (WITH_F) {
-        s1u = f_fma(coef * rE[0], sp.n[0] + sp.n[1], s1u);
-        s1s = f_fma(coef * rE[1], sp.n[2] + sp.n[3], s1s);
+        s1u = f_fma(coef * rE[0], nsu, s1u);
+        s1s = f_fma(coef * rE[1], nss, s1s);
         gsh[0] = f_fma(coef, f_fma(2.0, sp.r1[0] + sp.r2[1], sp.r1[2] + sp.r2[3]), gsh[0]);
         gsh[1] = f_fma(coef, f_fma(2.0, sp.r2[0] + sp.r1[1], sp.r2[2] + sp.r1[3]), gsh[1]);
     }
+}
+
+// After a th_pair_fast loop: turn slot 3 into sum c [n+ (E - mu) + n- (E + mu)] (see there).  Linear, so it may be applied
+// to per-lane partial sums.
+PNJL_HD void th_pair_finish(double mu, double tu[4], double ts[4]) {
+    tu[3] = f_fma(-mu, tu[0] - tu[1], tu[3]);
+    ts[3] = f_fma(-mu, ts[0] - ts[1], ts[3]);
 }
 
 // Mesh slice seen by one lane: nodes lane, lane+stride, ...   (host build: lane 0, stride 1)
@@ -877,6 +891,7 @@ PNJL_HD void thermo_partial(const Model& m, bool isospin, const PointCtx& c, con
                     const double k2 = f_fma(c.xi, mv.pc2[k], mv.p2[k]);
                     th_pair_fast<false, true>(fc, c.mu, c.M2[0], c.M2[2], k2, mv.coef[k], t0, t2, d0, d1, dg);
                 }
+                th_pair_finish(c.mu, t0, t2);
                 // t2[2] already holds 2 L_u + L_s; the combination below expects (L_u, L_d, L_s) = (t0, t1, t2)
 #pragma unroll
                 for (int q = 0; q < 4; ++q) t1[q] = t0[q];
@@ -887,6 +902,7 @@ PNJL_HD void thermo_partial(const Model& m, bool isospin, const PointCtx& c, con
                     const double k2 = f_fma(c.xi, mv.pc2[k], mv.p2[k]);
                     th_pair_fast<false, false>(fc, c.mu, c.M2[0], c.M2[2], k2, mv.coef[k], t0, t2, d0, d1, dg);
                 }
+                th_pair_finish(c.mu, t0, t2);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) t1[q] = t0[q];
             }
@@ -944,6 +960,7 @@ PNJL_HD bool ft_partial(const Model& m, bool isospin, const PointCtx& c, const d
                 th_pair_fast<true, false>(fc, c.mu, c.M2[0], c.M2[2], k2, mv.coef[k], tu, ts, s1u, s1s, gsh);
             }
         }
+        th_pair_finish(c.mu, tu, ts);
         facc[0] = s1u; facc[1] = s1u; facc[2] = s1s;
         facc[3] = gsh[0]; facc[4] = gsh[1];
         tacc[TH_NP + 0] = tu[0]; tacc[TH_NP + 1] = tu[0]; tacc[TH_NP + 2] = ts[0];
