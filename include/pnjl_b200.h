@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define PNJL_ABI_VERSION 9
+#define PNJL_ABI_VERSION 10
 
 /* ---- result record layout (doubles) --------------------------------------------------------- */
 #define PNJL_REC_DOUBLES 32
@@ -235,6 +235,14 @@ int pnjl_scan_lines_couplings_host(pnjl_handle* h, int64_t n_lines, const double
  * FJ: [n][30] = F[5] then J[5][5] row-major. */
 int pnjl_eval_fj_host(pnjl_handle* h, int64_t n, const double* T_fm, const double* mu_fm, const double* xi,
                       const double* x /* [n][5] */, double* FJ);
+
+/* F, J and the thermodynamic functions at given states x (no solve): what ThermoDerivatives.jl evaluates around a solution
+ * (gap_conditions :88-98, calculate_thermo / calculate_rho :360-420).  out: [n][48] =
+ * F[5], J[5][5] row-major, then Omega 30, P 31, rho_norm 32, s 33, eps 34, rho_i[3] 35, n_q[3] 38, n_qbar[3] 41, M_i[3] 44, 0.
+ * julia_relaxtime_b200/thermo_derivatives.py builds bulk_viscosity_coefficients / thermo_derivatives / mass_derivatives on it. */
+#define PNJL_STATE_DOUBLES 48
+int pnjl_eval_state_host(pnjl_handle* h, int64_t n, const double* T_fm, const double* mu_fm, const double* xi,
+                         const double* x /* [n][5] */, double* out);
 
 /* Accuracy self-test of the kernels' branch-free FP64 primitives (test hook):
  * which = 0: exp(x) for x in [-708, 0];  1: 1/x;  2: 1/sqrt(x)  (x normal, positive for 1 and 2). */

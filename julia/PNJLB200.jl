@@ -145,6 +145,17 @@ function dual_branch(e::Engine, T_MeV::Vector{Float64}, xi::Vector{Float64}, mu_
     return rec
 end
 
+"""F (5), J (5x5 row-major) and the thermodynamic functions at given states `x` (5, n) without solving: `Matrix{Float64}(48, n)`
+(PNJL_STATE layout: F 1:5, J 6:30, Ω 31, P 32, ρ_norm 33, s 34, ε 35, ρ_i 36:38, n_q 39:41, n_q̄ 42:44, M_i 45:47)."""
+function eval_state(e::Engine, T_fm::Vector{Float64}, mu_fm::Vector{Float64}, xi::Vector{Float64}, x::Matrix{Float64})
+    n = length(T_fm)
+    out = Matrix{Float64}(undef, 48, n)
+    check(ccall((:pnjl_eval_state_host, LIB), Cint,
+                (Ptr{Cvoid}, Int64, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+                e.handle, n, T_fm, mu_fm, xi, x, out), "pnjl_eval_state_host")
+    return out
+end
+
 # ---- one-loop integral A and effective couplings (build_K_data, run_gap_transport_scan.jl:297-305) -----------------
 """Replace the rule of A (default: DEFAULT_MOMENTUM_NODES / DEFAULT_MOMENTUM_WEIGHTS)."""
 function set_oneloop_rule!(e::Engine, nodes::Vector{Float64}, weights::Vector{Float64})

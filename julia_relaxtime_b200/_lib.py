@@ -87,6 +87,7 @@ def load():
     L.pnjl_effective_couplings_device.argtypes = [H, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pnjl_scan_lines_couplings_host.argtypes = [H, C.c_int64, dp, dp, ip, C.c_int32, dp, dp, dp]
     L.pnjl_eval_fj_host.argtypes = [H, C.c_int64, dp, dp, dp, dp, dp]
+    L.pnjl_eval_state_host.argtypes = [H, C.c_int64, dp, dp, dp, dp, dp]
     L.pnjl_selftest_math.argtypes = [H, C.c_int64, dp, C.c_int32, dp]
     L.pnjl_get_stats.argtypes = [H, C.POINTER(_abi.PnjlStats)]
     L.pnjl_measure_fp64_peak.argtypes = [H, C.c_double, dp, dp]
@@ -100,7 +101,7 @@ EXPORTED_SYMBOLS = [
     "pnjl_default_config", "pnjl_alloc_pinned", "pnjl_free_pinned", "pnjl_abi_version", "pnjl_last_error", "pnjl_create", "pnjl_destroy", "pnjl_gauleg",
     "pnjl_solve_points_host", "pnjl_solve_points_device", "pnjl_set_boundaries", "pnjl_scan_lines_host",
     "pnjl_scan_lines_device", "pnjl_set_oneloop_rule", "pnjl_effective_couplings_host",
-    "pnjl_effective_couplings_device", "pnjl_scan_lines_couplings_host", "pnjl_dual_branch_host", "pnjl_dual_branch_device", "pnjl_tmu_scan_host", "pnjl_tmu_scan_device", "pnjl_eval_fj_host", "pnjl_selftest_math", "pnjl_get_stats", "pnjl_measure_fp64_peak"]
+    "pnjl_effective_couplings_device", "pnjl_scan_lines_couplings_host", "pnjl_dual_branch_host", "pnjl_dual_branch_device", "pnjl_tmu_scan_host", "pnjl_tmu_scan_device", "pnjl_eval_fj_host", "pnjl_eval_state_host", "pnjl_selftest_math", "pnjl_get_stats", "pnjl_measure_fp64_peak"]
 
 
 class PinnedArray:
@@ -307,6 +308,19 @@ class Engine:
         self._check(self.L.pnjl_eval_fj_host(self.h, n, _abi.dptr(T_fm), _abi.dptr(mu_fm), _abi.dptr(xi), _abi.dptr(x),
                                              _abi.dptr(FJ)), "pnjl_eval_fj_host")
         return FJ[:, :5].copy(), FJ[:, 5:].reshape(n, 5, 5).copy()
+
+    def eval_state(self, T_fm, mu_fm, xi, x):
+        """F, J and the thermodynamic functions at given states (no solve): dict of arrays."""
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, 5)
+        n = x.shape[0]
+        T_fm, mu_fm, xi = _abi.as_f64(T_fm, n), _abi.as_f64(mu_fm, n), _abi.as_f64(xi, n)
+        out = np.empty((n, 48))
+        self._check(self.L.pnjl_eval_state_host(self.h, n, _abi.dptr(T_fm), _abi.dptr(mu_fm), _abi.dptr(xi), _abi.dptr(x),
+                                                _abi.dptr(out)), "pnjl_eval_state_host")
+        return dict(F=out[:, :5].copy(), J=out[:, 5:30].reshape(n, 5, 5).copy(), omega=out[:, 30].copy(),
+                    pressure=out[:, 31].copy(), rho_norm=out[:, 32].copy(), entropy=out[:, 33].copy(),
+                    energy=out[:, 34].copy(), rho=out[:, 35:38].copy(), n_q=out[:, 38:41].copy(),
+                    n_qbar=out[:, 41:44].copy(), masses=out[:, 44:47].copy())
 
     # ---- device-pointer entry points (torch tensors are only used for their data_ptr) --------------
     def solve_points_device(self, d_T, d_mu, d_xi, d_records, seed_mode=_abi.SEED_MULTI, d_seeds=None, n_seeds=6,

@@ -777,20 +777,32 @@ template <int G>
 __global__ void __launch_bounds__(512, 1) k_eval_fj(const DeviceConfig* __restrict__ cfg, const double* __restrict__ g_mesh,
                                                  long long n, const double* __restrict__ T_fm, const double* __restrict__ mu_fm,
                                                  const double* __restrict__ xi, const double* __restrict__ x,
-                                                 double* __restrict__ FJ, unsigned long long* counter) {
+                                                 double* __restrict__ FJ, unsigned long long* counter, int with_thermo) {
     extern __shared__ double s_mesh[];
     __shared__ int s_done;
     stage_mesh<G>(g_mesh, 3 * cfg->n_nodes + 2 * cfg->n_iso, s_mesh, &s_done);
     GroupEval<G> ev = make_eval<G>(cfg, s_mesh, &s_done);
+    const int stride = with_thermo ? PNJL_STATE_DOUBLES : 30;
     for (;;) {
         const long long i = next_task<G>(counter, ev);
         if (i >= n) break;
         double xs[5], F[5], J[25];
         copy5(xs, x + 5 * i);
         ev.fj(T_fm[i], mu_fm[i], xi[i], xs, F, J);
+        double* o = FJ + (long long)stride * i;
         if (ev.lane == 0) {
-            for (int q = 0; q < 5; ++q) FJ[30 * i + q] = F[q];
-            for (int q = 0; q < 25; ++q) FJ[30 * i + 5 + q] = J[q];
+            for (int q = 0; q < 5; ++q) o[q] = F[q];
+            for (int q = 0; q < 25; ++q) o[5 + q] = J[q];
+        }
+        if (with_thermo) {
+            // the thermodynamic functions at the same (not necessarily converged) state: Thermodynamics.jl:215-281
+            Thermo th;
+            ev.thermo(T_fm[i], mu_fm[i], xi[i], xs, th);
+            if (ev.lane == 0) {
+                o[30] = th.omega; o[31] = th.pressure; o[32] = th.rho_norm; o[33] = th.entropy; o[34] = th.energy;
+                for (int q = 0; q < 3; ++q) { o[35 + q] = th.rho[q]; o[38 + q] = th.nq[q]; o[41 + q] = th.nqb[q]; o[44 + q] = th.M[q]; }
+                o[47] = 0.0;
+            }
         }
     }
     ev.drain();
@@ -1101,13 +1113,13 @@ int launch_lines(pnjl_handle* h, long long n_lines, const double* muq, const dou
 
 template <int G>
 int launch_fj(pnjl_handle* h, long long n, const double* T, const double* mu, const double* xi, const double* x,
-              double* FJ, cudaStream_t st) {
+              double* FJ, cudaStream_t st, int with_thermo) {
     const size_t smem = sizeof(double) * (3 * h->n_nodes + 2 * h->host_cfg.n_iso);
     int blocks, threads;
     int rc = launch_geometry(h, k_eval_fj<G>, smem, n, G, &blocks, &threads);
     if (rc) return rc;
     CUDA_TRY(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned long long), st));
-    k_eval_fj<G><<<blocks, threads, smem, st>>>(h->d_cfg, h->d_mesh, n, T, mu, xi, x, FJ, h->d_counter);
+    k_eval_fj<G><<<blocks, threads, smem, st>>>(h->d_cfg, h->d_mesh, n, T, mu, xi, x, FJ, h->d_counter, with_thermo);
     CUDA_TRY(cudaGetLastError());
     h->stats.kernel_launches += 1;
     return PNJL_OK;
@@ -1161,11 +1173,11 @@ int dispatch_lines(pnjl_handle* h, long long n_lines, const double* muq, const d
     }
 }
 int dispatch_fj(pnjl_handle* h, long long n, const double* T, const double* mu, const double* xi, const double* x,
-                double* FJ, cudaStream_t st) {
+                double* FJ, cudaStream_t st, int with_thermo = 0) {
     switch (h->G) {
-        case 8: return launch_fj<8>(h, n, T, mu, xi, x, FJ, st);
-        case 16: return launch_fj<16>(h, n, T, mu, xi, x, FJ, st);
-        default: return launch_fj<32>(h, n, T, mu, xi, x, FJ, st);
+        case 8: return launch_fj<8>(h, n, T, mu, xi, x, FJ, st, with_thermo);
+        case 16: return launch_fj<16>(h, n, T, mu, xi, x, FJ, st, with_thermo);
+        default: return launch_fj<32>(h, n, T, mu, xi, x, FJ, st, with_thermo);
     }
 }
 
@@ -1716,8 +1728,9 @@ int pnjl_dual_branch_host(pnjl_handle* h, int64_t n_lines, const double* T_MeV, 
     return PNJL_OK;
 }
 
-int pnjl_eval_fj_host(pnjl_handle* h, int64_t n, const double* T, const double* mu, const double* xi, const double* x,
-                      double* FJ) {
+static int eval_state_impl(pnjl_handle* h, int64_t n, const double* T, const double* mu, const double* xi, const double* x,
+                           double* FJ, int with_thermo) {
+    const size_t stride = with_thermo ? PNJL_STATE_DOUBLES : 30;
     if (!h) return fail(PNJL_ERR_ARG, "null handle");
     if (n <= 0) return n == 0 ? PNJL_OK : fail(PNJL_ERR_ARG, "n < 0");
     if (!T || !mu || !xi || !x || !FJ) return fail(PNJL_ERR_ARG, "null buffer");
@@ -1727,7 +1740,7 @@ int pnjl_eval_fj_host(pnjl_handle* h, int64_t n, const double* T, const double* 
     CUDA_TRY(h->in_mu.reserve(nb));
     CUDA_TRY(h->in_xi.reserve(nb));
     CUDA_TRY(h->in_x.reserve(nb * 5));
-    CUDA_TRY(h->out_rec.reserve(nb * 30));
+    CUDA_TRY(h->out_rec.reserve(nb * stride));
     cudaStream_t st = h->stream;
     CUDA_TRY(cudaMemcpyAsync(h->in_T.p, T, nb, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(h->in_mu.p, mu, nb, cudaMemcpyHostToDevice, st));
@@ -1736,15 +1749,23 @@ int pnjl_eval_fj_host(pnjl_handle* h, int64_t n, const double* T, const double* 
     h->stats.kernel_launches = 0;
     CUDA_TRY(cudaEventRecord(h->ev0, st));
     int rc = dispatch_fj(h, n, (const double*)h->in_T.p, (const double*)h->in_mu.p, (const double*)h->in_xi.p,
-                         (const double*)h->in_x.p, (double*)h->out_rec.p, st);
+                         (const double*)h->in_x.p, (double*)h->out_rec.p, st, with_thermo);
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(h->ev1, st));
-    CUDA_TRY(cudaMemcpyAsync(FJ, h->out_rec.p, nb * 30, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(FJ, h->out_rec.p, nb * stride, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     float ms = 0;
     CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     h->stats.kernel_ms = ms;
     return PNJL_OK;
+}
+int pnjl_eval_fj_host(pnjl_handle* h, int64_t n, const double* T, const double* mu, const double* xi, const double* x,
+                      double* FJ) {
+    return eval_state_impl(h, n, T, mu, xi, x, FJ, 0);
+}
+int pnjl_eval_state_host(pnjl_handle* h, int64_t n, const double* T, const double* mu, const double* xi, const double* x,
+                         double* out) {
+    return eval_state_impl(h, n, T, mu, xi, x, out, 1);
 }
 
 int pnjl_selftest_math(pnjl_handle* h, int64_t n, const double* x, int32_t which, double* out) {

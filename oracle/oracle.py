@@ -335,3 +335,25 @@ def _dual_branch(self, T_MeV, xi, mu_MeV):
 
 
 Oracle.dual_branch = _dual_branch
+
+
+TD_NAMES = ("v_n_sq", "dmuB_dT_sigma", "M_u", "M_d", "M_s", "dM_u_dT", "dM_d_dT", "dM_s_dT", "dM_u_dmuB", "dM_d_dmuB",
+            "dM_s_dmuB", "s", "n_B", "P", "eps", "dP_dT", "dP_dmu", "dEps_dT", "dEps_dmu", "dn_dT", "dn_dmu", "dP_deps_n",
+            "dP_dn_eps", "dM_u_dmu", "dM_d_dmu", "dM_s_dmu")
+
+
+def _thermo_derivatives(self, T_fm, mu_fm, xi, x):
+    """ThermoDerivatives.jl (bulk_viscosity_coefficients, thermo_derivatives, mass_derivatives order 1) at given converged
+    states x [n, 5]: dict name -> array, by exact AD of Omega over (x, T, mu)."""
+    x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, 5)
+    n = x.shape[0]
+    T_fm = np.ascontiguousarray(np.broadcast_to(np.atleast_1d(T_fm), (n,)), dtype=np.float64)
+    mu_fm = np.ascontiguousarray(np.broadcast_to(np.atleast_1d(mu_fm), (n,)), dtype=np.float64)
+    xi = np.ascontiguousarray(np.broadcast_to(np.atleast_1d(xi), (n,)), dtype=np.float64)
+    out = np.zeros((n, 32))
+    self.lib.oracle_thermo_derivatives.restype = None
+    self.lib.oracle_thermo_derivatives(C.byref(self.cfg), C.c_int64(n), _dp(T_fm), _dp(mu_fm), _dp(xi), _dp(x), _dp(out))
+    return {name: out[:, i].copy() for i, name in enumerate(TD_NAMES)}
+
+
+Oracle.thermo_derivatives = _thermo_derivatives

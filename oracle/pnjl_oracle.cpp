@@ -1382,6 +1382,128 @@ int32_t oracle_dual_branch(const oracle_config* c, int64_t n_lines, const double
     return 0;
 }
 
+// ---- thermodynamic derivatives ---------------------------------------------------------------------------------------
+// src/pnjl/derivatives/ThermoDerivatives.jl differentiates through the solve with ImplicitDifferentiation.jl
+// (dx/dtheta = -J^-1 dF/dtheta, :80-109) and ForwardDiff on calculate_thermo / calculate_rho.  Restated with one nested
+// dual evaluation of Omega over the seven variables (x[5], T, mu_q): value, gradient and Hessian of P = -Omega.
+using D7 = Dual<7, double>;
+using D77 = Dual<7, D7>;
+
+// out[57] = P, grad P [7], Hess P [7][7] (row-major), variable order phi_u, phi_d, phi_s, Phi, Phibar, T, mu_q
+static void pressure_hessian7(const Problem& pb, const double x[5], double* out) {
+    D77 v[7];
+    const double base[7] = {x[0], x[1], x[2], x[3], x[4], pb.T, pb.mu};
+    for (int i = 0; i < 7; ++i) {
+        v[i] = Zero<D77>::make();
+        v[i].v.v = base[i];
+        v[i].v.d[i] = 1.0;
+        v[i].d[i].v = 1.0;
+    }
+    D77 mu[3] = {v[6], v[6], v[6]};
+    D77 om = calculate_omega(v, mu, v[5], *pb.mesh, pb.xi, *pb.k);
+    out[0] = -om.v.v;
+    for (int i = 0; i < 7; ++i) {
+        out[1 + i] = -om.v.d[i];
+        for (int j = 0; j < 7; ++j) out[8 + 7 * i + j] = -om.d[j].d[i];
+    }
+}
+
+static bool solve5_multi(const double J[25], const double* rhs, int nrhs, double* sol) {
+    // Gaussian elimination with partial pivoting, nrhs right-hand sides stored as rhs[r * 5 + i]
+    double A[5][5 + 4];
+    for (int i = 0; i < 5; ++i) {
+        for (int j = 0; j < 5; ++j) A[i][j] = J[i * 5 + j];
+        for (int r = 0; r < nrhs; ++r) A[i][5 + r] = rhs[r * 5 + i];
+    }
+    for (int c = 0; c < 5; ++c) {
+        int piv = c;
+        for (int i = c + 1; i < 5; ++i) if (std::fabs(A[i][c]) > std::fabs(A[piv][c])) piv = i;
+        if (A[piv][c] == 0.0) return false;
+        if (piv != c) for (int j = 0; j < 5 + nrhs; ++j) std::swap(A[piv][j], A[c][j]);
+        for (int i = c + 1; i < 5; ++i) {
+            const double f = A[i][c] / A[c][c];
+            for (int j = c; j < 5 + nrhs; ++j) A[i][j] -= f * A[c][j];
+        }
+    }
+    for (int r = 0; r < nrhs; ++r)
+        for (int i = 4; i >= 0; --i) {
+            double acc = A[i][5 + r];
+            for (int j = i + 1; j < 5; ++j) acc -= A[i][j] * sol[r * 5 + j];
+            sol[r * 5 + i] = acc / A[i][i];
+        }
+    return true;
+}
+
+// For n given states x (normally converged solutions at (T, mu, xi)):
+//   out[n][32] = [0] v_n_sq, [1] dmuB_dT_sigma, [2..4] masses (compute_masses_from_state, :111-121, with ITS bare masses
+//   5.5/197.327 and 140.0/197.327), [5..7] dM_dT, [8..10] dM_dmuB, [11] s, [12] n_B       bulk_viscosity_coefficients :342-467
+//   [13] P, [14] eps, [15] dP_dT, [16] dP_dmu, [17] dEps_dT, [18] dEps_dmu, [19] dn_dT, [20] dn_dmu,
+//   [21] dP_deps_n, [22] dP_dn_eps, [23..25] dM_dmu (per mu_q)                            thermo_derivatives :186-250, mass_derivatives :132-150
+void oracle_thermo_derivatives(const oracle_config* c, int64_t n, const double* T_fm, const double* mu_fm, const double* xi,
+                               const double* x, double* out) {
+    Consts k = consts_of(c);
+    Mesh m = mesh_of(c);
+#ifdef _OPENMP
+    int nt = c->n_threads > 0 ? c->n_threads : omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nt)
+#endif
+    for (int64_t p = 0; p < n; ++p) {
+        Problem pb{&k, &m, T_fm[p], mu_fm[p], xi[p]};
+        const double* xs = x + 5 * p;
+        double h[57];
+        pressure_hessian7(pb, xs, h);
+        const double P = h[0];
+        const double* g = h + 1;
+        auto H = [&](int i, int j) { return h[8 + 7 * i + j]; };
+        double J[25], rhs[10], dx[10];
+        for (int i = 0; i < 5; ++i) {
+            for (int j = 0; j < 5; ++j) J[i * 5 + j] = H(i, j);
+            rhs[i] = -H(i, 5);        // -dF/dT
+            rhs[5 + i] = -H(i, 6);    // -dF/dmu
+        }
+        double* o = out + 32 * p;
+        for (int q = 0; q < 32; ++q) o[q] = std::numeric_limits<double>::quiet_NaN();
+        if (!solve5_multi(J, rhs, 2, dx)) continue;
+        const double* dxT = dx;
+        const double* dxM = dx + 5;
+        const double T = pb.T, mu = pb.mu;
+        const double s = g[5], nB = g[6] / 3.0;
+        auto dot5 = [](const double* a, const double* b) { double r = 0; for (int i = 0; i < 5; ++i) r += a[i] * b[i]; return r; };
+        double ds_dx[5], dn_dx[5], F[5];
+        for (int i = 0; i < 5; ++i) { ds_dx[i] = H(5, i); dn_dx[i] = H(6, i) / 3.0; F[i] = g[i]; }
+        const double ds_dT = H(5, 5) + dot5(ds_dx, dxT);
+        const double ds_dmu = H(5, 6) + dot5(ds_dx, dxM);
+        const double dn_dT = H(6, 5) / 3.0 + dot5(dn_dx, dxT);
+        const double dn_dmu = H(6, 6) / 3.0 + dot5(dn_dx, dxM);
+        // dM/dx  (compute_masses_from_state differs from the solver's masses only in the bare masses)
+        const double G4 = -4 * k.G, K2 = 2 * k.K;
+        const double dM[3][5] = {{G4, K2 * xs[2], K2 * xs[1], 0, 0}, {K2 * xs[2], G4, K2 * xs[0], 0, 0}, {K2 * xs[1], K2 * xs[0], G4, 0, 0}};
+        const double mu0 = 0.0055 / 0.197327, ms0 = 0.140 / 0.197327;
+        o[2] = mu0 + G4 * xs[0] + K2 * xs[1] * xs[2];
+        o[3] = mu0 + G4 * xs[1] + K2 * xs[0] * xs[2];
+        o[4] = ms0 + G4 * xs[2] + K2 * xs[0] * xs[1];
+        for (int i = 0; i < 3; ++i) {
+            o[5 + i] = dot5(dM[i], dxT);
+            o[23 + i] = dot5(dM[i], dxM);
+            o[8 + i] = o[23 + i] / 3.0;
+        }
+        const double ds_dmuB = ds_dmu / 3.0, dn_dmuB = dn_dmu / 3.0;
+        o[0] = (s * dn_dmuB - nB * dn_dT) / (T * (ds_dT * dn_dmuB - ds_dmuB * dn_dT));
+        o[1] = -(nB * ds_dT - s * dn_dT) / (nB * ds_dmuB - s * dn_dmuB);
+        o[11] = s;
+        o[12] = nB;
+        // totals along the solution
+        const double P_T = s + dot5(F, dxT), P_mu = g[6] + dot5(F, dxM);
+        const double eps = -P + mu * g[6] + T * s;
+        const double E_T = -P_T + mu * 3.0 * dn_dT + s + T * ds_dT;
+        const double E_mu = -P_mu + g[6] + mu * 3.0 * dn_dmu + T * ds_dmu;
+        o[13] = P; o[14] = eps; o[15] = P_T; o[16] = P_mu; o[17] = E_T; o[18] = E_mu; o[19] = dn_dT; o[20] = dn_dmu;
+        const double den_e = E_T * dn_dmu - E_mu * dn_dT, den_n = dn_dT * E_mu - dn_dmu * E_T;
+        o[21] = den_e == 0 ? std::numeric_limits<double>::quiet_NaN() : (P_T * dn_dmu - P_mu * dn_dT) / den_e;
+        o[22] = den_n == 0 ? std::numeric_limits<double>::quiet_NaN() : (P_T * E_mu - P_mu * E_T) / den_n;
+    }
+}
+
 int32_t oracle_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

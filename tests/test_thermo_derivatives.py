@@ -1,0 +1,101 @@
+"""ThermoDerivatives: the oracle (exact AD over (x, T, mu)) against the reference's committed
+data/outputs/results/pnjl/{bulk_viscosity,derivatives}_xi0.0.csv (p_num=24, t_num=8; the T = 150 MeV rows — the T = 160 MeV
+rows of those files sit on an unphysical root, M_u = -636 MeV, of the solver version that wrote them), and the GPU path
+(pnjl_eval_state_host + fourth-order differences) against the oracle."""
+import numpy as np
+import pytest
+
+from oracle.oracle import HBARC, Oracle
+
+# rows 1-2 of bulk_viscosity_xi0.0.csv and derivatives_xi0.0.csv (T = 150 MeV; mu = 0, 50 MeV), %.6e / %.6f as printed
+GOLD_BULK = {
+    "v_n_sq": (7.879846e-02, 7.951898e-02), "dmuB_dT_sigma": (None, -2.179307e+00),
+    "M_u": (363.909334, 363.453557), "M_d": (363.909334, 363.453557), "M_s": (546.453381, 546.184966),
+    "dM_u_dT": (-3.035097e-01, -3.475445e-01), "dM_s_dT": (-1.929164e-01, -2.197904e-01),
+    "dM_u_dmuB": (None, -6.608376e-03), "dM_s_dmuB": (None, -3.890179e-03),
+    "s": (1.668448e-01, 1.832041e-01), "n_B": (None, 2.278966e-03)}
+GOLD_DERIV = {
+    "dM_u_dmu": (None, -1.982513e-02), "dM_s_dmu": (None, -1.167054e-02), "dP_dT": (1.668448e-01, 1.832041e-01),
+    "dP_dmu": (None, 6.836898e-03), "dEps_dT": (2.117361e+00, 2.415916e+00), "dEps_dmu": (None, 1.147412e-01),
+    "dn_dT": (None, 4.634741e-02), "dn_dmu": (7.617229e-03, 1.190139e-02), "P": (2.161791e+01, 2.161871e+01),
+    "eps": (-2.149108e+01, -2.147771e+01)}
+
+
+@pytest.fixture(scope="module")
+def orc():
+    return Oracle(p_num=24, t_num=8, max_iter=1000)
+
+
+def _oracle_at(orc, T_MeV, mu_MeV, xi=0.0):
+    T, mu = np.asarray(T_MeV, dtype=float) / HBARC, np.asarray(mu_MeV, dtype=float) / HBARC
+    r = orc.solve_points(T, mu, np.broadcast_to(xi, T.shape), "auto")
+    assert r.converged.all()
+    x = np.array([r.x[q] for q in range(5)]).T
+    return x, orc.thermo_derivatives(T, mu, xi, x)
+
+
+def test_oracle_reproduces_reference_derivative_tables(orc):
+    _, d = _oracle_at(orc, [150.0, 150.0], [0.0, 50.0])
+    for table in (GOLD_BULK, GOLD_DERIV):
+        for k, gold in table.items():
+            for i, g in enumerate(gold):
+                if g is None:
+                    assert abs(d[k][i]) < 1e-10, (k, d[k][i])       # round-off noise upstream too (1e-16 .. 1e-12)
+                    continue
+                v = d[k][i] * (HBARC if k in ("M_u", "M_d", "M_s") else 1.0)
+                assert abs(v - g) <= 6e-7 * abs(g), (k, i, v, g)    # 7 printed digits
+    assert abs(d["dmuB_dT_sigma"][0]) < 1e-10                        # upstream prints -2.6e-12 at mu = 0
+
+
+def test_oracle_derivatives_against_its_own_finite_differences(orc):
+    """The AD Hessian is consistent with differences of the oracle's own solve (an independent route through NLsolve)."""
+    T0, mu0 = 150.0 / HBARC, 50.0 / HBARC
+    _, d = _oracle_at(orc, [150.0], [50.0])
+    h = 1e-4 * T0
+    Ts = np.array([T0 - h, T0 + h, T0, T0])
+    Ms = np.array([mu0, mu0, mu0 - h, mu0 + h])
+    r = orc.solve_points(Ts, Ms, np.zeros(4), "auto")
+    M = np.asarray(r.mass)          # solver masses (bare masses differ by constants only -> same derivatives)
+    assert abs((M[0][1] - M[0][0]) / (2 * h) - d["dM_u_dT"][0]) < 1e-6
+    assert abs((M[2][3] - M[2][2]) / (2 * h) - d["dM_s_dmu"][0]) < 1e-6
+    assert abs((r.entropy[1] - r.entropy[0]) / (2 * h) - (d["dEps_dT"][0] - 3 * mu0 * d["dn_dT"][0]) / T0) < 1e-5
+
+
+@pytest.mark.gpu
+def test_gpu_thermo_derivatives_match_oracle_and_reference_tables(orc):
+    from julia_relaxtime_b200 import thermo_derivatives as td
+    from julia_relaxtime_b200._lib import Engine
+    e = Engine(p_num=24, t_num=8, max_iter=1000, nodes=(orc.p_nodes, orc.p_w, orc.c_nodes, orc.c_w))
+    T_MeV = np.array([150.0, 150.0, 100.0, 120.0, 200.0, 250.0, 140.0])
+    mu_MeV = np.array([0.0, 50.0, 200.0, 300.0, 100.0, 20.0, 250.0])
+    xi = np.array([0.0, 0.0, 0.0, 0.2, -0.4, 0.6, 0.0])
+    T, mu = T_MeV / HBARC, mu_MeV / HBARC
+    bulk = td.bulk_viscosity_coefficients(T, mu, xi=xi, engine=e)
+    thr = td.thermo_derivatives(T, mu, xi=xi, engine=e)
+    x, d = _oracle_at(orc, T_MeV, mu_MeV, xi)
+
+    def close(a, b, rel=2e-8, floor=1e-9):
+        return (np.abs(a - b) <= rel * np.abs(b) + floor * rel).all()
+
+    nz = mu_MeV > 0
+    assert close(bulk["v_n_sq"], d["v_n_sq"]) and close(bulk["dmuB_dT_sigma"][nz], d["dmuB_dT_sigma"][nz])
+    assert close(bulk["s"], d["s"], 1e-10) and close(bulk["n_B"], d["n_B"], 1e-9, 1e-3)
+    for i, f in enumerate("uds"):
+        assert close(bulk["masses"][:, i], d["M_" + f], 1e-10)
+        assert close(bulk["dM_dT"][:, i], d["dM_%s_dT" % f], 2e-8, 1e-4)
+        assert close(bulk["dM_dmuB"][:, i], d["dM_%s_dmuB" % f], 2e-8, 1e-4)
+        assert close(thr["dM_dmu"][:, i], d["dM_%s_dmu" % f], 2e-8, 1e-4)
+    for a, b in (("dP_dT", "dP_dT"), ("dP_dmu", "dP_dmu"), ("dEpsilon_dT", "dEps_dT"), ("dEpsilon_dmu", "dEps_dmu"),
+                 ("dn_dT", "dn_dT"), ("dn_dmu", "dn_dmu"), ("pressure", "P"), ("energy", "eps")):
+        assert close(thr[a], d[b], 2e-8, 1e-3), a
+    assert thr["converged"].all()
+    # the reference's own numbers, straight from the GPU path
+    assert abs(bulk["v_n_sq"][1] - 7.951898e-02) < 6e-9 and abs(bulk["dmuB_dT_sigma"][1] + 2.179307) < 2e-6
+    assert abs(bulk["masses"][0, 0] * HBARC - 363.909334) < 1e-6 and abs(bulk["masses"][0, 2] * HBARC - 546.453381) < 1e-6
+    assert abs(thr["dEpsilon_dT"][1] - 2.415916) < 2e-6
+    one = td.bulk_viscosity_coefficients(T[1], mu[1], engine=e)
+    assert np.ndim(one["v_n_sq"]) == 0 and abs(one["v_n_sq"] - bulk["v_n_sq"][1]) < 1e-14
+    md = td.mass_derivatives(T[:2], mu[:2], engine=e)
+    assert np.allclose(md["dM_dT"], bulk["dM_dT"][:2], rtol=0, atol=1e-13)
+    with pytest.raises(NotImplementedError):
+        td.mass_derivatives(T[0], mu[0], order=2, engine=e)
