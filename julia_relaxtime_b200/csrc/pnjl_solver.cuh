@@ -130,9 +130,12 @@ struct Solver {
     Ev& ev;
     double T, mu, xi;
     int n_fj, n_th, n_ft;   // full FJ passes, thermo-only passes, fused final passes (F + thermo)
+    int its_hint;           // Newton iterations the previous point of this line needed (0: unknown).  Along a continuity line
+                            // the residual sequence repeats almost exactly from point to point, so this predicts which pass
+                            // will be the last one; it only chooses the KIND of pass (fused final or not), never the iterates.
 
     PNJL_HD Solver(const Model& m_, const SolverParams& sp_, Ev& ev_)
-        : m(m_), sp(sp_), ev(ev_), T(0), mu(0), xi(0), n_fj(0), n_th(0), n_ft(0) {}
+        : m(m_), sp(sp_), ev(ev_), T(0), mu(0), xi(0), n_fj(0), n_th(0), n_ft(0), its_hint(0) {}
 
     PNJL_HD void set_point(double T_, double mu_, double xi_) { T = T_; mu = mu_; xi = xi_; }
 
@@ -174,7 +177,16 @@ struct Solver {
                 // NLsolve evaluates only F here and J at the top of the next iteration.  When the previous residual
                 // says this pass will most likely end the solve, run it as a fused final pass (F + thermo sums);
                 // otherwise fuse F with the next direction.  Either way the iterates are the same.
-                bool fused = (res <= sp.predict_tol) && ev.f_thermo(T, mu, xi, x, f, r.th);
+                // Prediction (predict_tol > 0): certain when the step is at most xtol (the x-criterion stops the solve
+                // whatever F is); otherwise "as many iterations as the previous point of the line", and the residual
+                // rule ||F|| <= predict_tol when there is no history or the solve outlasts it.
+                double pmax = 0.0;
+#pragma unroll
+                for (int i = 0; i < 5; ++i) pmax = fmax(pmax, fabs(p[i]));
+                const bool by_history = its_hint > 0 && it <= its_hint;
+                const bool predict = sp.predict_tol > 0.0 &&
+                                     (pmax <= sp.xtol || (by_history ? it == its_hint : res <= sp.predict_tol));
+                bool fused = predict && ev.f_thermo(T, mu, xi, x, f, r.th);
                 if (fused) ++n_ft;
                 else nonsing = FJ_step(x, f, p);
                 double dx = 0.0;
@@ -550,13 +562,17 @@ PNJL_HD_NOINL void scan_line(Solver<Ev>& sv, const PhaseTables* pt, int ti, doub
         sv.n_th = 0;
         sv.n_ft = 0;
         if (!tk.has_prev) {
+            sv.its_hint = 0;
             sv.solve_multi(nullptr, 6, r);
         } else {
             double x0[5];
             const bool sw = sv.tracker_seed(pt, ti, tk, x0);
+            if (sw) sv.its_hint = 0;               // re-seeded at a phase flip: no history for this point
             sv.solve_with_fallback(x0, r);
             if (sw) r.status |= PNJL_ST_PHASE_SWITCH;
         }
+        // history for the next point: plain Newton successes only (fallback results took another route)
+        sv.its_hint = (r.converged && !(r.status & (PNJL_ST_USED_TR | PNJL_ST_TR_ATTEMPTED | PNJL_ST_USED_MULTISEED))) ? r.it : 0;
         if (r.converged) {
             copy5(tk.prev, r.x);
             tk.has_prev = true;
