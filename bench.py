@@ -217,6 +217,9 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--gather", choices=("peer", "nccl"), default="peer",
+                    help="multi-GPU result collection: peer = every rank's kernel stores its records straight into rank 0's buffer "
+                         "over NVLink (CUDA IPC; falls back to nccl if the mapping cannot be set up); nccl = dist.gather after the kernel")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-flush", action="store_true", help="skip the L2 flush between steps (ncu traffic captures only)")
     ap.add_argument("--n-mu", type=int, default=0, help="override the mu density (profiling runs only; recorded in config)")
@@ -236,7 +239,7 @@ def main():
     from julia_relaxtime_b200 import _abi as A
     from julia_relaxtime_b200._lib import Engine
     from julia_relaxtime_b200.boundary import default_tables
-    from julia_relaxtime_b200.distributed import rank_line_indices, scan_sharded
+    from julia_relaxtime_b200.distributed import PeerRecords, rank_line_indices, scan_sharded, scan_sharded_peer
     from julia_relaxtime_b200.scan import build_grid
 
     rank = int(os.environ.get("RANK", "0"))
@@ -283,7 +286,21 @@ def main():
             eng.scan_lines_device(d_muq, d_xi, d_tidx, d_T, d_rec, stream)
             return d_rec
 
+        peer = None
+        if world > 1 and args.gather == "peer":
+            try:
+                peer = PeerRecords(grid.n_lines, n_T, rank, world, dev)
+                peer_inputs = dict(muq=d_muq, xi=d_xi, tidx=d_tidx, T=d_T,
+                                   out_index=torch.as_tensor(mine.astype(np.int64), device=dev))
+            except Exception as exc:                                     # noqa: BLE001 - any failure -> NCCL gather
+                if rank == 0:
+                    print("peer gather unavailable (%s); using dist.gather" % exc, file=sys.stderr)
+                peer = None
+
         def step():
+            if peer is not None:
+                full, _ = scan_sharded_peer(eng, grid, len(xis), n_mu, peer, rank, world, dev, stream, peer_inputs)
+                return full
             full, _ = scan_sharded(grid, len(xis), n_mu, compute, rank, world)
             return full
     else:
@@ -331,7 +348,13 @@ def main():
         barrier()
         e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         e0.record()
-        if kind == "lines":
+        if kind == "lines" and peer is not None:
+            # the kernel writes into rank 0's array itself; e1 = this rank's kernel, e2 after the closing barrier
+            eng.scan_lines_device_indexed(d_muq, d_xi, d_tidx, d_T, peer.ptr, peer_inputs["out_index"], stream)
+            e1.record()
+            torch.cuda.synchronize()
+            dist.barrier()
+        elif kind == "lines":
             compute(None)
             e1.record()
             full, _ = scan_sharded(grid, len(xis), n_mu, lambda _l: d_rec, rank, world)
@@ -347,6 +370,9 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     tot = torch.tensor([sum(step_ms), sum(kern_ms)], dtype=torch.float64, device=dev)
     # converged points / evaluation counts of this rank's slab (identical every step; counted once)
+    if kind == "lines" and peer is not None:
+        compute(None)                    # untimed: this rank's slab once more into its local buffer, for the counts below
+        torch.cuda.synchronize()
     r2 = d_rec.reshape(-1, A.REC_DOUBLES)
     conv = ((r2[:, A.REC_STATUS].to(torch.int64) & 1) != 0).sum().to(torch.float64)
     # quadrature nodes a pass actually sweeps at each point: p_num when xi == 0 (isotropic collapse: the cos(theta) sum
@@ -430,7 +456,9 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": w, "description": DESCR[w], "points": int(n_total), "converged": int(n_conv),
-                       "nodes": "%dx%d" % (p, t), "max_iter": MAX_ITER, "sharding": "contiguous mu-slabs, %d rank(s)" % world,
+                       "nodes": "%dx%d" % (p, t), "max_iter": MAX_ITER, "sharding": "contiguous mu-slabs, %d rank(s)" % world + ("" if world == 1 else (
+                      "; records stored by every rank's kernel directly into rank 0's array (CUDA IPC, NVLink), closing barrier only"
+                      if (kind == "lines" and peer is not None) else "; dist.gather to rank 0 after the kernel")),
                        "l2": "512 MB buffer written between timed steps (L2 flush); inputs are O(100 KB), outputs 256 B/point",
                        "lanes_per_solve": st["lanes_per_solve"], "blocks": st["blocks"], "threads": st["threads"],
                        "regs_per_thread": st["regs_per_thread"]},

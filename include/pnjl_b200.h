@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define PNJL_ABI_VERSION 10
+#define PNJL_ABI_VERSION 11
 
 /* ---- result record layout (doubles) --------------------------------------------------------- */
 #define PNJL_REC_DOUBLES 32
@@ -171,6 +171,20 @@ int pnjl_scan_lines_host(pnjl_handle* h, int64_t n_lines, const double* muq_MeV,
 int pnjl_scan_lines_device(pnjl_handle* h, int64_t n_lines, const double* d_muq_MeV, const double* d_xi,
                            const int32_t* d_table_idx, int32_t n_T, const double* d_T_MeV, double* d_records,
                            void* stream);
+
+/* Same scan, but line l writes its n_T records at record line d_out_index[l] of d_records_base (instead of l).  With a base that
+ * is another GPU's buffer (pnjl_ipc_alloc on rank 0, pnjl_ipc_open on the others) every rank's kernel stores its mu-slab
+ * straight into rank 0's result array over NVLink while it runs: the final gather of the multi-GPU scan is fused into the
+ * kernel's stores and costs no time of its own (julia_relaxtime_b200/distributed.py: PeerRecords, scan_sharded_peer). */
+int pnjl_scan_lines_device_indexed(pnjl_handle* h, int64_t n_lines, const double* d_muq_MeV, const double* d_xi,
+                                   const int32_t* d_table_idx, int32_t n_T, const double* d_T_MeV, double* d_records_base,
+                                   const int64_t* d_out_index, void* stream);
+/* Device buffers that other processes on the node can map (CUDA IPC): alloc on the owner (current device), open/close on
+ * the peers (peer access is enabled on open), free on the owner after every peer closed. */
+int pnjl_ipc_alloc(uint64_t bytes, void** dptr, unsigned char handle[64]);
+int pnjl_ipc_open(const unsigned char handle[64], void** dptr);
+int pnjl_ipc_close(void* dptr);
+int pnjl_ipc_free(void* dptr);
 
 /* T-mu scan with TmuScan.run_tmu_scan semantics (src/pnjl/scans/TmuScan.jl:120-234): line l = (xi[l], T_MeV[l]) marches
  * mu_MeV[0..n_mu) in the given order with a fresh PhaseAwareContinuitySeed tracker per line, the four-candidate seed

@@ -3,7 +3,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 10
+ABI_VERSION = 11
 REC_DOUBLES = 32
 REC_X, REC_MASS, REC_OMEGA, REC_PRESSURE, REC_RHO_NORM, REC_ENTROPY, REC_ENERGY = 0, 5, 8, 9, 10, 11, 12
 REC_NQ, REC_NQBAR, REC_RESNORM, REC_ITER, REC_STATUS, REC_NEVAL, REC_RHO, REC_NTHERMO = 13, 16, 19, 20, 21, 22, 23, 26

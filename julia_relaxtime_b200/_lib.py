@@ -77,6 +77,12 @@ def load():
     L.pnjl_scan_lines_host.argtypes = [H, C.c_int64, dp, dp, ip, C.c_int32, dp, dp]
     L.pnjl_scan_lines_device.argtypes = [H, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                          C.c_void_p, C.c_void_p]
+    L.pnjl_scan_lines_device_indexed.argtypes = [H, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                                 C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pnjl_ipc_alloc.argtypes = [C.c_uint64, C.POINTER(C.c_void_p), C.c_char_p]
+    L.pnjl_ipc_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    L.pnjl_ipc_close.argtypes = [C.c_void_p]
+    L.pnjl_ipc_free.argtypes = [C.c_void_p]
     L.pnjl_tmu_scan_host.argtypes = [H, C.c_int64, dp, dp, ip, C.c_int32, dp, dp]
     L.pnjl_tmu_scan_device.argtypes = [H, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                        C.c_void_p, C.c_void_p]
@@ -100,7 +106,8 @@ def load():
 EXPORTED_SYMBOLS = [
     "pnjl_default_config", "pnjl_alloc_pinned", "pnjl_free_pinned", "pnjl_abi_version", "pnjl_last_error", "pnjl_create", "pnjl_destroy", "pnjl_gauleg",
     "pnjl_solve_points_host", "pnjl_solve_points_device", "pnjl_set_boundaries", "pnjl_scan_lines_host",
-    "pnjl_scan_lines_device", "pnjl_set_oneloop_rule", "pnjl_effective_couplings_host",
+    "pnjl_scan_lines_device", "pnjl_scan_lines_device_indexed", "pnjl_ipc_alloc", "pnjl_ipc_open", "pnjl_ipc_close",
+    "pnjl_ipc_free", "pnjl_set_oneloop_rule", "pnjl_effective_couplings_host",
     "pnjl_effective_couplings_device", "pnjl_scan_lines_couplings_host", "pnjl_dual_branch_host", "pnjl_dual_branch_device", "pnjl_tmu_scan_host", "pnjl_tmu_scan_device", "pnjl_eval_fj_host", "pnjl_eval_state_host", "pnjl_selftest_math", "pnjl_get_stats", "pnjl_measure_fp64_peak"]
 
 
@@ -336,6 +343,13 @@ class Engine:
             self.h, d_muq.numel(), d_muq.data_ptr(), d_xi.data_ptr(),
             d_table_idx.data_ptr() if d_table_idx is not None else None, d_T.numel(), d_T.data_ptr(),
             d_records.data_ptr(), C.c_void_p(stream)), "pnjl_scan_lines_device")
+
+    def scan_lines_device_indexed(self, d_muq, d_xi, d_table_idx, d_T, records_base_ptr, d_out_index, stream=0):
+        """records_base_ptr: integer device address (may be a peer GPU's buffer); d_out_index: int64 tensor [n_lines]."""
+        self._check(self.L.pnjl_scan_lines_device_indexed(
+            self.h, d_muq.numel(), d_muq.data_ptr(), d_xi.data_ptr(),
+            d_table_idx.data_ptr() if d_table_idx is not None else None, d_T.numel(), d_T.data_ptr(),
+            C.c_void_p(int(records_base_ptr)), d_out_index.data_ptr(), C.c_void_p(stream)), "pnjl_scan_lines_device_indexed")
 
     def selftest_math(self, x, which):
         """which: 'exp' (x in [-708, 0]), 'rcp', 'rsqrt' — the kernels' branch-free primitives evaluated on the GPU."""

@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(512, 1) k_scan_lines(const DeviceConfig* __res
                                                     long long n_lines, const double* __restrict__ muq_MeV,
                                                     const double* __restrict__ xi, const int* __restrict__ table_idx,
                                                     int n_T, const double* __restrict__ T_MeV, double* __restrict__ records,
-                                                    unsigned long long* counter, int mode) {
+                                                    unsigned long long* counter, int mode, const long long* __restrict__ out_index) {
     extern __shared__ double s_mesh[];
     __shared__ int s_done;
     stage_mesh<G>(g_mesh, 3 * cfg->n_nodes + 2 * cfg->n_iso, s_mesh, &s_done);
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(512, 1) k_scan_lines(const DeviceConfig* __res
         // mode 0: (xi, mu) line marching T (run_gap_transport_scan.jl); mode 1: (xi, T) line marching mu (TmuScan.jl);
         // mode 2: task l = branch (l & 1) of the (xi, T) line l >> 1 (DualBranchScan.jl), records [line][branch][mu]
         const long long li = mode == 2 ? (l >> 1) : l;
-        LineSink<G> sink{&ev, records + (long long)PNJL_REC_DOUBLES * n_T * l, xi[li]};
+        LineSink<G> sink{&ev, records + (long long)PNJL_REC_DOUBLES * n_T * (out_index ? out_index[l] : l), xi[li]};
         if (mode == 0) scan_line(sv, &cfg->pt, table_idx ? table_idx[l] : -1, muq_MeV[l], xi[l], n_T, T_MeV, sink);
         else if (mode == 1) scan_tmu_line(sv, &cfg->pt, table_idx ? table_idx[l] : -1, muq_MeV[l], xi[l], n_T, T_MeV, sink);
         else scan_branch_line(sv, muq_MeV[li], xi[li], n_T, T_MeV, (int)(l & 1), sink);
@@ -371,6 +371,7 @@ struct WsTask {
     // points
     const double* T_fm; const double* mu_fm; int seed_mode; int n_seeds; const double* seeds;
     double* records;
+    const long long* out_index;   // optional: task t writes its rows at record line out_index[t] instead of t (lines modes)
 };
 
 struct CtrlEval {
@@ -733,18 +734,18 @@ __global__ void __launch_bounds__(PNJL_WS_MAX_THREADS, 1) k_solve_ws(const Devic
         if (tk >= task.n_tasks) break;
         const long long t = (long long)(((unsigned long long)tk * (unsigned long long)task.perm_mult) % (unsigned long long)task.n_tasks);
         if (task.mode == 0) {
-            CtrlSink sink{task.records + (long long)PNJL_REC_DOUBLES * task.n_T * t, task.xi[t]};
+            CtrlSink sink{task.records + (long long)PNJL_REC_DOUBLES * task.n_T * (task.out_index ? task.out_index[t] : t), task.xi[t]};
             scan_line(sv, &cfg->pt, task.table_idx ? task.table_idx[t] : -1, task.muq_MeV[t], task.xi[t], task.n_T, task.T_MeV,
                       sink);
         } else if (task.mode == 2) {
             // here muq_MeV holds the line's T_MeV and T_MeV the shared mu grid
-            CtrlSink sink{task.records + (long long)PNJL_REC_DOUBLES * task.n_T * t, task.xi[t]};
+            CtrlSink sink{task.records + (long long)PNJL_REC_DOUBLES * task.n_T * (task.out_index ? task.out_index[t] : t), task.xi[t]};
             scan_tmu_line(sv, &cfg->pt, task.table_idx ? task.table_idx[t] : -1, task.muq_MeV[t], task.xi[t], task.n_T,
                           task.T_MeV, sink);
         } else if (task.mode == 3) {
             // dual-branch scan: task t = branch (t & 1) of line t >> 1; muq_MeV holds the lines' T_MeV, T_MeV the mu grid
             const long long li = t >> 1;
-            CtrlSink sink{task.records + (long long)PNJL_REC_DOUBLES * task.n_T * t, task.xi[li]};
+            CtrlSink sink{task.records + (long long)PNJL_REC_DOUBLES * task.n_T * (task.out_index ? task.out_index[t] : t), task.xi[li]};
             scan_branch_line(sv, task.muq_MeV[li], task.xi[li], task.n_T, task.T_MeV, (int)(t & 1), sink);
         } else {
             const double T = task.T_fm[t], mu = task.mu_fm[t], x_i = task.xi[t];
@@ -959,6 +960,7 @@ struct pnjl_handle {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     DevBuf in_T, in_mu, in_xi, in_seeds, in_idx, in_x, out_rec, out_aux, in_c[6];
+    const long long* out_index_next = nullptr;   // per-line output index for the next lines launch only (device pointer)
     double* d_rule = nullptr;      // one-loop rule: p^2 [n] | w p^2 [n]
     int n_rule = 0;
     pnjl_stats stats;
@@ -1085,6 +1087,7 @@ int launch_lines_ws(pnjl_handle* h, long long n_lines, const double* muq, const 
     WsTask t;
     std::memset(&t, 0, sizeof(t));
     t.mode = mode == 0 ? 0 : (mode == 1 ? 2 : 3); t.n_tasks = n_lines; t.muq_MeV = muq; t.xi = xi; t.table_idx = tidx; t.n_T = n_T; t.T_MeV = T; t.records = rec;
+    t.out_index = h->out_index_next;
     return launch_ws(h, t, st);
 }
 
@@ -1105,7 +1108,7 @@ int launch_lines(pnjl_handle* h, long long n_lines, const double* muq, const dou
     int rc = launch_geometry(h, k_scan_lines<G>, smem, n_lines, G, &blocks, &threads);
     if (rc) return rc;
     CUDA_TRY(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned long long), st));
-    k_scan_lines<G><<<blocks, threads, smem, st>>>(h->d_cfg, h->d_mesh, n_lines, muq, xi, tidx, n_T, T, rec, h->d_counter, mode);
+    k_scan_lines<G><<<blocks, threads, smem, st>>>(h->d_cfg, h->d_mesh, n_lines, muq, xi, tidx, n_T, T, rec, h->d_counter, mode, h->out_index_next);
     CUDA_TRY(cudaGetLastError());
     h->stats.kernel_launches += 1;
     return PNJL_OK;
@@ -1634,6 +1637,50 @@ int pnjl_scan_lines_couplings_host(pnjl_handle* h, int64_t n_lines, const double
     h->stats.kernel_launches += scan_launches;
     CUDA_TRY(cudaMemcpyAsync(aux, h->out_aux.p, nb, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return PNJL_OK;
+}
+
+int pnjl_scan_lines_device_indexed(pnjl_handle* h, int64_t n_lines, const double* d_muq, const double* d_xi,
+                                   const int32_t* d_tidx, int32_t n_T, const double* d_T, double* d_records_base,
+                                   const int64_t* d_out_index, void* stream) {
+    if (!h) return fail(PNJL_ERR_ARG, "null handle");
+    h->out_index_next = (const long long*)d_out_index;
+    const int rc = pnjl_scan_lines_device(h, n_lines, d_muq, d_xi, d_tidx, n_T, d_T, d_records_base, stream);
+    h->out_index_next = nullptr;
+    return rc;
+}
+
+// ---- peer-visible result buffers (multi-GPU: every rank's kernel stores its records straight into rank 0's buffer) ----
+int pnjl_ipc_alloc(uint64_t bytes, void** dptr, unsigned char handle[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    if (!dptr || !handle) return fail(PNJL_ERR_ARG, "null buffer");
+    *dptr = nullptr;
+    cudaError_t e = cudaMalloc(dptr, bytes ? bytes : 1);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(e == cudaErrorMemoryAllocation ? PNJL_ERR_NOMEM : PNJL_ERR_CUDA, cudaGetErrorString(e)); }
+    cudaIpcMemHandle_t hd;
+    e = cudaIpcGetMemHandle(&hd, *dptr);
+    if (e != cudaSuccess) { cudaGetLastError(); cudaFree(*dptr); *dptr = nullptr; return fail(PNJL_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)); }
+    std::memcpy(handle, &hd, 64);
+    return PNJL_OK;
+}
+int pnjl_ipc_open(const unsigned char handle[64], void** dptr) {
+    if (!dptr || !handle) return fail(PNJL_ERR_ARG, "null buffer");
+    cudaIpcMemHandle_t hd;
+    std::memcpy(&hd, handle, 64);
+    cudaError_t e = cudaIpcOpenMemHandle(dptr, hd, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { cudaGetLastError(); *dptr = nullptr; return fail(PNJL_ERR_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e)); }
+    return PNJL_OK;
+}
+int pnjl_ipc_close(void* dptr) {
+    if (!dptr) return PNJL_OK;
+    cudaError_t e = cudaIpcCloseMemHandle(dptr);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(PNJL_ERR_CUDA, cudaGetErrorString(e)); }
+    return PNJL_OK;
+}
+int pnjl_ipc_free(void* dptr) {
+    if (!dptr) return PNJL_OK;
+    cudaError_t e = cudaFree(dptr);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(PNJL_ERR_CUDA, cudaGetErrorString(e)); }
     return PNJL_OK;
 }
 

@@ -56,3 +56,86 @@ def scan_sharded(grid: ScanGrid, n_xi: int, n_mu: int, compute: Callable, rank: 
         return out, local
     dist.gather(send, None, dst=0, group=group)
     return None, local
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Gather fused into the kernel: every rank's scan kernel stores its records straight into rank 0's result array
+# (CUDA IPC mapping of one buffer, NVLink peer stores), so there is no collective after the kernel — only a barrier.
+# ------------------------------------------------------------------------------------------------------------
+class _DevArray:
+    """Minimal __cuda_array_interface__ carrier so torch can view a raw device allocation."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+class PeerRecords:
+    """The result array [n_lines, n_T, 32] of the whole grid, allocated on rank 0 and mapped into every other rank of the
+    node.  `ptr` is the address to hand to `Engine.scan_lines_device_indexed` on this rank; `tensor` (rank 0 only) is a torch
+    view of it.  Collective constructor (one small broadcast of the IPC handle); close() is collective too."""
+
+    def __init__(self, n_lines, n_T, rank, world_size, device, group=None):
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+
+        from ._lib import PnjlError, load
+        self.L, self.rank, self.world, self.group = load(), rank, world_size, group
+        self.shape = (int(n_lines), int(n_T), A.REC_DOUBLES)
+        nbytes = 8 * self.shape[0] * self.shape[1] * self.shape[2]
+        handle = C.create_string_buffer(64)
+        p = C.c_void_p()
+        ok = torch.ones(1, dtype=torch.int32, device=device)
+        if rank == 0:
+            if self.L.pnjl_ipc_alloc(C.c_uint64(nbytes), C.byref(p), handle) != 0:
+                ok.zero_()
+        h = torch.frombuffer(bytearray(handle.raw), dtype=torch.uint8).to(device)
+        if world_size > 1:
+            dist.broadcast(h, src=0, group=group)
+        if rank != 0:
+            hb = C.create_string_buffer(bytes(h.cpu().numpy().tobytes()), 64)
+            if self.L.pnjl_ipc_open(hb, C.byref(p)) != 0:
+                ok.zero_()
+        if world_size > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        self.ptr = p.value
+        if int(ok.item()) == 0:
+            err = self.L.pnjl_last_error().decode()
+            self.close(collective=False)
+            raise PnjlError("peer-visible result buffer could not be set up on every rank: %s" % err)
+        self.tensor = torch.as_tensor(_DevArray(self.ptr, self.shape), device=device) if rank == 0 else None
+
+    def close(self, collective=True):
+        import torch.distributed as dist
+        if not getattr(self, "ptr", None):
+            return
+        self.tensor = None
+        if self.rank != 0:
+            self.L.pnjl_ipc_close(self.ptr)
+        if collective and self.world > 1:
+            dist.barrier(group=self.group)          # every peer has unmapped before the owner frees
+        if self.rank == 0:
+            self.L.pnjl_ipc_free(self.ptr)
+        self.ptr = None
+
+
+def scan_sharded_peer(engine, grid: ScanGrid, n_xi: int, n_mu: int, peer: PeerRecords, rank: int, world_size: int,
+                      device, stream=0, inputs=None, group=None):
+    """This rank's mu-slab, written by the kernel directly into `peer` (global line order, the order of scan.build_grid).
+    `inputs` caches the device copies of this rank's line parameters between calls.  Returns (records on rank 0 | None,
+    inputs).  The only communication is the closing barrier."""
+    import torch
+    import torch.distributed as dist
+
+    if inputs is None:
+        mine = rank_line_indices(n_xi, n_mu, rank, world_size)
+        inputs = dict(muq=torch.as_tensor(grid.muq_MeV[mine], device=device), xi=torch.as_tensor(grid.xi[mine], device=device),
+                      tidx=torch.as_tensor(grid.table_idx[mine], device=device), T=torch.as_tensor(grid.T_MeV, device=device),
+                      out_index=torch.as_tensor(mine.astype(np.int64), device=device))
+    engine.scan_lines_device_indexed(inputs["muq"], inputs["xi"], inputs["tidx"], inputs["T"], peer.ptr, inputs["out_index"],
+                                     stream)
+    torch.cuda.synchronize(device)
+    if world_size > 1:
+        dist.barrier(group=group)                   # all slabs are in rank 0's buffer
+    return (peer.tensor if rank == 0 else None), inputs
