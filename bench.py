@@ -484,6 +484,8 @@ def main():
         print(json.dumps(out))
     if world > 1:
         dist.barrier()
+        if kind == "lines" and peer is not None:
+            peer.close()
         dist.destroy_process_group()
 
 
