@@ -600,6 +600,7 @@ PNJL_HD_NOINL void scan_tmu_line(Solver<Ev>& sv, const PhaseTables* pt, int ti, 
     const double T_fm = T_MeV / sv.m.hbarc;
     const double kAcceptable = 1e-4;
     PointRes r, a;
+    int line_hint = 0;
     for (int im = 0; im < n_mu; ++im) {
         const double mu_fm = mu_MeV[im] / sv.m.hbarc;
         sv.set_point(T_fm, mu_fm, xi);
@@ -610,9 +611,12 @@ PNJL_HD_NOINL void scan_tmu_line(Solver<Ev>& sv, const PhaseTables* pt, int ti, 
         bool success = false;
         for (int ci = 0; ci < 4 && !success; ++ci) {
             double x0[5];
-            if (ci == 0) sv.tracker_seed(pt, ti, tk, x0);
+            bool sw = false;
+            if (ci == 0) sw = sv.tracker_seed(pt, ti, tk, x0);
             else if (ci == 1) { if (!have_cache) continue; copy5(x0, cache); }
             else seed_const(((ci == 2) == quark_first) ? 1 : 0, x0);
+            // pass-kind prediction from the line's history only for the continuity candidate (see Solver::its_hint)
+            sv.its_hint = (ci == 0 && tk.has_prev && !sw) ? line_hint : 0;
             sv.solve_with_fallback(x0, a);
             if (a.status & PNJL_ST_NONFINITE) continue;
             const bool ok = a.converged || (finite_d(a.res) && a.res <= kAcceptable);
@@ -652,6 +656,8 @@ PNJL_HD_NOINL void scan_tmu_line(Solver<Ev>& sv, const PhaseTables* pt, int ti, 
             copy5(cache, r.x);
             have_cache = true;
         }
+        line_hint = (success && !(r.status & (PNJL_ST_USED_TR | PNJL_ST_TR_ATTEMPTED | PNJL_ST_USED_MULTISEED | PNJL_ST_REFINED |
+                                              PNJL_ST_PROMOTED | PNJL_ST_CAND_MASK))) ? r.it : 0;
         sink(im, r, T_fm, mu_fm, sv.n_fj, sv.n_th, sv.n_ft);
     }
 }
@@ -671,6 +677,7 @@ PNJL_HD_NOINL void scan_branch_line(Solver<Ev>& sv, double T_MeV, double xi, int
     double prev[5] = {0, 0, 0, 0, 0};
     double prev_Mu = 0.0;
     PointRes r;
+    int line_hint = 0;
     for (int k = 0; k < n_mu; ++k) {
         const int im = branch == 0 ? k : n_mu - 1 - k;
         const double mu_fm = mu_MeV[im] / sv.m.hbarc;
@@ -683,7 +690,9 @@ PNJL_HD_NOINL void scan_branch_line(Solver<Ev>& sv, double T_MeV, double xi, int
             double x0[5];
             if (has_prev) copy5(x0, prev);
             else default_seed(branch == 0 ? 0 : 1, T_fm, mu_fm, x0);
+            sv.its_hint = has_prev ? line_hint : 0;
             sv.solve_with_fallback(x0, r);
+            line_hint = (r.converged && !(r.status & (PNJL_ST_USED_TR | PNJL_ST_TR_ATTEMPTED | PNJL_ST_USED_MULTISEED))) ? r.it : 0;
             if (r.converged && !(r.status & PNJL_ST_NONFINITE)) {
                 const bool jump = has_prev && (fabs(prev[0] - r.x[0]) > 0.5 || fabs(prev_Mu - r.th.M[0]) * 197.327 > 50.0);
                 if (!jump) {
