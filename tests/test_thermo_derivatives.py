@@ -61,6 +61,54 @@ def test_oracle_derivatives_against_its_own_finite_differences(orc):
     assert abs((r.entropy[1] - r.entropy[0]) / (2 * h) - (d["dEps_dT"][0] - 3 * mu0 * d["dn_dT"][0]) / T0) < 1e-5
 
 
+class _HostEngine:
+    """Stands in for Engine in the host-logic test below: same methods, evaluated by the TEST-ONLY host build of the
+    product's math/solver headers (tests/hostsim) — the finite-difference / implicit-differentiation algebra of
+    thermo_derivatives.py is then checked on the CPU against the oracle's exact AD."""
+
+    def __init__(self, orc):
+        from julia_relaxtime_b200.constants import DEFAULT
+        from tests.hostsim.hostsim import HostSim
+        self.hs = HostSim(orc.p_nodes, orc.p_w, orc.c_nodes, orc.c_w, max_iter=1000)
+        self.consts = DEFAULT
+
+    def solve_points(self, T, mu, xi, seed_mode):
+        return self.hs.solve_points(T, mu, xi, seed_mode)
+
+    def eval_state(self, T, mu, xi, x):
+        x = np.asarray(x, dtype=float).reshape(-1, 5)
+        n = x.shape[0]
+        out = dict(F=np.zeros((n, 5)), J=np.zeros((n, 5, 5)), entropy=np.zeros(n), pressure=np.zeros(n), rho=np.zeros((n, 3)),
+                   rho_norm=np.zeros(n))
+        for i in range(n):
+            out["F"][i], out["J"][i] = self.hs.fj(x[i], T[i], mu[i], xi[i])
+            th = self.hs.thermo(x[i], T[i], mu[i], xi[i])
+            out["entropy"][i], out["pressure"][i], out["rho"][i], out["rho_norm"][i] = th["entropy"], th["pressure"], th["rho"], th["rho_norm"]
+        return out
+
+
+def test_host_algebra_of_thermo_derivatives_matches_oracle_on_cpu(orc):
+    from julia_relaxtime_b200 import thermo_derivatives as td
+    e = _HostEngine(orc)
+    T_MeV = np.array([150.0, 150.0, 110.0, 220.0])
+    mu_MeV = np.array([0.0, 50.0, 280.0, 120.0])
+    xi = np.array([0.0, 0.0, 0.2, -0.4])
+    T, mu = T_MeV / HBARC, mu_MeV / HBARC
+    bulk = td.bulk_viscosity_coefficients(T, mu, xi=xi, engine=e)
+    thr = td.thermo_derivatives(T, mu, xi=xi, engine=e)
+    _, d = _oracle_at(orc, T_MeV, mu_MeV, xi)
+    nz = mu_MeV > 0
+    assert np.allclose(bulk["v_n_sq"], d["v_n_sq"], rtol=2e-8, atol=0)
+    assert np.allclose(bulk["dmuB_dT_sigma"][nz], d["dmuB_dT_sigma"][nz], rtol=2e-8, atol=0)
+    for i, f in enumerate("uds"):
+        assert np.allclose(bulk["dM_dT"][:, i], d["dM_%s_dT" % f], rtol=2e-8, atol=1e-12)
+        assert np.allclose(thr["dM_dmu"][:, i], d["dM_%s_dmu" % f], rtol=2e-8, atol=1e-12)
+        assert np.allclose(bulk["masses"][:, i], d["M_" + f], rtol=1e-10, atol=0)
+    for a, b in (("dP_dT", "dP_dT"), ("dEpsilon_dT", "dEps_dT"), ("dEpsilon_dmu", "dEps_dmu"), ("dn_dmu", "dn_dmu"), ("energy", "eps")):
+        assert np.allclose(thr[a], d[b], rtol=2e-8, atol=1e-11), a
+    assert abs(bulk["v_n_sq"][1] - 7.951898e-02) < 6e-9          # the reference's printed value
+
+
 @pytest.mark.gpu
 def test_gpu_thermo_derivatives_match_oracle_and_reference_tables(orc):
     from julia_relaxtime_b200 import thermo_derivatives as td
