@@ -1037,7 +1037,11 @@ long long coprime_multiplier(long long n) {
 
 int launch_ws(pnjl_handle* h, const WsTask& task_in, cudaStream_t st) {
     WsTask task = task_in;
-    task.perm_mult = coprime_multiplier(task.n_tasks);
+    // Task order.  The first wave is dealt round-robin (CTA b, mailbox j -> ticket b + gridDim * j, see k_solve_ws), so with
+    // the identity order every SM samples the (xi, mu) index space with a fixed stride — a stratified sample of a cost that
+    // varies smoothly with the line index: SM load max/mean 1.017 on cfg5 against 1.035 for a pseudo-random order
+    // (scripts/line_balance.py data).  The golden-ratio permutation dates from the contiguous hand-out (PNJL_WS_PERM=1 restores it).
+    task.perm_mult = (getenv("PNJL_WS_PERM") && atoi(getenv("PNJL_WS_PERM")) != 0) ? coprime_multiplier(task.n_tasks) : 1;
     int nw = h->ws_workers, nc = h->ws_ctrl_warps, spw = h->ws_spw, parts = 1;
     const long long per_sm = (task.n_tasks + h->sm_count - 1) / h->sm_count;   // tasks an SM has to carry at least
     long long n_slots = h->ws_slots > 0 ? h->ws_slots : (long long)spw * nw;
