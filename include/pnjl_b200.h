@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define PNJL_ABI_VERSION 11
+#define PNJL_ABI_VERSION 12
 
 /* ---- result record layout (doubles) --------------------------------------------------------- */
 #define PNJL_REC_DOUBLES 32
@@ -76,6 +76,9 @@ extern "C" {
 #define PNJL_ST_CAND_SHIFT 12        /* bits 12..13: index of the TmuScan seed candidate that succeeded   TmuScan.jl:269-300 */
 #define PNJL_ST_CAND_MASK 0x3000
 #define PNJL_ST_NO_RESULT 16384      /* TmuScan: every candidate failed (the reference writes an all-NaN row) */
+#define PNJL_ST_MASS_INVERSION 32768 /* converged with M_s <= M_u: the high-Omega root (phi_u ~ -5.3, phi_s ~ +1.9, Omega ~ -18.1) that passes
+                                        the reference's physicality filter (ImplicitSolver.jl:50-60) and that continuity seeding then
+                                        follows; the reference returns it silently — here it is flagged (the values are unchanged) */
 
 /* ---- errors --------------------------------------------------------------------------------- */
 #define PNJL_OK 0
@@ -88,9 +91,6 @@ extern "C" {
                                 n_seeds>1: solve_multi over the given candidates  (ImplicitSolver.jl:539-546) */
 #define PNJL_SEED_AUTO 1     /* DefaultSeed(phase_hint=:auto)   SeedStrategies.jl:193-225 */
 #define PNJL_SEED_MULTI 2    /* MultiSeed(): the six built-in candidates  SeedStrategies.jl:251-284 */
-
-#define PNJL_MAX_TABLES 8
-#define PNJL_MAX_TABLE_ROWS 64
 
 typedef struct pnjl_handle pnjl_handle;
 
@@ -119,10 +119,14 @@ typedef struct pnjl_config {
                                        mu_u = mu_d and m_u0 = m_d0 on this path) evaluate the d flavour as the u flavour and
                                        keep Newton/dogleg steps u<->d symmetric (a <= 1 ulp change of the step).  0: three
                                        independent flavours everywhere, like the reference's loop (Integrals.jl:250-257). */
-    int32_t schedule;               /* kernel organisation for the 32-lane layout.  0 (default): warp-specialised — worker warps
-                                       run only quadrature loops, controller lanes own one line/point each and run the
-                                       solve cascade in SIMT, passes are handed over through shared-memory mailboxes.
+    int32_t schedule;               /* kernel organisation for the 32-lane layout.
+                                       0 (default): continuity lines are marched by the line-march kernel — a warp (or a team of
+                                       warps when the GPU holds few lines) keeps a line's Newton solve in its registers, lines
+                                       are time-sliced through a global queue; independent points use organisation 2.
                                        1: every warp owns a line/point, CTAs phase-aligned by named barriers.
+                                       2: warp-specialised — worker warps run only quadrature loops, controller lanes own one
+                                       line/point each and run the solve cascade in SIMT, passes are handed over through
+                                       shared-memory mailboxes.
                                        Results agree to round-off; the 8- and 16-lane layouts always use organisation 1. */
     int32_t isotropic_collapse;     /* 1 (default): for xi == 0 exactly the integrand does not depend on cos(theta)
                                        (E = sqrt(p^2 + M^2), Integrals.jl:178-180), so a pass sums over the p_num momentum
@@ -135,13 +139,21 @@ typedef struct pnjl_config {
 typedef struct pnjl_boundary {
     const double* T_MeV;    /* [n] ascending */
     const double* mu_c_MeV; /* [n] */
-    int32_t n;              /* <= PNJL_MAX_TABLE_ROWS */
+    int32_t n;              /* any length (bisection on the device) */
     double T_CEP_MeV;       /* NaN if unknown */
 } pnjl_boundary;
 
 void pnjl_default_config(pnjl_config* cfg);  /* config/pnjl/default.toml values, 64x8 nodes, max_iter 1000 */
 int pnjl_abi_version(void);
 const char* pnjl_last_error(void);
+
+/* Layout self-check for hand-written mirrors of the structs above (the Julia `struct Config` of julia/PNJLB200.jl, the ctypes
+ * Structure of julia_relaxtime_b200/_abi.py): sizes in bytes, and the byte offset of a field by name (-1: no such field).
+ * Bindings assert these against their own sizeof/fieldoffset when they load the library. */
+int64_t pnjl_sizeof_config(void);
+int64_t pnjl_sizeof_boundary(void);
+int64_t pnjl_sizeof_stats(void);
+int64_t pnjl_config_field_offset(const char* field);
 
 /* Page-locked, device-addressable host memory for result buffers (what a Julia caller wraps with unsafe_wrap). */
 int pnjl_alloc_pinned(uint64_t bytes, void** out);
@@ -153,6 +165,17 @@ void pnjl_destroy(pnjl_handle* h);
 /* gauleg(a, b, n) (src/integration/GaussLegendre.jl:94-119): host-side helper so callers without
  * FastGaussQuadrature can build the same rule the library would. */
 int pnjl_gauleg(double a, double b, int32_t n, double* nodes, double* weights);
+
+/* Run-time options of a handle (launch geometry, nothing that changes results beyond round-off):
+ *   "schedule"        0 default, 1, 2: as pnjl_config.schedule
+ *   "march_parts"     warps per line in the line-march kernel: 0 automatic, 1, 2, 4, 8, 16
+ *   "march_quantum"   points per time slice of a line in the line-march kernel (0 automatic)
+ *   "isotropic_batch" 1: the caller promises xi == 0 on every line of the following *_device calls (the host entry points
+ *                     look at xi themselves), so teams are sized for p_num nodes instead of p_num * t_num */
+int pnjl_set_option(pnjl_handle* h, const char* key, int64_t value);
+
+/* Record and aux buffers (`records`, `d_records`, `aux`, ...) must be 16-byte aligned: the kernels write them with 16-byte
+ * stores.  malloc, numpy, Julia arrays and cudaMalloc all satisfy this. */
 
 /* Independent points: PNJL.solve / solve_multi at n (T, mu, xi) triples.  records: [n][32]. */
 int pnjl_solve_points_host(pnjl_handle* h, int64_t n, const double* T_fm, const double* mu_fm, const double* xi,

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD_DIR = os.path.join(CSRC, "_build")
 LIB_PATH = os.path.join(BUILD_DIR, "libpnjl_b200.so")
-SOURCES = [os.path.join(CSRC, f) for f in ("pnjl_kernels.cu", "pnjl_math.cuh", "pnjl_solver.cuh")] + [
+SOURCES = [os.path.join(CSRC, f) for f in ("pnjl_kernels.cu", "pnjl_math.cuh", "pnjl_solver.cuh", "pnjl_march.cuh")] + [
     os.path.join(HERE, "..", "include", "pnjl_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -97,8 +97,12 @@ def load():
     L.pnjl_selftest_math.argtypes = [H, C.c_int64, dp, C.c_int32, dp]
     L.pnjl_get_stats.argtypes = [H, C.POINTER(_abi.PnjlStats)]
     L.pnjl_measure_fp64_peak.argtypes = [H, C.c_double, dp, dp]
+    L.pnjl_set_option.argtypes = [H, C.c_char_p, C.c_int64]
     if L.pnjl_abi_version() != _abi.ABI_VERSION:
         raise PnjlError("ABI version mismatch between _abi.py and libpnjl_b200.so")
+    bad = _abi.check_layout(L)
+    if bad:
+        raise PnjlError("struct layout mismatch between _abi.py and libpnjl_b200.so: " + "; ".join(bad))
     _LIB = L
     return L
 
@@ -108,7 +112,8 @@ EXPORTED_SYMBOLS = [
     "pnjl_solve_points_host", "pnjl_solve_points_device", "pnjl_set_boundaries", "pnjl_scan_lines_host",
     "pnjl_scan_lines_device", "pnjl_scan_lines_device_indexed", "pnjl_ipc_alloc", "pnjl_ipc_open", "pnjl_ipc_close",
     "pnjl_ipc_free", "pnjl_set_oneloop_rule", "pnjl_effective_couplings_host",
-    "pnjl_effective_couplings_device", "pnjl_scan_lines_couplings_host", "pnjl_dual_branch_host", "pnjl_dual_branch_device", "pnjl_tmu_scan_host", "pnjl_tmu_scan_device", "pnjl_eval_fj_host", "pnjl_eval_state_host", "pnjl_selftest_math", "pnjl_get_stats", "pnjl_measure_fp64_peak"]
+    "pnjl_effective_couplings_device", "pnjl_scan_lines_couplings_host", "pnjl_dual_branch_host", "pnjl_dual_branch_device", "pnjl_tmu_scan_host", "pnjl_tmu_scan_device", "pnjl_eval_fj_host", "pnjl_eval_state_host", "pnjl_selftest_math", "pnjl_get_stats", "pnjl_measure_fp64_peak",
+    "pnjl_set_option", "pnjl_sizeof_config", "pnjl_sizeof_boundary", "pnjl_sizeof_stats", "pnjl_config_field_offset"]
 
 
 class PinnedArray:
@@ -197,6 +202,10 @@ class Engine:
         if rc != 0:
             raise PnjlError("%s failed (%d): %s" % (what, rc, self.L.pnjl_last_error().decode()))
 
+    def set_option(self, key, value):
+        """Run-time option of the handle (pnjl_set_option): 'schedule', 'march_parts', 'march_quantum', 'isotropic_batch'."""
+        self._check(self.L.pnjl_set_option(self.h, key.encode(), int(value)), "pnjl_set_option(%s)" % key)
+
     # ---- boundaries -------------------------------------------------------------------------------
     def set_boundaries(self, tables):
         """tables: list of (T_MeV[], mu_c_MeV[], T_CEP_MeV)."""
@@ -220,7 +229,7 @@ class Engine:
             seeds = np.ascontiguousarray(seeds, dtype=np.float64).reshape(n, -1, 5)
             n_seeds = seeds.shape[1]
             sp = _abi.dptr(seeds)
-        rec = out if out is not None else np.empty((n, _abi.REC_DOUBLES))
+        rec = _abi.check_records(out, n * _abi.REC_DOUBLES) if out is not None else np.empty((n, _abi.REC_DOUBLES))
         self._check(self.L.pnjl_solve_points_host(self.h, n, _abi.dptr(T_fm), _abi.dptr(mu_fm), _abi.dptr(xi),
                                                   int(seed_mode), int(n_seeds), sp, _abi.dptr(rec)),
                     "pnjl_solve_points_host")
@@ -235,7 +244,8 @@ class Engine:
         if table_idx is not None:
             table_idx = np.ascontiguousarray(table_idx, dtype=np.int32)
             ti = _abi.iptr(table_idx)
-        rec = out if out is not None else np.empty((n_lines, T_MeV.size, _abi.REC_DOUBLES))
+        rec = (_abi.check_records(out, n_lines * T_MeV.size * _abi.REC_DOUBLES) if out is not None
+               else np.empty((n_lines, T_MeV.size, _abi.REC_DOUBLES)))
         self._check(self.L.pnjl_scan_lines_host(self.h, n_lines, _abi.dptr(muq_MeV), _abi.dptr(xi), ti,
                                                 int(T_MeV.size), _abi.dptr(T_MeV), _abi.dptr(rec)),
                     "pnjl_scan_lines_host")
@@ -291,7 +301,8 @@ class Engine:
         if table_idx is not None:
             table_idx = np.ascontiguousarray(table_idx, dtype=np.int32)
             ti = _abi.iptr(table_idx)
-        rec = out if out is not None else np.empty((n_lines, mu_MeV.size, _abi.REC_DOUBLES))
+        rec = (_abi.check_records(out, n_lines * mu_MeV.size * _abi.REC_DOUBLES) if out is not None
+               else np.empty((n_lines, mu_MeV.size, _abi.REC_DOUBLES)))
         self._check(self.L.pnjl_tmu_scan_host(self.h, n_lines, _abi.dptr(T_MeV), _abi.dptr(xi), ti, int(mu_MeV.size),
                                               _abi.dptr(mu_MeV), _abi.dptr(rec)), "pnjl_tmu_scan_host")
         return rec

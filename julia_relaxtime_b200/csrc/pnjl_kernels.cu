@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
@@ -540,12 +541,12 @@ __device__ __forceinline__ void warp_sum_store(double (&v)[N], int lane, double*
 
 // One quadrature pass (or one part of it: nodes lane + 32 part, stride 32 parts) of a worker warp for mailbox `sl`;
 // the warp-reduced sums go to out[0..20].
-__device__ __noinline__ void ws_worker_pass(const DeviceConfig* cfg, const MeshView& mv, const WsSlot* sl, int type, int lane,
-                                            int part, int parts, double* out) {
-    const double T = sl->d[0], mu = sl->d[1], xi = sl->d[2];
+__device__ __noinline__ void ws_worker_pass(const DeviceConfig* cfg, const MeshView& mv, const double* d /* T, mu, xi, x[5] */, int type,
+                                            int lane, int part, int parts, double* out) {
+    const double T = d[0], mu = d[1], xi = d[2];
     double x[5];
 #pragma unroll
-    for (int i = 0; i < 5; ++i) x[i] = sl->d[3 + i];
+    for (int i = 0; i < 5; ++i) x[i] = d[3 + i];
     PointCtx c;
     make_ctx(cfg->m, T, mu, xi, x, c);
     const bool iso = cfg->sp.isospin != 0;
@@ -656,10 +657,10 @@ __global__ void __launch_bounds__(PNJL_WS_MAX_THREADS, 1) k_solve_ws(const Devic
                 bool slot_complete = true;
                 if (type != WS_EXIT) {
                     if (parts == 1) {
-                        ws_worker_pass(cfg, mv, sl, type, lane, 0, 1, sl->r);
+                        ws_worker_pass(cfg, mv, sl->d, type, lane, 0, 1, sl->r);
                     } else {
                         double* mine = s_part + ((size_t)si * parts + part) * kWsR;
-                        ws_worker_pass(cfg, mv, sl, type, lane, part, parts, mine);
+                        ws_worker_pass(cfg, mv, sl->d, type, lane, part, parts, mine);
                         __syncwarp();
                         __threadfence_block();
                         int c = 0;
@@ -772,6 +773,8 @@ __global__ void __launch_bounds__(PNJL_WS_MAX_THREADS, 1) k_solve_ws(const Devic
     }
     ev.retire();
 }
+
+#include "pnjl_march.cuh"
 
 // ---- single FJ evaluation (test hook) ------------------------------------------------------------
 template <int G>
@@ -951,8 +954,15 @@ struct pnjl_handle {
     int G_next = 0;               // layout for the next launch only (host entry points: all-isotropic batches), 0 = G
     int block_threads = 128;
     bool block_threads_forced = false;   // PNJL_BLOCK_THREADS given
-    int schedule = 0;             // 0: every warp owns a line (phase-aligned CTAs); 1: worker/controller warps
+    int schedule = 2;             // 0: every warp owns a line (phase-aligned CTAs); 1: worker/controller warps (k_solve_ws);
+                                  // 2: line march in registers, time-sliced lines (k_march; lines only — points use 1)
     int ws_workers = 14, ws_ctrl_warps = 2, ws_spw = 4, ws_slots = 0;
+    int march_parts = 0;          // warps per team in k_march (0 = automatic)
+    int march_quantum = 0;        // points per time slice in k_march (0 = automatic)
+    bool iso_batch = false;       // option "isotropic_batch": the caller promises xi == 0 on every line (device entry points)
+    bool iso_next = false;        // the next launch is all-isotropic (set by the host entry points, which see xi)
+    DevBuf march_state, march_slots, march_counters;
+    DevBuf pt_start, pt_tcep, pt_T, pt_mu;   // flattened phase-boundary tables (pnjl_set_boundaries)
     DeviceConfig host_cfg;
     DeviceConfig* d_cfg = nullptr;
     double* d_mesh = nullptr;
@@ -1104,6 +1114,56 @@ int launch_points_ws(pnjl_handle* h, long long n, const double* T, const double*
     return launch_ws(h, t, st);
 }
 
+// Launch geometry of the line-march kernel.  Team size: one warp per line while there are at least half as many lines as
+// warps on the GPU; otherwise the largest power of two that still gives every line a team and every lane two nodes.
+int launch_march(pnjl_handle* h, long long n_lines, const double* muq, const double* xi, const int* tidx, int n_T,
+                 const double* T, double* rec, cudaStream_t st) {
+    const long long total_warps = (long long)h->sm_count * kMarchWarps;
+    const bool iso = (h->iso_next || h->iso_batch) && h->host_cfg.n_iso > 0;
+    h->iso_next = false;
+    const int n_eff = iso ? h->host_cfg.n_iso : h->n_nodes;
+    int parts = 1;
+    while (parts < kMarchWarps && n_lines * 2 * parts <= total_warps && n_eff / (64 * parts) >= 2) parts *= 2;
+    if (h->march_parts > 0) parts = h->march_parts;
+    if (parts != 1 && parts != 2 && parts != 4 && parts != 8 && parts != 16) return fail(PNJL_ERR_ARG, "march_parts must be 1, 2, 4, 8 or 16");
+    const long long n_teams = total_warps / parts;
+    int quantum = h->march_quantum > 0 ? h->march_quantum : (n_lines <= n_teams ? n_T : 32);
+    if (quantum > n_T) quantum = n_T;
+    const long long n_quanta = (n_T + quantum - 1) / quantum;
+    MarchArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.n_lines = n_lines; a.muq_MeV = muq; a.xi = xi; a.table_idx = tidx; a.n_T = n_T; a.T_MeV = T; a.records = rec;
+    a.out_index = h->out_index_next;
+    a.capacity = n_lines * n_quanta;
+    a.quantum = quantum;
+    a.parts = parts;
+    CUDA_TRY(h->march_state.reserve(sizeof(LineState) * (size_t)n_lines));
+    CUDA_TRY(h->march_slots.reserve(sizeof(int) * (size_t)a.capacity));
+    CUDA_TRY(h->march_counters.reserve(sizeof(unsigned long long) * 4));
+    a.state = (LineState*)h->march_state.p;
+    a.slots = (int*)h->march_slots.p;
+    a.counters = (unsigned long long*)h->march_counters.p;
+    const int n_mesh = 3 * h->n_nodes + 2 * h->host_cfg.n_iso;
+    const size_t smem = sizeof(double) * (size_t)(((n_mesh + 1) & ~1) + kMarchWarps * kStageDoubles + 2 * kMarchWarps * kBufStride) +
+                        sizeof(int) * kMarchWarps;
+    cudaFuncAttributes fa;
+    CUDA_TRY(cudaFuncGetAttributes(&fa, k_march));
+    if (smem > 40 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_march, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int blocks = (int)(n_lines < h->sm_count ? n_lines : h->sm_count);
+    h->stats.regs_per_thread = fa.numRegs;
+    h->stats.smem_bytes = (int)smem;
+    h->stats.blocks = blocks;
+    h->stats.threads = 32 * kMarchWarps;
+    h->stats.lanes_per_solve = 32 * parts;
+    const long long n_init = a.capacity > n_lines ? a.capacity : n_lines;
+    k_march_init<<<(unsigned)((n_init + 255) / 256), 256, 0, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    k_march<<<blocks, 32 * kMarchWarps, smem, st>>>(h->d_cfg, h->d_mesh, a);
+    CUDA_TRY(cudaGetLastError());
+    h->stats.kernel_launches += 2;
+    return PNJL_OK;
+}
+
 template <int G>
 int launch_lines(pnjl_handle* h, long long n_lines, const double* muq, const double* xi, const int* tidx, int n_T,
                  const double* T, double* rec, cudaStream_t st, int mode) {
@@ -1150,11 +1210,16 @@ int take_layout(pnjl_handle* h) {
 // Host entry points know xi: when the whole batch is isotropic (xi == 0 everywhere) and the collapse is on, a pass sweeps
 // p_num nodes only, so the layout is chosen for that mesh (8 or 16 lanes per solve) instead of the full one — the
 // warp-specialised kernel would be bound by its controller warps there.
-void choose_layout_for_batch(pnjl_handle* h, long long n, const double* xi) {
+void choose_layout_for_batch(pnjl_handle* h, long long n, const double* xi, bool march_lines = false) {
     h->G_next = 0;
+    h->iso_next = false;
     if (h->G_user != 0 || h->host_cfg.n_iso == 0) return;
     for (long long i = 0; i < n; ++i)
         if (xi[i] != 0.0) return;
+    if (march_lines && h->schedule == 2 && h->G == 32) {
+        h->iso_next = true;      // the line-march kernel keeps its layout and only sizes its teams for p_num nodes
+        return;
+    }
     const int n_eff = h->host_cfg.n_iso;
     h->G_next = n_eff <= 96 ? 8 : (n_eff <= 256 ? 16 : 32);
 }
@@ -1165,7 +1230,7 @@ int dispatch_points(pnjl_handle* h, long long n, const double* T, const double* 
         case 8: return launch_points<8>(h, n, T, mu, xi, seed_mode, n_seeds, seeds, rec, st);
         case 16: return launch_points<16>(h, n, T, mu, xi, seed_mode, n_seeds, seeds, rec, st);
         default:
-            if (h->schedule == 1) return launch_points_ws(h, n, T, mu, xi, seed_mode, n_seeds, seeds, rec, st);
+            if (h->schedule >= 1) return launch_points_ws(h, n, T, mu, xi, seed_mode, n_seeds, seeds, rec, st);
             return launch_points<32>(h, n, T, mu, xi, seed_mode, n_seeds, seeds, rec, st);
     }
 }
@@ -1175,7 +1240,8 @@ int dispatch_lines(pnjl_handle* h, long long n_lines, const double* muq, const d
         case 8: return launch_lines<8>(h, n_lines, muq, xi, tidx, n_T, T, rec, st, mode);
         case 16: return launch_lines<16>(h, n_lines, muq, xi, tidx, n_T, T, rec, st, mode);
         default:
-            if (h->schedule == 1) return launch_lines_ws(h, n_lines, muq, xi, tidx, n_T, T, rec, st, mode);
+            if (h->schedule == 2 && mode == 0) return launch_march(h, n_lines, muq, xi, tidx, n_T, T, rec, st);
+            if (h->schedule >= 1) return launch_lines_ws(h, n_lines, muq, xi, tidx, n_T, T, rec, st, mode);
             return launch_lines<32>(h, n_lines, muq, xi, tidx, n_T, T, rec, st, mode);
     }
 }
@@ -1208,6 +1274,23 @@ extern "C" {
 int pnjl_abi_version(void) { return PNJL_ABI_VERSION; }
 
 const char* pnjl_last_error(void) { return g_last_error.c_str(); }
+
+int64_t pnjl_sizeof_config(void) { return (int64_t)sizeof(pnjl_config); }
+int64_t pnjl_sizeof_boundary(void) { return (int64_t)sizeof(pnjl_boundary); }
+int64_t pnjl_sizeof_stats(void) { return (int64_t)sizeof(pnjl_stats); }
+int64_t pnjl_config_field_offset(const char* field) {
+    if (!field) return -1;
+    const std::string f(field);
+#define PNJL_FIELD(name) if (f == #name) return (int64_t)offsetof(pnjl_config, name);
+    PNJL_FIELD(hbarc) PNJL_FIELD(Lambda) PNJL_FIELD(m_ud0) PNJL_FIELD(m_s0) PNJL_FIELD(G) PNJL_FIELD(K) PNJL_FIELD(T0)
+    PNJL_FIELD(a0) PNJL_FIELD(a1) PNJL_FIELD(a2) PNJL_FIELD(b3) PNJL_FIELD(rho0) PNJL_FIELD(Nc) PNJL_FIELD(p_num) PNJL_FIELD(t_num)
+    PNJL_FIELD(p_nodes) PNJL_FIELD(p_w) PNJL_FIELD(c_nodes) PNJL_FIELD(c_w) PNJL_FIELD(xtol) PNJL_FIELD(ftol)
+    PNJL_FIELD(residual_norm_max) PNJL_FIELD(phi_tol) PNJL_FIELD(max_iter) PNJL_FIELD(tr_fallback) PNJL_FIELD(auto_multiseed_fallback)
+    PNJL_FIELD(omega_tie_rel) PNJL_FIELD(device) PNJL_FIELD(lanes_per_solve) PNJL_FIELD(predict_tol) PNJL_FIELD(isospin_symmetric)
+    PNJL_FIELD(schedule) PNJL_FIELD(isotropic_collapse)
+#undef PNJL_FIELD
+    return -1;
+}
 
 void pnjl_default_config(pnjl_config* c) {
     std::memset(c, 0, sizeof(*c));
@@ -1344,7 +1427,9 @@ int pnjl_create(const pnjl_config* c, pnjl_handle** out) {
         if (h->block_threads < 32 || h->block_threads > 512 || (h->block_threads & 31)) h->block_threads = 128;
         // internal numbering: 1 = warp-specialised, 0 = one warp per line; PNJL_SCHEDULE overrides for experiments
         const char* es = getenv("PNJL_SCHEDULE");
-        h->schedule = es ? atoi(es) : (c->schedule == 1 ? 0 : 1);
+        h->schedule = es ? atoi(es) : (c->schedule == 1 ? 0 : (c->schedule == 2 ? 1 : 2));
+        if (getenv("PNJL_MARCH_PARTS")) h->march_parts = atoi(getenv("PNJL_MARCH_PARTS"));
+        if (getenv("PNJL_MARCH_Q")) h->march_quantum = atoi(getenv("PNJL_MARCH_Q"));
         if (getenv("PNJL_WS_WORKERS")) h->ws_workers = atoi(getenv("PNJL_WS_WORKERS"));
         if (getenv("PNJL_WS_CTRL")) h->ws_ctrl_warps = atoi(getenv("PNJL_WS_CTRL"));
         if (getenv("PNJL_WS_SPW")) h->ws_spw = atoi(getenv("PNJL_WS_SPW"));
@@ -1413,6 +1498,8 @@ void pnjl_destroy(pnjl_handle* h) {
 #endif
     h->in_T.release(); h->in_mu.release(); h->in_xi.release(); h->in_seeds.release(); h->in_idx.release();
     h->in_x.release(); h->out_rec.release(); h->out_aux.release();
+    h->march_state.release(); h->march_slots.release(); h->march_counters.release();
+    h->pt_start.release(); h->pt_tcep.release(); h->pt_T.release(); h->pt_mu.release();
     for (auto& b : h->in_c) b.release();
     if (h->d_rule) cudaFree(h->d_rule);
     if (h->d_cfg) cudaFree(h->d_cfg);
@@ -1426,23 +1513,70 @@ void pnjl_destroy(pnjl_handle* h) {
 
 int pnjl_set_boundaries(pnjl_handle* h, int32_t n_tables, const pnjl_boundary* tables) {
     if (!h) return fail(PNJL_ERR_ARG, "null handle");
-    if (n_tables < 0 || n_tables > PNJL_MAX_TABLES) return fail(PNJL_ERR_ARG, "too many boundary tables");
-    DeviceGuard guard(h->device);
-    PhaseTables& pt = h->host_cfg.pt;
-    std::memset(&pt, 0, sizeof(pt));
-    pt.n_tables = n_tables;
+    if (n_tables < 0 || (n_tables > 0 && !tables)) return fail(PNJL_ERR_ARG, "bad boundary table list");
+    // validate and flatten into local buffers first: the handle's tables are replaced only when everything is in order
+    std::vector<int> start(n_tables + 1, 0);
+    std::vector<double> tcep((size_t)(n_tables > 0 ? n_tables : 1), 0.0), Ts, ms;
     for (int t = 0; t < n_tables; ++t) {
-        if (tables[t].n < 0 || tables[t].n > PNJL_MAX_TABLE_ROWS) return fail(PNJL_ERR_ARG, "boundary table too long");
-        pt.n[t] = tables[t].n;
-        pt.T_CEP[t] = tables[t].T_CEP_MeV;
-        for (int i = 0; i < tables[t].n; ++i) {
-            pt.T[t][i] = tables[t].T_MeV[i];
-            pt.mu[t][i] = tables[t].mu_c_MeV[i];
-            if (i > 0 && !(pt.T[t][i] >= pt.T[t][i - 1])) return fail(PNJL_ERR_ARG, "boundary table must be sorted by T");
+        const int n = tables[t].n;
+        if (n < 0 || (n > 0 && (!tables[t].T_MeV || !tables[t].mu_c_MeV))) return fail(PNJL_ERR_ARG, "bad boundary table");
+        tcep[t] = tables[t].T_CEP_MeV;
+        for (int i = 0; i < n; ++i) {
+            if (i > 0 && !(tables[t].T_MeV[i] >= tables[t].T_MeV[i - 1])) return fail(PNJL_ERR_ARG, "boundary table must be sorted by T");
+            Ts.push_back(tables[t].T_MeV[i]);
+            ms.push_back(tables[t].mu_c_MeV[i]);
         }
+        start[t + 1] = (int)Ts.size();
     }
+    DeviceGuard guard(h->device);
     CUDA_TRY(cudaStreamSynchronize(h->stream));
-    CUDA_TRY(cudaMemcpy(h->d_cfg, &h->host_cfg, sizeof(DeviceConfig), cudaMemcpyHostToDevice));
+    const size_t rows = Ts.size() ? Ts.size() : 1;
+    DevBuf nb_start, nb_tcep, nb_T, nb_mu;
+    cudaError_t e = nb_start.reserve(sizeof(int) * start.size());
+    if (e == cudaSuccess) e = nb_tcep.reserve(sizeof(double) * tcep.size());
+    if (e == cudaSuccess) e = nb_T.reserve(sizeof(double) * rows);
+    if (e == cudaSuccess) e = nb_mu.reserve(sizeof(double) * rows);
+    if (e == cudaSuccess) e = cudaMemcpy(nb_start.p, start.data(), sizeof(int) * start.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(nb_tcep.p, tcep.data(), sizeof(double) * tcep.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && Ts.size()) e = cudaMemcpy(nb_T.p, Ts.data(), sizeof(double) * Ts.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && ms.size()) e = cudaMemcpy(nb_mu.p, ms.data(), sizeof(double) * ms.size(), cudaMemcpyHostToDevice);
+    DeviceConfig next = h->host_cfg;
+    next.pt.n_tables = n_tables;
+    next.pt.start = (const int*)nb_start.p;
+    next.pt.T_CEP = (const double*)nb_tcep.p;
+    next.pt.T = (const double*)nb_T.p;
+    next.pt.mu = (const double*)nb_mu.p;
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_cfg, &next, sizeof(DeviceConfig), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        nb_start.release(); nb_tcep.release(); nb_T.release(); nb_mu.release();
+        return fail(e == cudaErrorMemoryAllocation ? PNJL_ERR_NOMEM : PNJL_ERR_CUDA, std::string("pnjl_set_boundaries: ") + cudaGetErrorString(e));
+    }
+    // commit
+    h->pt_start.release(); h->pt_tcep.release(); h->pt_T.release(); h->pt_mu.release();
+    h->pt_start = nb_start; h->pt_tcep = nb_tcep; h->pt_T = nb_T; h->pt_mu = nb_mu;
+    h->host_cfg = next;
+    return PNJL_OK;
+}
+
+int pnjl_set_option(pnjl_handle* h, const char* key, int64_t value) {
+    if (!h || !key) return fail(PNJL_ERR_ARG, "null argument");
+    const std::string k(key);
+    if (k == "schedule") {
+        if (value < 0 || value > 2) return fail(PNJL_ERR_ARG, "schedule: 0 line march, 1 one warp per line, 2 worker/controller warps");
+        h->schedule = value == 1 ? 0 : (value == 2 ? 1 : 2);
+    } else if (k == "march_parts") {
+        if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8 && value != 16)
+            return fail(PNJL_ERR_ARG, "march_parts must be 0 (automatic), 1, 2, 4, 8 or 16");
+        h->march_parts = (int)value;
+    } else if (k == "march_quantum") {
+        if (value < 0 || value > (1 << 30)) return fail(PNJL_ERR_ARG, "march_quantum out of range");
+        h->march_quantum = (int)value;
+    } else if (k == "isotropic_batch") {
+        h->iso_batch = value != 0;
+    } else {
+        return fail(PNJL_ERR_ARG, "unknown option: " + k);
+    }
     return PNJL_OK;
 }
 
@@ -1534,7 +1668,7 @@ static int scan_lines_host_impl(pnjl_handle* h, int64_t n_lines, const double* m
         d_idx = (const int32_t*)h->in_idx.p;
     }
     CUDA_TRY(cudaEventRecord(h->ev0, st));
-    choose_layout_for_batch(h, n_lines, xi);
+    choose_layout_for_batch(h, n_lines, xi, true);
     int rc = pnjl_scan_lines_device(h, n_lines, (const double*)h->in_mu.p, (const double*)h->in_xi.p, d_idx, n_T,
                                     (const double*)h->in_T.p, alias ? alias : (double*)h->out_rec.p, st);
     if (rc) return rc;

@@ -25,7 +25,7 @@
 #define PNJL_HD_NOINL __host__ __device__ __noinline__
 #else
 #define PNJL_HD inline
-#define PNJL_HD_NOINL
+#define PNJL_HD_NOINL inline
 #endif
 
 #ifndef PNJL_FJ_UNROLL
@@ -720,19 +720,30 @@ PNJL_HD bool fj_partial(const Model& m, bool isospin, const PointCtx& c, const d
 //   16 pi^2 I   = L s (2 L^2 + m^2) - m^4 ln((L + s)/m),   s = sqrt(L^2 + m^2)
 //    4 pi^2 I'  = L m s - m^3 ln((L + s)/m)
 //    4 pi^2 I'' = L s + 2 L m^2 / s - 3 m^2 ln((L + s)/m)
-PNJL_HD void vacuum_terms(double Lam, double M, double& I0, double& I1, double& I2) {
+// ASSUME_TAME: the caller has checked vacuum_tame(); the libm fall-backs are then not even compiled in (the line-march
+// kernel keeps its per-pass code small that way).  Same arithmetic either way.
+PNJL_HD bool vacuum_tame(double Lam, double M) {
+    const double m = fabs(M) + 1e-12;
+    return (m < 1e100) && (Lam > 1e-100) && (Lam < 1e100);   // everything in vacuum_terms is then a positive normal number
+}
+template <bool ASSUME_TAME>
+PNJL_HD void vacuum_terms_t(double Lam, double M, double& I0, double& I1, double& I2) {
     const double m = fabs(M) + 1e-12;
     const double m2 = m * m;
     const double s2 = Lam * Lam + m2;
-    const bool tame = (m < 1e100) && (Lam > 1e-100) && (Lam < 1e100);   // everything below is a positive normal number
-    const double rs = tame ? fast_rsqrt(s2) : 1.0 / sqrt(s2);
+    const bool tame = ASSUME_TAME || ((m < 1e100) && (Lam > 1e-100) && (Lam < 1e100));
+    double rs, lg;
+    if (ASSUME_TAME) rs = fast_rsqrt(s2);
+    else rs = tame ? fast_rsqrt(s2) : 1.0 / sqrt(s2);
     const double s = s2 * rs;
-    const double lg = tame ? fast_log_pos((Lam + s) * fast_rcp(m)) : log((Lam + s) / m);
+    if (ASSUME_TAME) lg = fast_log_pos((Lam + s) * fast_rcp(m));
+    else lg = tame ? fast_log_pos((Lam + s) * fast_rcp(m)) : log((Lam + s) / m);
     I0 = (Lam * s * (2 * (Lam * Lam) + m2) - (m2 * m2) * lg) * (1.0 / (16 * (kPi * kPi)));
     const double sgn = (M > 0.0) ? 1.0 : ((M < 0.0) ? -1.0 : 0.0);
     I1 = sgn * (Lam * m * s - m2 * m * lg) * (1.0 / (4 * (kPi * kPi)));
     I2 = (Lam * s + 2 * Lam * m2 * rs - 3 * m2 * lg) * (1.0 / (4 * (kPi * kPi)));
 }
+PNJL_HD void vacuum_terms(double Lam, double M, double& I0, double& I1, double& I2) { vacuum_terms_t<false>(Lam, M, I0, I1, I2); }
 
 struct UTerms {
     double U, U_P, U_Pb, U_PP, U_PPb, U_PbPb, U_T;
@@ -740,45 +751,72 @@ struct UTerms {
 
 // U = T^4 [ -1/2 A(T) Phi Phibar + B(T) ln v ],  v = 1 - 6 Phi Phibar + 4 (Phi^3 + Phibar^3) - 3 (Phi Phibar)^2,
 // A = a0 + a1 t + a2 t^2, B = b3 t^3, t = T0/T;  ln v is floored at ln 1e-16 (safe_log) -> zero derivative.
-PNJL_HD void polyakov_U(const Model& m, double T, double iT, double P, double Pb, UTerms& u) {
+// WITH_VALUE = false: only the first and second derivatives in (Phi, Phibar) — what an Omega-gradient/Jacobian pass needs, no
+// logarithm; U and U_T are left untouched.  ASSUME_TAME: the caller has checked polyakov_tame() (v is a positive normal number
+// above the floor); the libm fall-backs are then not compiled in.  Same arithmetic in every variant.
+PNJL_HD double polyakov_v(double P, double Pb) {
+    const double PPb = Pb * P;
+    return 1 - 6 * PPb + 4 * (Pb * Pb * Pb + P * P * P) - 3 * (PPb * PPb);
+}
+PNJL_HD bool polyakov_tame(double P, double Pb) {
+    const double v = polyakov_v(P, Pb);
+    return !(v <= 0.0) && !(v < kPolyakovEps) && (v < 1e100);
+}
+template <bool ASSUME_TAME, bool WITH_VALUE>
+PNJL_HD void polyakov_eval(const Model& m, double T, double iT, double P, double Pb, UTerms& u) {
     const double t = m.T0 * iT;
     const double A = m.a0 + m.a1 * t + m.a2 * (t * t);
     const double B = m.b3 * (t * t * t);
     const double T2 = T * T, T4 = T2 * T2;
     const double PPb = Pb * P;
     const double v = 1 - 6 * PPb + 4 * (Pb * Pb * Pb + P * P * P) - 3 * (PPb * PPb);
-    const bool live = !(v <= 0.0) && !(v < kPolyakovEps);
-    const bool tame = live && (v < 1e100);
-    const double lv = tame ? fast_log_pos(v) : (live ? log(v) : log(kPolyakovEps));
-    const double iv = tame ? fast_rcp(v) : (live ? 1.0 / v : 0.0);
+    double lv = 0.0, iv;
+    if (ASSUME_TAME) {
+        if (WITH_VALUE) lv = fast_log_pos(v);
+        iv = fast_rcp(v);
+    } else {
+        const bool live = !(v <= 0.0) && !(v < kPolyakovEps);
+        const bool tame = live && (v < 1e100);
+        if (WITH_VALUE) lv = tame ? fast_log_pos(v) : (live ? log(v) : log(kPolyakovEps));
+        iv = tame ? fast_rcp(v) : (live ? 1.0 / v : 0.0);
+    }
     const double vP = -6 * Pb + 12 * P * P - 6 * P * Pb * Pb;
     const double vPb = -6 * P + 12 * Pb * Pb - 6 * P * P * Pb;
     const double vPP = 24 * P - 6 * Pb * Pb;
     const double vPbPb = 24 * Pb - 6 * P * P;
     const double vPPb = -6 - 12 * PPb;
-    u.U = T4 * (-0.5 * A * PPb + B * lv);
     u.U_P = T4 * (-0.5 * A * Pb + B * vP * iv);
     u.U_Pb = T4 * (-0.5 * A * P + B * vPb * iv);
     u.U_PP = T4 * B * (vPP * iv - (vP * iv) * (vP * iv));
     u.U_PbPb = T4 * B * (vPbPb * iv - (vPb * iv) * (vPb * iv));
     u.U_PPb = T4 * (-0.5 * A + B * (vPPb * iv - (vP * iv) * (vPb * iv)));
-    // dU/dT at fixed Phi: Thermodynamics.jl:147-165
-    const double iT2 = iT * iT;
-    const double dA = -m.a1 * m.T0 * iT2 - 2 * m.a2 * (m.T0 * m.T0) * (iT2 * iT);
-    const double dB = -3 * m.b3 * (m.T0 * m.T0 * m.T0) * (iT2 * iT2);
-    u.U_T = 4 * (T2 * T) * (-0.5 * A * PPb + B * lv) + T4 * (dA * (-0.5 * PPb) + dB * lv);
+    if (WITH_VALUE) {
+        u.U = T4 * (-0.5 * A * PPb + B * lv);
+        // dU/dT at fixed Phi: Thermodynamics.jl:147-165
+        const double iT2 = iT * iT;
+        const double dA = -m.a1 * m.T0 * iT2 - 2 * m.a2 * (m.T0 * m.T0) * (iT2 * iT);
+        const double dB = -3 * m.b3 * (m.T0 * m.T0 * m.T0) * (iT2 * iT2);
+        u.U_T = 4 * (T2 * T) * (-0.5 * A * PPb + B * lv) + T4 * (dA * (-0.5 * PPb) + dB * lv);
+    }
+}
+PNJL_HD void polyakov_U(const Model& m, double T, double iT, double P, double Pb, UTerms& u) {
+    polyakov_eval<false, true>(m, T, iT, P, Pb, u);
+}
+PNJL_HD void polyakov_derivs(const Model& m, double T, double iT, double P, double Pb, UTerms& u) {
+    polyakov_eval<false, false>(m, T, iT, P, Pb, u);
 }
 
 // Assemble F = grad_x P (5) and J = Hess_x P (5x5 row-major) from the reduced accumulators.
-PNJL_HD void finish_fj(const Model& m, const PointCtx& c, const double x[5], const double acc[kFJAcc], double F[5],
-                       double J[25], bool fast = false) {
+// The closed-form ingredients are passed in (I1v[i] = dI/dM, I2v[i] = d2I/dM2 of flavour i; u = the derivatives of U), so
+// that callers may compute them however they like (finish_fj below: serially; the line-march kernel: one flavour per lane).
+PNJL_HD void finish_fj_pre(const Model& m, const PointCtx& c, const double x[5], const double acc[kFJAcc], const double I1v[3],
+                           const double I2v[3], const UTerms& u, double F[5], double J[25], bool fast) {
     const double T = c.T, invT = c.invT;
     const double twoT = 2.0 * T;
     // dP/dM_i, d2P/dM_i^2, d2P/dM_i dPhi, d2P/dM_i dPhibar  (thermal + vacuum)
     double PM[3], PMM[3], PMP[3], PMPb[3];
-    double I0 = 0, I1 = 0, I2 = 0;
     for (int i = 0; i < 3; ++i) {
-        if (!(i == 1 && c.M[1] == c.M[0])) vacuum_terms(m.Lambda, c.M[i], I0, I1, I2);   // M_d == M_u: reuse
+        const double I1 = I1v[i], I2 = I2v[i];
         const double S1 = -3.0 * invT * c.M[i] * acc[ACC_S1 + i];
         // general path: S2B = sum c n k^2/E^3;  fast path: S2B = sum c n/E^3 and k^2/E^3 = 1/E - M^2/E^3
         const double s2b = fast ? (acc[ACC_S1 + i] - c.M2[i] * acc[ACC_S2B + i]) : acc[ACC_S2B + i];
@@ -796,8 +834,6 @@ PNJL_HD void finish_fj(const Model& m, const PointCtx& c, const double x[5], con
     D[0][0] = g4;        D[0][1] = k2 * x[2]; D[0][2] = k2 * x[1];
     D[1][0] = k2 * x[2]; D[1][1] = g4;        D[1][2] = k2 * x[0];
     D[2][0] = k2 * x[1]; D[2][1] = k2 * x[0]; D[2][2] = g4;
-    UTerms u;
-    polyakov_U(m, T, c.invT, x[3], x[4], u);
     // -chi: d/dphi_j = -4G phi_j + 4K phi_k phi_l
     const double chi1[3] = {-4 * m.G * x[0] + 4 * m.K * x[1] * x[2], -4 * m.G * x[1] + 4 * m.K * x[0] * x[2],
                             -4 * m.G * x[2] + 4 * m.K * x[0] * x[1]};
@@ -826,23 +862,44 @@ PNJL_HD void finish_fj(const Model& m, const PointCtx& c, const double x[5], con
     J[4 * 5 + 4] = -9.0 * twoT * acc[ACC_HPBPB] - u.U_PbPb;
 }
 
-// F = grad_x P alone, from the reduced sums of a fused final pass (same formulas as finish_fj).
-PNJL_HD void finish_f(const Model& m, const PointCtx& c, const double x[5], const double facc[5], double F[5]) {
-    const double twoT = 2.0 * c.T;
-    double PM[3];
+PNJL_HD void finish_fj(const Model& m, const PointCtx& c, const double x[5], const double acc[kFJAcc], double F[5],
+                       double J[25], bool fast = false) {
+    double I1v[3], I2v[3];
     double I0 = 0, I1 = 0, I2 = 0;
     for (int i = 0; i < 3; ++i) {
-        if (!(i == 1 && c.M[1] == c.M[0])) vacuum_terms(m.Lambda, c.M[i], I0, I1, I2);
-        PM[i] = twoT * (-3.0 * c.invT * c.M[i] * facc[i]) + 2.0 * m.Nc * I1;
+        if (!(i == 1 && c.M[1] == c.M[0])) vacuum_terms(m.Lambda, c.M[i], I0, I1, I2);   // M_d == M_u: reuse
+        I1v[i] = I1;
+        I2v[i] = I2;
     }
-    const double g4 = -4.0 * m.G, k2 = 2.0 * m.K;
     UTerms u;
     polyakov_U(m, c.T, c.invT, x[3], x[4], u);
+    finish_fj_pre(m, c, x, acc, I1v, I2v, u, F, J, fast);
+}
+
+// F = grad_x P alone, from the reduced sums of a fused final pass (same formulas as finish_fj).
+PNJL_HD void finish_f_pre(const Model& m, const PointCtx& c, const double x[5], const double facc[5], const double I1v[3],
+                          const UTerms& u, double F[5]) {
+    const double twoT = 2.0 * c.T;
+    double PM[3];
+    for (int i = 0; i < 3; ++i) PM[i] = twoT * (-3.0 * c.invT * c.M[i] * facc[i]) + 2.0 * m.Nc * I1v[i];
+    const double g4 = -4.0 * m.G, k2 = 2.0 * m.K;
     F[0] = PM[0] * g4 + PM[1] * (k2 * x[2]) + PM[2] * (k2 * x[1]) + (-4 * m.G * x[0] + 4 * m.K * x[1] * x[2]);
     F[1] = PM[0] * (k2 * x[2]) + PM[1] * g4 + PM[2] * (k2 * x[0]) + (-4 * m.G * x[1] + 4 * m.K * x[0] * x[2]);
     F[2] = PM[0] * (k2 * x[1]) + PM[1] * (k2 * x[0]) + PM[2] * g4 + (-4 * m.G * x[2] + 4 * m.K * x[0] * x[1]);
     F[3] = twoT * 3.0 * facc[3] - u.U_P;
     F[4] = twoT * 3.0 * facc[4] - u.U_Pb;
+}
+
+PNJL_HD void finish_f(const Model& m, const PointCtx& c, const double x[5], const double facc[5], double F[5]) {
+    double I1v[3];
+    double I0 = 0, I1 = 0, I2 = 0;
+    for (int i = 0; i < 3; ++i) {
+        if (!(i == 1 && c.M[1] == c.M[0])) vacuum_terms(m.Lambda, c.M[i], I0, I1, I2);
+        I1v[i] = I1;
+    }
+    UTerms u;
+    polyakov_U(m, c.T, c.invT, x[3], x[4], u);
+    finish_f_pre(m, c, x, facc, I1v, u, F);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -992,16 +1049,13 @@ struct Thermo {
     double rho[3], nq[3], nqb[3], M[3];
 };
 
-PNJL_HD void finish_thermo(const Model& m, const PointCtx& c, const double x[5], const double acc[kThAcc], Thermo& th) {
+PNJL_HD void finish_thermo_pre(const Model& m, const PointCtx& c, const double x[5], const double acc[kThAcc],
+                               const double I0v[3], const UTerms& u, Thermo& th) {
     const double T = c.T;
-    UTerms u;
-    polyakov_U(m, T, c.invT, x[3], x[4], u);
     const double chi = 2 * m.G * ((x[0] * x[0] + x[1] * x[1]) + x[2] * x[2]) - 4 * m.K * ((x[0] * x[1]) * x[2]);
     double vac = 0.0;
-    double I0 = 0, I1 = 0, I2 = 0;
     for (int i = 0; i < 3; ++i) {
-        if (!(i == 1 && c.M[1] == c.M[0])) vacuum_terms(m.Lambda, c.M[i], I0, I1, I2);
-        vac += I0;
+        vac += I0v[i];
         th.M[i] = c.M[i];
     }
     const double omega = chi + u.U + (-2.0 * m.Nc) * vac + (-2.0 * T) * acc[TH_L];
@@ -1020,6 +1074,18 @@ PNJL_HD void finish_thermo(const Model& m, const PointCtx& c, const double x[5],
     // s = dP/dT at fixed x:  -dU/dT + 2 sum c L + 2T sum c dL/dT,  dL+/dT = 3 n+ (E - mu)/T^2
     th.entropy = -u.U_T + 2.0 * acc[TH_L] + 6.0 * c.invT * acc[TH_T];
     th.energy = -th.pressure + murho + T * th.entropy;
+}
+
+PNJL_HD void finish_thermo(const Model& m, const PointCtx& c, const double x[5], const double acc[kThAcc], Thermo& th) {
+    UTerms u;
+    polyakov_U(m, c.T, c.invT, x[3], x[4], u);
+    double I0v[3];
+    double I0 = 0, I1 = 0, I2 = 0;
+    for (int i = 0; i < 3; ++i) {
+        if (!(i == 1 && c.M[1] == c.M[0])) vacuum_terms(m.Lambda, c.M[i], I0, I1, I2);
+        I0v[i] = I0;
+    }
+    finish_thermo_pre(m, c, x, acc, I0v, u, th);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1070,9 +1136,11 @@ PNJL_HD_NOINL bool lu_solve5(const double A_in[25], const double b_in[5], double
 
 // Same elimination order as lu_solve5, fully unrolled with select-based row swaps so that A, b and y live in
 // registers (used in the fused quadrature-pass epilogue; A and b are destroyed).
+PNJL_HD_NOINL double cold_rcp(double v) { return 1.0 / v; }   // out of line: IEEE division is ~100 instructions
 PNJL_HD double guarded_rcp(double v) {
     const double a = fabs(v);
-    return (a > 1e-280 && a < 1e280) ? fast_rcp(v) : 1.0 / v;
+    if (a > 1e-280 && a < 1e280) return fast_rcp(v);
+    return cold_rcp(v);
 }
 PNJL_HD bool lu_solve5_regs(double A[25], double b[5], double y[5]) {
     bool ok = true;

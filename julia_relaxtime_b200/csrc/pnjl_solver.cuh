@@ -43,12 +43,14 @@ struct PointRes {
     bool converged;
 };
 
+// First-order boundary tables mu_c(T), one per xi (PhaseBoundaryData, SeedStrategies.jl:365-371), flattened: table t owns the
+// rows [start[t], start[t + 1]) of T / mu.  Any number of tables and rows (device: the arrays live in global memory).
 struct PhaseTables {
     int n_tables;
-    int n[PNJL_MAX_TABLES];
-    double T_CEP[PNJL_MAX_TABLES];
-    double T[PNJL_MAX_TABLES][PNJL_MAX_TABLE_ROWS];
-    double mu[PNJL_MAX_TABLES][PNJL_MAX_TABLE_ROWS];
+    const int* start;      // [n_tables + 1]
+    const double* T_CEP;   // [n_tables]  NaN: unknown
+    const double* T;       // [rows] ascending within a table
+    const double* mu;      // [rows]
 };
 
 enum { PH_UNKNOWN = 0, PH_HADRON = 1, PH_QUARK = 2, PH_CROSSOVER = 3 };
@@ -92,26 +94,31 @@ PNJL_HD void multiseed_seed(int s, double T_fm, double mu_fm, double out[5]) {
 }
 
 // ---- phase table ---------------------------------------------------------------------------------
+// _get_current_phase (SeedStrategies.jl:762-782) over interpolate_mu_c (:446-475).  The reference scans the rows for the
+// first i with T[i] <= T_MeV <= T[i+1]; for ascending rows and T[0] < T_MeV < T[n-1] that is i = j - 1 with j the first row
+// index >= 1 whose T[j] >= T_MeV, found here by bisection (same segment, same arithmetic, any table length).
 PNJL_HD int current_phase(const PhaseTables* pt, int ti, double T_MeV, double mu_MeV) {
     if (ti < 0 || ti >= pt->n_tables) return PH_UNKNOWN;  // empty table, NaN CEP -> :unknown
     const double tcep = pt->T_CEP[ti];
     if (tcep == tcep && T_MeV > tcep) return PH_CROSSOVER;
-    const int n = pt->n[ti];
+    const int n = pt->start[ti + 1] - pt->start[ti];
     if (n == 0) return PH_UNKNOWN;
-    const double* Ts = pt->T[ti];
-    const double* ms = pt->mu[ti];
+    const double* Ts = pt->T + pt->start[ti];
+    const double* ms = pt->mu + pt->start[ti];
     double mu_c;
     if (T_MeV <= Ts[0]) mu_c = ms[0];
     else if (T_MeV >= Ts[n - 1]) mu_c = ms[n - 1];
+    else if (!(T_MeV == T_MeV)) mu_c = NAN;
     else {
-        mu_c = NAN;
-        for (int i = 0; i + 1 < n; ++i) {
-            if (Ts[i] <= T_MeV && T_MeV <= Ts[i + 1]) {
-                const double w = (T_MeV - Ts[i]) / (Ts[i + 1] - Ts[i]);
-                mu_c = ms[i] + w * (ms[i + 1] - ms[i]);
-                break;
-            }
+        int lo = 1, hi = n - 1;          // invariant: Ts[hi] >= T_MeV; the answer j is in [lo, hi]
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (Ts[mid] >= T_MeV) hi = mid;
+            else lo = mid + 1;
         }
+        const int i = lo - 1;
+        const double w = (T_MeV - Ts[i]) / (Ts[i + 1] - Ts[i]);
+        mu_c = ms[i] + w * (ms[i + 1] - ms[i]);
     }
     if (mu_c != mu_c) return PH_UNKNOWN;
     return mu_MeV < mu_c ? PH_HADRON : PH_QUARK;
@@ -531,7 +538,8 @@ PNJL_HD void fill_record(const PointRes& r, double T, double mu, double xi, int 
     rec[PNJL_REC_ENERGY] = r.th.energy;
     rec[PNJL_REC_RESNORM] = r.res;
     rec[PNJL_REC_ITER] = (double)r.it;
-    rec[PNJL_REC_STATUS] = (double)r.status;
+    // flag the high-Omega root the reference's physicality filter lets through (see PNJL_ST_MASS_INVERSION); values unchanged
+    rec[PNJL_REC_STATUS] = (double)(r.status | ((r.converged && r.th.M[2] <= r.th.M[0]) ? PNJL_ST_MASS_INVERSION : 0));
     rec[PNJL_REC_NEVAL] = (double)n_fj;
     rec[PNJL_REC_NTHERMO] = (double)n_th;
     rec[PNJL_REC_T] = T;
@@ -580,6 +588,63 @@ PNJL_HD_NOINL void scan_line(Solver<Ev>& sv, const PhaseTables* pt, int ti, doub
         }
         sink(it, r, T_fm, mu_fm, sv.n_fj, sv.n_th, sv.n_ft);
     }
+}
+
+// The same march in resumable form: everything a (xi, muq) line carries from one T to the next — the tracker of
+// PhaseAwareContinuitySeed (SeedStrategies.jl:851-856: previous solution + its phase), the index of the next T and the
+// iteration-count history — lives in a LineState, so that a line can be advanced a few points at a time by whichever
+// warp (team) is free and parked in between (k_march: time-sliced lines from a global queue).  Marching a line in
+// slices gives bit-identical records to scan_line() in one go.
+struct LineState {
+    double prev[5];     // tracker: previous converged solution
+    int it_next;        // next T index to solve
+    int prev_phase;     // tracker: phase of the previous converged point
+    int has_prev;       // tracker holds a solution
+    int its_hint;       // Solver::its_hint carried across points
+    int pad[4];
+};
+
+template <class Ev, class Sink>
+PNJL_HD_NOINL void scan_line_slice(Solver<Ev>& sv, const PhaseTables* pt, int ti, double muq_MeV, double xi, int n_T,
+                                   const double* T_MeV, LineState& st, int max_points, Sink& sink) {
+    Tracker tk;
+    copy5(tk.prev, st.prev);
+    tk.has_prev = st.has_prev != 0;
+    tk.prev_phase = st.prev_phase;
+    sv.its_hint = st.its_hint;
+    const double mu_fm = muq_MeV / sv.m.hbarc;
+    const int it_end = (st.it_next + max_points < n_T) ? st.it_next + max_points : n_T;
+    PointRes r;
+    for (int it = st.it_next; it < it_end; ++it) {
+        const double Tm = T_MeV[it];
+        const double T_fm = Tm / sv.m.hbarc;
+        sv.set_point(T_fm, mu_fm, xi);
+        sv.n_fj = 0;
+        sv.n_th = 0;
+        sv.n_ft = 0;
+        if (!tk.has_prev) {
+            sv.its_hint = 0;
+            sv.solve_multi(nullptr, 6, r);
+        } else {
+            double x0[5];
+            const bool sw = sv.tracker_seed(pt, ti, tk, x0);
+            if (sw) sv.its_hint = 0;
+            sv.solve_with_fallback(x0, r);
+            if (sw) r.status |= PNJL_ST_PHASE_SWITCH;
+        }
+        sv.its_hint = (r.converged && !(r.status & (PNJL_ST_USED_TR | PNJL_ST_TR_ATTEMPTED | PNJL_ST_USED_MULTISEED))) ? r.it : 0;
+        if (r.converged) {
+            copy5(tk.prev, r.x);
+            tk.has_prev = true;
+            tk.prev_phase = current_phase(pt, ti, Tm, muq_MeV);
+        }
+        sink(it, r, T_fm, mu_fm, sv.n_fj, sv.n_th, sv.n_ft);
+    }
+    copy5(st.prev, tk.prev);
+    st.has_prev = tk.has_prev ? 1 : 0;
+    st.prev_phase = tk.prev_phase;
+    st.its_hint = sv.its_hint;
+    st.it_next = it_end;
 }
 
 // One (xi, T) line of TmuScan.run_tmu_scan (src/pnjl/scans/TmuScan.jl:120-234): march mu in the given order.

@@ -170,19 +170,33 @@ void hostsim_scan_lines_mode(const pnjl_config* c, int64_t n_lines, const double
     Model m = model_of(c);
     SolverParams sp = params_of(c);
     HostMesh mesh = mesh_of(c);
-    PhaseTables* pt = new PhaseTables();
-    pt->n_tables = n_tables;
+    std::vector<int> pt_start(n_tables + 1, 0);
+    std::vector<double> pt_tcep(n_tables > 0 ? n_tables : 1), pt_T, pt_mu;
     for (int t = 0; t < n_tables; ++t) {
-        pt->n[t] = tables[t].n;
-        pt->T_CEP[t] = tables[t].T_CEP_MeV;
-        for (int i = 0; i < tables[t].n; ++i) { pt->T[t][i] = tables[t].T_MeV[i]; pt->mu[t][i] = tables[t].mu_c_MeV[i]; }
+        pt_tcep[t] = tables[t].T_CEP_MeV;
+        for (int i = 0; i < tables[t].n; ++i) { pt_T.push_back(tables[t].T_MeV[i]); pt_mu.push_back(tables[t].mu_c_MeV[i]); }
+        pt_start[t + 1] = (int)pt_T.size();
     }
+    PhaseTables pts{n_tables, pt_start.data(), pt_tcep.data(), pt_T.data(), pt_mu.data()};
+    const PhaseTables* pt = &pts;
 #pragma omp parallel for schedule(dynamic, 1)
     for (int64_t l = 0; l < n_lines; ++l) {
         HostEval ev{&m, &mesh, c->isospin_symmetric};
         Solver<HostEval> sv(m, sp, ev);
         Sink sink{records + PNJL_REC_DOUBLES * n_T * (mode == 2 ? 0 : l), xi[l]};
         if (mode == 0) scan_line(sv, pt, table_idx ? table_idx[l] : -1, muq_MeV[l], xi[l], n_T, T_MeV, sink);
+        else if (mode >= 100) {
+            // the resumable march of the line-march kernel, in slices of (mode - 100) points, each slice with a FRESH solver
+            // object (as when another warp picks the line up)
+            LineState st;
+            std::memset(&st, 0, sizeof(st));
+            st.prev_phase = PH_UNKNOWN;
+            while (st.it_next < n_T) {
+                HostEval ev2{&m, &mesh, c->isospin_symmetric};
+                Solver<HostEval> sv2(m, sp, ev2);
+                scan_line_slice(sv2, pt, table_idx ? table_idx[l] : -1, muq_MeV[l], xi[l], n_T, T_MeV, st, mode - 100, sink);
+            }
+        }
         else if (mode == 1) scan_tmu_line(sv, pt, table_idx ? table_idx[l] : -1, muq_MeV[l], xi[l], n_T, T_MeV, sink);
         else {
             // dual-branch: records [line][2][n_mu]
@@ -192,7 +206,6 @@ void hostsim_scan_lines_mode(const pnjl_config* c, int64_t n_lines, const double
             }
         }
     }
-    delete pt;
 }
 
 // build_K_data through the product's header (oneloop_A + effective_couplings): aux [n][16]
