@@ -11,12 +11,13 @@ A "step" is one full pass of the hot path over the workload grid:
   cfg4: 2048x2048 window near the CEP (T 100..160, mu_q 260..330, xi=0), 64x16.
   cfg3: 256x256x8 independent points, MultiSeed at every point, 64x16.
   cfg2: 128x128 isotropic scan, 12x6 nodes (the script's defaults).
-With N GPUs the grid is split by contiguous mu-slabs; each rank runs its slab with no exchange, rank 0 gathers the
-records over NCCL (inside the timed region), `value` = all converged points / max-over-ranks device time.
-  --scaling weak   (default, the contract's rule for a path that partitions): every GPU carries one full workload
-                   slab, i.e. the mu axis is refined to N x n_mu points over the same range; N = 1 is exactly the
-                   BASELINE config.
-  --scaling strong the SAME grid at every N (BASELINE's "1024x1024x8 at 1/2/4/8 B200"): n_mu / N mu-values per GPU.
+With N GPUs the mu axis is dealt out over the ranks (round-robin by default, --layout slab for contiguous slabs); each
+rank runs its lines with no exchange and its kernel stores the records straight into rank 0's array over NVLink (or rank 0
+gathers them over NCCL, --gather nccl), inside the timed region; `value` = all converged points / max-over-ranks device time.
+  --scaling strong (default) the SAME grid at every N — BASELINE's "1024x1024x8 at 1/2/4/8 B200": n_mu / N mu-values per GPU.
+                   At N > 1 a short weak-scaling measurement follows and is reported under the key "weak".
+  --scaling weak   every GPU carries one full workload slab, i.e. the mu axis is refined to N x n_mu points over the same
+                   range; N = 1 is exactly the BASELINE config.
 """
 import argparse
 import json
@@ -123,7 +124,24 @@ def build_lines(w):
 # CPU arm: the oracle (C++ restatement of the reference algorithm, nested-dual AD like the reference) on all
 # host cores, on a bounded sample of the same workload.
 # ------------------------------------------------------------------------------------------------------------
-def cpu_sample(workload, target_seconds=12.0, threads=None):
+def _lines_sample(workload, n_lines):
+    """`n_lines` complete lines of the workload grid, stratified over (xi, mu) exactly like a GPU rank's share of an
+    interleaved n-rank run would be (every xi, mu spread over the whole range)."""
+    xis, mus, T, p, t = build_lines(workload)
+    n_mu = len(mus)
+    total = len(xis) * n_mu
+    li = (np.arange(n_lines) * (total / float(n_lines)) + 0.5 * total / float(n_lines)).astype(int) % total
+    return li, np.array([xis[i // n_mu] for i in li], dtype=float), mus[li % n_mu], T
+
+
+def cpu_sample(workload, target_seconds=12.0, threads=None, engine="ad"):
+    """The path on the host CPU, SAME CONFIG as the GPU arm: complete lines of the workload grid marched over the complete T
+    grid (MultiSeed bootstrap at T[0], then PhaseAwareContinuitySeed — run_gap_transport_scan.jl:417-443), `threads` lines at a
+    time in parallel, as many as fit the time budget.
+      engine "ad"        oracle/pnjl_oracle.cpp: the reference's arithmetic (Omega once, F and J by nested dual numbers like
+                         ForwardDiff inside NLsolve's autodiff=:forward)
+      engine "analytic"  oracle/pnjl_analytic_cpu.cpp: the GPU kernel's own algorithm (closed-form Jacobian, isospin shortcut,
+                         fused final pass) compiled for the host — the analytic-Jacobian CPU baseline of SURVEY.md §8d"""
     from oracle.oracle import Oracle, load_phase_tables
     kind, xis, n_mu, _, n_T, _, p, t = WORKLOADS[workload]
     xis, mus, T, p, t = build_lines(workload)
@@ -131,48 +149,52 @@ def cpu_sample(workload, target_seconds=12.0, threads=None):
     o = Oracle(p_num=p, t_num=t, max_iter=MAX_ITER, n_threads=threads)
     gdir = os.path.join(ROOT, "julia_relaxtime_b200", "data")
     tables, index = load_phase_tables(os.path.join(gdir, "boundary.csv"), os.path.join(gdir, "cep.csv"), xis)
+    hs = None
+    if engine == "analytic":
+        from tests.hostsim.hostsim import HostSim
+        os.environ["OMP_NUM_THREADS"] = str(threads)
+        hs = HostSim(o.p_nodes, o.p_w, o.c_nodes, o.c_w, max_iter=MAX_ITER)
     rng = np.random.default_rng(0)
     if kind == "points":
-        # calibrate on `threads` points, then size the sample
         def run(n):
             Tm = rng.choice(T, n); mm = rng.choice(mus, n); xx = rng.choice(xis, n)
             t0 = time.perf_counter()
-            r = o.solve_points(Tm / HBARC, mm / HBARC, xx, "multi")
-            return time.perf_counter() - t0, r
-        dt, _ = run(threads)
-        n = int(max(threads, min(200000, threads * target_seconds / max(dt, 1e-3))))
-        dt, r = run(n)
-        return dict(points=n, seconds=dt, converged=int(r.converged.sum()), n_fj=int(r.n_fj.sum()), threads=threads,
+            if hs is None:
+                r = o.solve_points(Tm / HBARC, mm / HBARC, xx, "multi")
+                conv, nfj = int(r.converged.sum()), int(r.n_fj.sum())
+            else:
+                rec = hs.solve_points(Tm / HBARC, mm / HBARC, xx)
+                conv = int(((rec[:, 21].astype(np.int64) & 1) != 0).sum())
+                nfj = int(rec[:, 22].sum() + rec[:, 30].sum())
+            return time.perf_counter() - t0, conv, nfj
+        dt, _, _ = run(threads)
+        n = int(max(threads, min(400000, threads * target_seconds / max(dt, 1e-3))))
+        dt, conv, nfj = run(n)
+        return dict(points=n, seconds=dt, converged=conv, n_fj=nfj, threads=threads, engine=engine,
                     sample="%d random grid points of the %s grid, MultiSeed each" % (n, workload))
-    # lines: G groups of `threads` lines (spread over xi and mu); every group marches one contiguous window of
-    # the true T grid (true dT) in a single OpenMP-parallel oracle call, the windows of successive groups being
-    # spread evenly over [T0, T1]; each window starts with the MultiSeed bootstrap like a line does.
-    win = min(n_T, 32)
-    n_win = max(1, n_T // win)
 
-    def run(groups):
-        n_lines = groups * threads
-        li = np.linspace(0, len(xis) * n_mu - 1, n_lines).astype(int)
-        rng.shuffle(li)
-        lx = np.array([xis[i // n_mu] for i in li], dtype=float)
-        lm = np.array([mus[i % n_mu] for i in li])
+    def run(n_lines, n_t):
+        li, lx, lm, _ = _lines_sample(workload, n_lines)
         tidx = np.array([index[x] for x in lx], dtype=np.int32)
         t0 = time.perf_counter()
-        tot = conv = nfj = 0
-        for g in range(groups):
-            wdx = int(round(g * (n_win - 1) / max(1, groups - 1))) if groups > 1 else n_win // 2
-            sel = slice(g * threads, (g + 1) * threads)
-            r = o.scan_lines(lm[sel], lx[sel], T[wdx * win:(wdx + 1) * win], tables, tidx[sel])
-            tot += r.n; conv += int(r.converged.sum()); nfj += int(r.n_fj.sum())
+        if hs is None:
+            r = o.scan_lines(lm, lx, T[:n_t], tables, tidx)
+            conv, nfj, tot = int(r.converged.sum()), int(r.n_fj.sum()), r.n
+        else:
+            rec = hs.scan_lines(lm, lx, T[:n_t], tables, tidx).reshape(-1, 32)
+            conv = int(((rec[:, 21].astype(np.int64) & 1) != 0).sum())
+            nfj, tot = int(rec[:, 22].sum() + rec[:, 30].sum()), rec.shape[0]
         return time.perf_counter() - t0, tot, conv, nfj
 
-    dt, tot, _, _ = run(1)
-    groups = int(max(1, min(n_win, round(target_seconds / max(dt, 1e-3)))))
-    dt, tot, conv, nfj = run(groups)
-    return dict(points=tot, seconds=dt, converged=conv, n_fj=nfj, threads=threads,
-                sample="%d groups x %d lines (spread over xi, mu), each group marching one %d-point contiguous window "
-                       "of the true T grid (windows spread over %g-%g MeV; MultiSeed bootstrap at each window "
-                       "start)" % (groups, threads, win, T[0], T[-1]))
+    # calibrate on a short prefix, then march whole lines: `groups` x `threads` of them
+    n_cal = min(n_T, 48)
+    dt, tot, _, _ = run(threads, n_cal)
+    per_line = dt * n_T / n_cal
+    groups = int(max(1, min(64, round(target_seconds / max(per_line, 1e-3)))))
+    dt, tot, conv, nfj = run(groups * threads, n_T)
+    return dict(points=tot, seconds=dt, converged=conv, n_fj=nfj, threads=threads, engine=engine,
+                sample="%d complete lines (stratified over xi and mu) x all %d T of the %s grid, %d lines at a time "
+                       "(MultiSeed bootstrap at T[0], then PhaseAwareContinuitySeed)" % (groups * threads, n_T, workload, threads))
 
 
 def run_reference(args):

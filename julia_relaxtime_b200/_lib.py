@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD_DIR = os.path.join(CSRC, "_build")
 LIB_PATH = os.path.join(BUILD_DIR, "libpnjl_b200.so")
-SOURCES = [os.path.join(CSRC, f) for f in ("pnjl_kernels.cu", "pnjl_math.cuh", "pnjl_solver.cuh", "pnjl_march.cuh")] + [
+SOURCES = [os.path.join(CSRC, f) for f in ("pnjl_kernels.cu", "pnjl_math.cuh", "pnjl_solver.cuh", "pnjl_march.cuh", "pnjl_lean.cuh")] + [
     os.path.join(HERE, "..", "include", "pnjl_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

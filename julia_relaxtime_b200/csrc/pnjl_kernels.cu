@@ -26,6 +26,7 @@
 #include <vector>
 
 #include "pnjl_solver.cuh"
+#include "pnjl_lean.cuh"
 
 namespace pnjl {
 
@@ -1136,7 +1137,6 @@ int launch_march(pnjl_handle* h, long long n_lines, const double* muq, const dou
     a.out_index = h->out_index_next;
     a.capacity = n_lines * n_quanta;
     a.quantum = quantum;
-    a.parts = parts;
     CUDA_TRY(h->march_state.reserve(sizeof(LineState) * (size_t)n_lines));
     CUDA_TRY(h->march_slots.reserve(sizeof(int) * (size_t)a.capacity));
     CUDA_TRY(h->march_counters.reserve(sizeof(unsigned long long) * 4));
@@ -1144,8 +1144,18 @@ int launch_march(pnjl_handle* h, long long n_lines, const double* muq, const dou
     a.slots = (int*)h->march_slots.p;
     a.counters = (unsigned long long*)h->march_counters.p;
     const int n_mesh = 3 * h->n_nodes + 2 * h->host_cfg.n_iso;
-    const size_t smem = sizeof(double) * (size_t)(((n_mesh + 1) & ~1) + kMarchWarps * kStageDoubles + 2 * kMarchWarps * kBufStride) +
-                        sizeof(int) * kMarchWarps;
+    MarchConst mc;
+    std::memset(&mc, 0, sizeof(mc));
+    mc.cfg = h->d_cfg;
+    mc.parts = parts;
+    mc.stage0 = (n_mesh + 1) & ~1;
+    mc.lean0 = mc.stage0 + kMarchWarps * kStageDoubles;
+    mc.team0 = mc.lean0 + kMarchWarps * LW_END;
+    mc.int0 = mc.team0 + 2 * kMarchWarps * kBufStride;
+    mc.n = h->n_nodes; mc.n_iso = h->host_cfg.n_iso;
+    mc.p2max = h->host_cfg.p2max; mc.pc2max = h->host_cfg.pc2max;
+    mc.sp = h->host_cfg.sp;
+    const size_t smem = sizeof(double) * (size_t)(mc.int0 + kMarchWarps);     // 2 x 16 ints at the end
     cudaFuncAttributes fa;
     CUDA_TRY(cudaFuncGetAttributes(&fa, k_march));
     if (smem > 40 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_march, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1155,10 +1165,14 @@ int launch_march(pnjl_handle* h, long long n_lines, const double* muq, const dou
     h->stats.blocks = blocks;
     h->stats.threads = 32 * kMarchWarps;
     h->stats.lanes_per_solve = 32 * parts;
+    // model and launch constants go to constant memory on the launch stream (stream-ordered with the kernel; two handles with
+    // DIFFERENT constants must not launch concurrently on the same device — calls on one handle are serial anyway)
+    CUDA_TRY(cudaMemcpyToSymbolAsync(c_model, &h->host_cfg.m, sizeof(Model), 0, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyToSymbolAsync(c_mc, &mc, sizeof(MarchConst), 0, cudaMemcpyHostToDevice, st));
     const long long n_init = a.capacity > n_lines ? a.capacity : n_lines;
     k_march_init<<<(unsigned)((n_init + 255) / 256), 256, 0, st>>>(a);
     CUDA_TRY(cudaGetLastError());
-    k_march<<<blocks, 32 * kMarchWarps, smem, st>>>(h->d_cfg, h->d_mesh, a);
+    k_march<<<blocks, 32 * kMarchWarps, smem, st>>>(h->d_mesh, a);
     CUDA_TRY(cudaGetLastError());
     h->stats.kernel_launches += 2;
     return PNJL_OK;

@@ -1,14 +1,18 @@
-// pnjl_march.cuh — the line-march kernel k_march (included by pnjl_kernels.cu inside namespace pnjl).
+// pnjl_march.cuh — the line-march kernel k_march (included by pnjl_kernels.cu inside namespace pnjl, after pnjl_lean.cuh).
 //
 // One warp (or a team of 2/4/8/16 warps when a GPU holds fewer lines than warps) owns a (xi, mu) line and runs its whole
 // continuity march — seed, Newton iterations, final thermodynamics, record — in its own registers
 // (run_gap_transport_scan.jl:407-443, ImplicitSolver.jl:211-328 through Solver<WarpEval>):
 //   * a quadrature pass is the same paired FP64 loop as in k_solve_ws (ws_worker_pass: lanes stride the mesh in shared
-//     memory, transposed shuffle butterfly), the 20 sums are broadcast to all lanes through the warp's shared-memory
-//     scratch line, and the closed-form finish + the 5x5 elimination run in the same warp right away — no hand-over, no
-//     controller warps, no polling.  The finish is kept small: the vacuum integrals of the u and the s flavour are
-//     evaluated by different lanes, a Jacobian pass skips the logarithm of the Polyakov potential, and every libm
-//     fall-back sits in an out-of-line cold function;
+//     memory, transposed shuffle butterfly); the 20 sums land in the warp's shared-memory scratch line and the closed-form
+//     finish + the 5x5 elimination run in the same warp right away, LANE-PARALLEL (pnjl_lean.cuh: one flavour / one matrix
+//     entry per lane) — no hand-over, no controller warps, no polling;
+//   * the common case — plain Newton from the continuity seed converges to a physical state (ImplicitSolver.jl:103-128) — is
+//     a small state machine inlined in the kernel (one pass site, registers only, constants from constant memory): the
+//     per-pass code is ~10 KB including the quadrature loop, so 16 desynchronised warps stay inside the SM's 32 KB
+//     instruction cache (the redundant-per-lane version ran 1.8x slower for that reason alone).  Everything else
+//     (MultiSeed bootstrap, trust-region fallback, unphysical or floored states) goes through the generic Solver<WarpEval>
+//     cascade out of line;
 //   * lines are time-sliced: a global ticket queue hands out (line, next T index) quanta of `quantum` points; a warp that
 //     finishes a quantum parks the line's tracker state (64 bytes) in global memory, re-queues the line and takes the oldest
 //     waiting one.  All lines therefore advance at the same pace on ALL SMs (no per-SM imbalance, the tail is one quantum),
@@ -37,8 +41,23 @@ struct MarchArgs {
     unsigned long long* counters;     // [0] pop tickets, [1] push tickets, [2] finished lines
     long long capacity;
     int quantum;                      // points per time slice
-    int parts;                        // warps per team
 };
+
+// Launch constants in constant memory (uploaded by launch_march on the launch stream, like the model constants): the per-warp
+// context — which lines of shared memory are mine, how big is my team — is derived from threadIdx and these, so no warp keeps
+// a context object in (local) memory and the finish code takes its constants as constant-bank operands.
+struct MarchConst {
+    const DeviceConfig* cfg;
+    int parts;                        // warps per team (1, 2, 4, 8 or 16)
+    int stage0, lean0, team0, int0;   // offsets (in doubles) into the dynamic shared memory: staging lines [16][32] | scratch
+                                      // lines [16][LW_END] | team buffers [2][16][24] | ints: popped line [16], pass parity [16]
+    int n, n_iso;
+    double p2max, pc2max;
+    SolverParams sp;
+};
+__constant__ MarchConst c_mc;
+__constant__ Model c_model;
+extern __shared__ double g_smem[];    // namespace scope: device functions address their lines by index, i.e. as SHARED memory
 
 __global__ void k_march_init(MarchArgs a) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -54,197 +73,291 @@ __global__ void k_march_init(MarchArgs a) {
     if (i == 0) { a.counters[0] = 0ULL; a.counters[1] = (unsigned long long)a.n_lines; a.counters[2] = 0ULL; }
 }
 
-__device__ __noinline__ void vacuum_terms_cold(double Lam, double M, double& I0, double& I1, double& I2) {
-    vacuum_terms_t<false>(Lam, M, I0, I1, I2);
+// ---- per-warp context, recomputed where it is needed ----
+__device__ __forceinline__ int mc_lane() { return threadIdx.x & 31; }
+__device__ __forceinline__ int mc_warp() { return threadIdx.x >> 5; }
+__device__ __forceinline__ int mc_part() { return mc_warp() & (c_mc.parts - 1); }
+__device__ __forceinline__ int mc_team() { return mc_warp() / c_mc.parts; }
+__device__ __forceinline__ double* mc_stage() { return g_smem + c_mc.stage0 + mc_warp() * kStageDoubles; }
+__device__ __forceinline__ double* mc_W() { return g_smem + c_mc.lean0 + mc_warp() * LW_END; }
+__device__ __forceinline__ int* mc_ints() { return reinterpret_cast<int*>(g_smem + c_mc.int0); }
+__device__ __forceinline__ void mc_mesh(MeshView& mv) {
+    const int n = c_mc.n;
+    mv.p2 = g_smem; mv.pc2 = g_smem + n; mv.coef = g_smem + 2 * n; mv.n = n;
+    mv.p2max = c_mc.p2max; mv.pc2max = c_mc.pc2max;
+    mv.p2_iso = g_smem + 3 * n; mv.coef_iso = g_smem + 3 * n + c_mc.n_iso; mv.n_iso = c_mc.n_iso;
 }
-__device__ __noinline__ void polyakov_cold(const Model& m, double T, double iT, double P, double Pb, UTerms& u) {
-    polyakov_eval<false, true>(m, T, iT, P, Pb, u);
+__device__ __forceinline__ void mc_team_sync() {
+    if (c_mc.parts > 1) asm volatile("bar.sync %0, %1;" ::"r"(1 + mc_team()), "r"(32 * c_mc.parts) : "memory");
+    else __syncwarp();
 }
 
-struct WarpEval {
-    const DeviceConfig* cfg;
-    const Model* m;
+// One quadrature pass of kind `type` at (T, mu, xi, x); afterwards the reduced sums of the whole mesh are in W[LW_S ..] of every
+// warp of the team.  Partial sums of the team's warps are added in part order (lane-parallel), so the result does not depend
+// on which warp is faster; the team buffers are double-buffered by pass parity, so one named barrier per pass suffices.
+__device__ __noinline__ void march_pass(int type, double T, double mu, double xi, double x0, double x1, double x2, double x3, double x4) {
+    const int lane = mc_lane();
+    double* stage = mc_stage();
+    double* W = mc_W();
+    __syncwarp();
+    if (lane == 0) {
+        stage[0] = T; stage[1] = mu; stage[2] = xi;
+        stage[3] = x0; stage[4] = x1; stage[5] = x2; stage[6] = x3; stage[7] = x4;
+    }
+    __syncwarp();
     MeshView mv;
-    double* stage;       // this warp's staging line in shared memory [kStageDoubles]
-    double* team_buf;    // this team's reduced partial sums [2][parts][kBufStride] (double-buffered by pass parity)
-    int lane, part, parts, bar_id, parity, isospin;
-
-    __device__ __forceinline__ void team_sync() const {
-        if (parts > 1) asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(32 * parts) : "memory");
-        else __syncwarp();
-    }
-
-    // One quadrature pass of kind `type` at (T, mu, xi, x): every lane of every warp of the team ends up with the N sums.
-    // Partial sums of the team's warps are added in part order, so the result does not depend on which warp is faster.
-    template <int N>
-    __device__ __forceinline__ bool pass(int type, double T, double mu, double xi, const double x[5], double (&acc)[N]) {
+    mc_mesh(mv);
+    const int parts = c_mc.parts;
+    if (parts == 1) {
+        ws_worker_pass(c_mc.cfg, mv, stage, type, lane, 0, 1, W + LW_S);
         __syncwarp();
-        if (lane == 0) {
-            stage[0] = T; stage[1] = mu; stage[2] = xi;
+        return;
+    }
+    int* parity = mc_ints() + kMarchWarps + mc_warp();
+    double* base = g_smem + c_mc.team0 + (mc_team() * 2 + *parity) * parts * kBufStride;
+    ws_worker_pass(c_mc.cfg, mv, stage, type, lane, mc_part(), parts, base + mc_part() * kBufStride);
+    mc_team_sync();
+    if (lane < kBufStride) {
+        double v = base[lane];
+        if (lane != 20)
+            for (int q = 1; q < parts; ++q) v += base[q * kBufStride + lane];
+        W[LW_S + lane] = v;
+    }
+    if (lane == 0) *parity ^= 1;
+    __syncwarp();
+}
+
+// ---- lane-parallel finishes (pnjl_lean.cuh) of the three kinds of pass; the sums are in W[LW_S ..] ----
+// Phase A.  KIND 0: Jacobian pass, 1: fused final pass, 2: thermo pass.  Returns false (uniformly) when a closed form is not
+// tame (Polyakov argument at its floor, absurd masses): the caller then takes the redundant cold version.
+template <int KIND>
+__device__ __forceinline__ bool lean_phase_a(const PointCtx& c, const double x[5], const LeanConst& k, UTerms& u) {
+    const int lane = mc_lane();
+    double* W = mc_W();
+    bool tame = polyakov_tame(c.Phi, c.Phib);
+    if (lane < 3) {
+        const double Mf = lane == 0 ? c.M[0] : (lane == 1 ? c.M[1] : c.M[2]);
+        const double M2f = lane == 0 ? c.M2[0] : (lane == 1 ? c.M2[1] : c.M2[2]);
+        if (KIND == 0) tame = lean_flavour_fj(lane, k, Mf, M2f, W[LW_S + 20] != 0.0, W) && tame;
+        else if (KIND == 1) tame = lean_flavour_ft(lane, k, Mf, W) && tame;
+        else tame = lean_flavour_th(lane, k, Mf, W) && tame;
+    } else if (lane < 12) {
+        const int r = (lane - 3) / 3, j = (lane - 3) - 3 * r;
+        if (KIND != 2) lean_dtable(r, j, k, x, W);
+    } else if (lane == 12) {
+        if (KIND != 2) {
 #pragma unroll
-            for (int i = 0; i < 5; ++i) stage[3 + i] = x[i];
+            for (int q = 0; q < 5; ++q) W[LW_X + q] = x[q];
         }
+    }
+    tame = __all_sync(0xffffffffu, tame);
+    if (!tame) return false;
+    polyakov_eval<true, KIND != 0>(c_model, c.T, c.invT, c.Phi, c.Phib, u);
+    if (KIND != 2 && lane == 13) {
+        W[LW_U + 0] = u.U_P; W[LW_U + 1] = u.U_Pb;
+        if (KIND == 0) { W[LW_U + 2] = u.U_PP; W[LW_U + 3] = u.U_PPb; W[LW_U + 4] = u.U_PbPb; }
+    }
+    __syncwarp();
+    return true;
+}
+
+// Jacobian pass: F(x) and the Newton direction p = -J^{-1} F.  1: ok, 0: a pivot was exactly zero, -1: not tame.
+__device__ __forceinline__ int lean_finish_fj(double T, double mu, double xi, const double x[5], double F[5], double p[5]) {
+    const int lane = mc_lane();
+    double* W = mc_W();
+    PointCtx c;
+    make_ctx(c_model, T, mu, xi, x, c);
+    LeanConst k;
+    lean_consts(c_model, c.T, c.invT, k);
+    UTerms u;
+    if (!lean_phase_a<0>(c, x, k, u)) return -1;
+    const int li = lane / 6, lc = lane - 6 * li;
+    double a = 0.0;
+    if (lane < 30) {
+        a = lean_aug_entry(li, lc, k, W, ACC_GP, ACC_GPB);
+        W[LW_AUG + lane] = a;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 5; ++i) F[i] = W[LW_AUG + 6 * i + 5];
+    bool ok = true;
+#pragma unroll 1
+    for (int step = 0; step < 5; ++step) {
+        double inv = 0.0, nxt = a;
+        if (lane < 30) nxt = lean_lu_step(step, li, lc, W, a, inv, ok);
         __syncwarp();
-        double* base = team_buf + (size_t)parity * parts * kBufStride;
-        ws_worker_pass(cfg, mv, stage, type, lane, part, parts, base + part * kBufStride);
-        team_sync();
+        if (lane < 30) { a = nxt; W[LW_AUG + lane] = a; }
+        if (lane == 0) W[LW_INV + step] = inv;
+        __syncwarp();
+    }
+    ok = __shfl_sync(0xffffffffu, (int)ok, 0) != 0;
+    lean_backsub(W, p);
 #pragma unroll
-        for (int i = 0; i < N; i += 2) {
-            const double2 v = *reinterpret_cast<const double2*>(base + i);
-            acc[i] = v.x;
-            if (i + 1 < N) acc[i + 1] = v.y;
-        }
-        for (int q = 1; q < parts; ++q) {
+    for (int i = 0; i < 5; ++i) p[i] = -p[i];
+    return ok ? 1 : 0;
+}
+// Fused final pass: F(x) and the thermodynamic functions at x.  false: not tame.
+__device__ __forceinline__ bool lean_finish_ft(double T, double mu, double xi, const double x[5], double F[5], Thermo& th) {
+    const int lane = mc_lane();
+    double* W = mc_W();
+    PointCtx c;
+    make_ctx(c_model, T, mu, xi, x, c);
+    LeanConst k;
+    lean_consts(c_model, c.T, c.invT, k);
+    UTerms u;
+    if (!lean_phase_a<1>(c, x, k, u)) return false;
+    const int li = lane / 6, lc = lane - 6 * li;
+    if (lane < 30 && lc == 5) W[LW_AUG + lane] = lean_aug_entry(li, lc, k, W, 3, 4);
+    __syncwarp();
 #pragma unroll
-            for (int i = 0; i < N; i += 2) {
-                const double2 v = *reinterpret_cast<const double2*>(base + q * kBufStride + i);
-                acc[i] += v.x;
-                if (i + 1 < N) acc[i + 1] += v.y;
-            }
-        }
-        const bool fast = base[20] != 0.0;
-        parity ^= 1;
-        return fast;
-    }
+    for (int i = 0; i < 5; ++i) F[i] = W[LW_AUG + 6 * i + 5];
+    double tacc[kThAcc], I0v[3];
+#pragma unroll
+    for (int i = 0; i < kThAcc; ++i) tacc[i] = W[LW_S + kFtAcc + i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) I0v[i] = W[LW_I0 + i];
+    finish_thermo_pre(c_model, c, x, tacc, I0v, u, th);
+    return true;
+}
+// Thermo pass.
+__device__ __forceinline__ bool lean_finish_th(double T, double mu, double xi, const double x[5], Thermo& th) {
+    double* W = mc_W();
+    PointCtx c;
+    make_ctx(c_model, T, mu, xi, x, c);
+    LeanConst k;
+    lean_consts(c_model, c.T, c.invT, k);
+    UTerms u;
+    if (!lean_phase_a<2>(c, x, k, u)) return false;
+    double tacc[kThAcc], I0v[3];
+#pragma unroll
+    for (int i = 0; i < kThAcc; ++i) tacc[i] = W[LW_S + i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) I0v[i] = W[LW_I0 + i];
+    finish_thermo_pre(c_model, c, x, tacc, I0v, u, th);
+    return true;
+}
 
-    // Closed-form ingredients, one flavour per lane: even lanes take the u flavour (M[0]; M[1] is taken from it when the
-    // masses coincide bitwise), odd lanes the s flavour; the d flavour falls back to the generic evaluation when it differs.
-    __device__ __forceinline__ void vacuum_all(const PointCtx& c, double I0v[3], double I1v[3], double I2v[3]) const {
-#if PNJL_MARCH_LEAN
-        const bool odd = (lane & 1) != 0;
-        const double Mf = odd ? c.M[2] : c.M[0];
-        double I0, I1, I2;
-        if (vacuum_tame(m->Lambda, Mf)) vacuum_terms_t<true>(m->Lambda, Mf, I0, I1, I2);
-        else vacuum_terms_cold(m->Lambda, Mf, I0, I1, I2);
-        I0v[0] = __shfl_sync(0xffffffffu, I0, 0); I0v[2] = __shfl_sync(0xffffffffu, I0, 1);
-        I1v[0] = __shfl_sync(0xffffffffu, I1, 0); I1v[2] = __shfl_sync(0xffffffffu, I1, 1);
-        I2v[0] = __shfl_sync(0xffffffffu, I2, 0); I2v[2] = __shfl_sync(0xffffffffu, I2, 1);
-        if (c.M[1] == c.M[0]) { I0v[1] = I0v[0]; I1v[1] = I1v[0]; I2v[1] = I2v[0]; }
-        else vacuum_terms_cold(m->Lambda, c.M[1], I0v[1], I1v[1], I2v[1]);
-#else
-        double I0 = 0, I1 = 0, I2 = 0;
-        for (int i = 0; i < 3; ++i) {
-            if (!(i == 1 && c.M[1] == c.M[0])) vacuum_terms(m->Lambda, c.M[i], I0, I1, I2);
-            I0v[i] = I0; I1v[i] = I1; I2v[i] = I2;
-        }
-#endif
-    }
-    template <bool WITH_VALUE>
-    __device__ __forceinline__ void polyakov(const PointCtx& c, UTerms& u) const {
-#if PNJL_MARCH_LEAN
-        if (polyakov_tame(c.Phi, c.Phib)) polyakov_eval<true, WITH_VALUE>(*m, c.T, c.invT, c.Phi, c.Phib, u);
-        else polyakov_cold(*m, c.T, c.invT, c.Phi, c.Phib, u);
-#else
-        polyakov_U(*m, c.T, c.invT, c.Phi, c.Phib, u);
-#endif
-    }
+// Redundant-per-lane finishes (finish_fj / finish_f / finish_thermo with their libm fall-backs) for states that are not tame.
+__device__ __noinline__ bool cold_fj_step(double T, double mu, double xi, const double x[5], double F[5], double p[5]) {
+    const double* S = mc_W() + LW_S;
+    PointCtx c;
+    make_ctx(c_model, T, mu, xi, x, c);
+    double acc[kFJAcc], J[25], b[5];
+#pragma unroll
+    for (int i = 0; i < kFJAcc; ++i) acc[i] = S[i];
+    finish_fj(c_model, c, x, acc, F, J, S[20] != 0.0);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) b[i] = F[i];
+    const bool ok = lu_solve5_regs(J, b, p);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) p[i] = -p[i];
+    return ok;
+}
+__device__ __noinline__ void cold_fj(double T, double mu, double xi, const double x[5], double F[5], double J[25]) {
+    const double* S = mc_W() + LW_S;
+    PointCtx c;
+    make_ctx(c_model, T, mu, xi, x, c);
+    double acc[kFJAcc];
+#pragma unroll
+    for (int i = 0; i < kFJAcc; ++i) acc[i] = S[i];
+    finish_fj(c_model, c, x, acc, F, J, S[20] != 0.0);
+}
+__device__ __noinline__ void cold_f_thermo(double T, double mu, double xi, const double x[5], double F[5], Thermo& th) {
+    const double* S = mc_W() + LW_S;
+    PointCtx c;
+    make_ctx(c_model, T, mu, xi, x, c);
+    double facc[kFtAcc], tacc[kThAcc];
+#pragma unroll
+    for (int i = 0; i < kFtAcc; ++i) facc[i] = S[i];
+#pragma unroll
+    for (int i = 0; i < kThAcc; ++i) tacc[i] = S[kFtAcc + i];
+    finish_f(c_model, c, x, facc, F);
+    finish_thermo(c_model, c, x, tacc, th);
+}
+__device__ __noinline__ void cold_thermo(double T, double mu, double xi, const double x[5], Thermo& th) {
+    const double* S = mc_W() + LW_S;
+    PointCtx c;
+    make_ctx(c_model, T, mu, xi, x, c);
+    double tacc[kThAcc];
+#pragma unroll
+    for (int i = 0; i < kThAcc; ++i) tacc[i] = S[i];
+    finish_thermo(c_model, c, x, tacc, th);
+}
 
+// Evaluation policy of the generic cascade (Solver<WarpEval>: MultiSeed bootstrap, trust-region fallback, everything the
+// in-kernel fast path hands back).  Stateless: the context comes from threadIdx and constant memory.
+struct WarpEval {
     __device__ __noinline__ void fj(double T, double mu, double xi, const double x[5], double F[5], double J[25]) {
-        double acc[kFJAcc];
-        const bool fast = pass<kFJAcc>(WS_FJ, T, mu, xi, x, acc);
-        PointCtx c;
-        make_ctx(*m, T, mu, xi, x, c);
-        double I0v[3], I1v[3], I2v[3];
-        vacuum_all(c, I0v, I1v, I2v);
-        UTerms u;
-        polyakov<false>(c, u);
-        finish_fj_pre(*m, c, x, acc, I1v, I2v, u, F, J, fast);
+        march_pass(WS_FJ, T, mu, xi, x[0], x[1], x[2], x[3], x[4]);
+        cold_fj(T, mu, xi, x, F, J);                     // only the trust-region method wants J itself
     }
     __device__ __noinline__ bool fj_step(double T, double mu, double xi, const double x[5], double F[5], double p[5]) {
-        double acc[kFJAcc];
-        const bool fast = pass<kFJAcc>(WS_FJ, T, mu, xi, x, acc);
-        PointCtx c;
-        make_ctx(*m, T, mu, xi, x, c);
-        double I0v[3], I1v[3], I2v[3];
-        vacuum_all(c, I0v, I1v, I2v);
-        UTerms u;
-        polyakov<false>(c, u);
-        double J[25], b[5];
-        finish_fj_pre(*m, c, x, acc, I1v, I2v, u, F, J, fast);
-#pragma unroll
-        for (int i = 0; i < 5; ++i) b[i] = F[i];
-        const bool ok = lu_solve5_regs(J, b, p);
-#pragma unroll
-        for (int i = 0; i < 5; ++i) p[i] = -p[i];
-        return ok;
+        march_pass(WS_FJ, T, mu, xi, x[0], x[1], x[2], x[3], x[4]);
+        const int rc = lean_finish_fj(T, mu, xi, x, F, p);
+        if (rc < 0) return cold_fj_step(T, mu, xi, x, F, p);
+        return rc != 0;
     }
     __device__ __noinline__ bool f_thermo(double T, double mu, double xi, const double x[5], double F[5], Thermo& th) {
         PointCtx c;
-        make_ctx(*m, T, mu, xi, x, c);
-        {
-            const double k2max = mv.p2max + (xi > 0.0 ? xi * mv.pc2max : 0.0);
-            if (!fast_path_ok(c.T, c.mu, c.Phi, c.Phib, k2max, c.M2)) return false;   // uniform over the team
-        }
-        double acc[kFtAcc + kThAcc + 1];
-        pass<kFtAcc + kThAcc + 1>(WS_FT, T, mu, xi, x, acc);
-        double I0v[3], I1v[3], I2v[3];
-        vacuum_all(c, I0v, I1v, I2v);
-        UTerms u;
-        polyakov<true>(c, u);
-        finish_f_pre(*m, c, x, acc, I1v, u, F);
-        finish_thermo_pre(*m, c, x, acc + kFtAcc, I0v, u, th);
+        make_ctx(c_model, T, mu, xi, x, c);
+        const double k2max = c_mc.p2max + (xi > 0.0 ? xi * c_mc.pc2max : 0.0);
+        if (!fast_path_ok(c.T, c.mu, c.Phi, c.Phib, k2max, c.M2)) return false;   // uniform over the team
+        march_pass(WS_FT, T, mu, xi, x[0], x[1], x[2], x[3], x[4]);
+        if (!lean_finish_ft(T, mu, xi, x, F, th)) cold_f_thermo(T, mu, xi, x, F, th);
         return true;
     }
     __device__ __noinline__ void thermo(double T, double mu, double xi, const double x[5], Thermo& th) {
-        double acc[kThAcc];
-        pass<kThAcc>(WS_TH, T, mu, xi, x, acc);
-        PointCtx c;
-        make_ctx(*m, T, mu, xi, x, c);
-        double I0v[3], I1v[3], I2v[3];
-        vacuum_all(c, I0v, I1v, I2v);
-        UTerms u;
-        polyakov<true>(c, u);
-        finish_thermo_pre(*m, c, x, acc, I0v, u, th);
+        march_pass(WS_TH, T, mu, xi, x[0], x[1], x[2], x[3], x[4]);
+        if (!lean_finish_th(T, mu, xi, x, th)) cold_thermo(T, mu, xi, x, th);
     }
 };
 
 // Record writer of a team: warp 0 of the team stages the row in its shared-memory line and the 32 lanes store it.
+__device__ __forceinline__ void march_store_row(const double rec[PNJL_REC_DOUBLES], double* row) {
+    if (mc_part() != 0) return;
+    const int lane = mc_lane();
+    double* stage = mc_stage();
+    __syncwarp();
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < PNJL_REC_DOUBLES; q += 2) *reinterpret_cast<double2*>(stage + q) = make_double2(rec[q], rec[q + 1]);
+    }
+    __syncwarp();
+    row[lane] = stage[lane];
+    __syncwarp();
+}
 struct MarchSink {
-    WarpEval* ev;
     double* base;
     double xi;
     __device__ __forceinline__ void operator()(int it, const PointRes& r, double T_fm, double mu_fm, int n_fj, int n_th,
                                                int n_ft) {
-        if (ev->part != 0) return;
         double rec[PNJL_REC_DOUBLES];
         fill_record(r, T_fm, mu_fm, xi, n_fj, n_th, n_ft, rec);
-        __syncwarp();
-        if (ev->lane == 0) {
-#pragma unroll
-            for (int q = 0; q < PNJL_REC_DOUBLES; q += 2) *reinterpret_cast<double2*>(ev->stage + q) = make_double2(rec[q], rec[q + 1]);
-        }
-        __syncwarp();
-        base[(long long)PNJL_REC_DOUBLES * it + ev->lane] = ev->stage[ev->lane];
-        __syncwarp();
+        march_store_row(rec, base + (long long)PNJL_REC_DOUBLES * it);
     }
 };
 
-// Dynamic shared memory: mesh [3 n + 2 n_iso] | staging lines [16][32] | team buffers [2][16][24] | popped line per team [16]
-__global__ void __launch_bounds__(32 * kMarchWarps, 1) k_march(const DeviceConfig* __restrict__ cfg, const double* __restrict__ g_mesh,
-                                                               MarchArgs a) {
-    extern __shared__ double s_dyn[];
-    const int n = cfg->n_nodes;
-    const int n_mesh = 3 * n + 2 * cfg->n_iso;
-    double* s_mesh = s_dyn;
-    double* s_stage = s_dyn + ((n_mesh + 1) & ~1);
-    double* s_team = s_stage + kMarchWarps * kStageDoubles;
-    int* s_line = reinterpret_cast<int*>(s_team + 2 * kMarchWarps * kBufStride);
-    for (int i = threadIdx.x; i < n_mesh; i += blockDim.x) s_mesh[i] = g_mesh[i];
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int parts = a.parts;
-    const int team = warp / parts, part = warp - team * parts;
+// Anything that is not the common case: one point through the generic cascade, exactly as scan_line_slice does it.
+__device__ __noinline__ void march_generic_point(const PhaseTables* pt, int ti, double muq_MeV, double xi, int n_T, const double* T_MeV,
+                                                 LineState& st, double* rows) {
     WarpEval ev;
-    ev.cfg = cfg;
-    ev.m = &cfg->m;
-    ev.mv.p2 = s_mesh; ev.mv.pc2 = s_mesh + n; ev.mv.coef = s_mesh + 2 * n; ev.mv.n = n;
-    ev.mv.p2max = cfg->p2max; ev.mv.pc2max = cfg->pc2max;
-    ev.mv.p2_iso = s_mesh + 3 * n; ev.mv.coef_iso = s_mesh + 3 * n + cfg->n_iso; ev.mv.n_iso = cfg->n_iso;
-    ev.stage = s_stage + warp * kStageDoubles;
-    ev.team_buf = s_team + (size_t)team * parts * 2 * kBufStride;
-    ev.lane = lane; ev.part = part; ev.parts = parts; ev.bar_id = 1 + team; ev.parity = 0;
-    ev.isospin = cfg->sp.isospin;
-    Solver<WarpEval> sv(cfg->m, cfg->sp, ev);
+    Solver<WarpEval> sv(c_model, c_mc.sp, ev);
+    MarchSink sink{rows, xi};
+    scan_line_slice(sv, pt, ti, muq_MeV, xi, n_T, T_MeV, st, 1, sink);
+}
+
+// Dynamic shared memory: mesh [3 n + 2 n_iso] | staging lines [16][32] | scratch lines [16][LW_END] | team buffers [16][2][24] |
+// ints: popped line per team [16], pass parity per warp [16]
+__global__ void __launch_bounds__(32 * kMarchWarps, 1) k_march(const double* __restrict__ g_mesh, MarchArgs a) {
+    const DeviceConfig* cfg = c_mc.cfg;
+    const int n_mesh = 3 * c_mc.n + 2 * c_mc.n_iso;
+    for (int i = threadIdx.x; i < n_mesh; i += blockDim.x) g_smem[i] = g_mesh[i];
+    if (threadIdx.x < 2 * kMarchWarps) mc_ints()[threadIdx.x] = 0;
+    __syncthreads();
+    const int lane = mc_lane();
+    const int parts = c_mc.parts;
+    const int part = mc_part();
+    const SolverParams& sp = c_mc.sp;
     volatile int* slots = a.slots;
     volatile unsigned long long* done = a.counters + 2;
     for (;;) {
@@ -264,15 +377,15 @@ __global__ void __launch_bounds__(32 * kMarchWarps, 1) k_march(const DeviceConfi
                 __threadfence();
             }
             line = __shfl_sync(0xffffffffu, line, 0);
-            if (parts > 1 && lane == 0) s_line[team] = line;
+            if (parts > 1 && lane == 0) mc_ints()[mc_team()] = line;
         }
         if (parts > 1) {
-            ev.team_sync();
-            line = s_line[team];
-            ev.team_sync();          // everybody has read the slot before the leader can overwrite it
+            mc_team_sync();
+            line = mc_ints()[mc_team()];
+            mc_team_sync();          // everybody has read the slot before the leader can overwrite it
         }
         if (line < 0) break;
-        // ---- run one time slice of the line ----
+        // ---- this line's parameters and parked tracker state ----
         LineState st;
         {
             const LineState* g = a.state + line;
@@ -282,9 +395,121 @@ __global__ void __launch_bounds__(32 * kMarchWarps, 1) k_march(const DeviceConfi
             st.has_prev = __ldcg(&g->has_prev); st.its_hint = __ldcg(&g->its_hint);
         }
         const long long row = a.out_index ? a.out_index[line] : (long long)line;
-        MarchSink sink{&ev, a.records + (long long)PNJL_REC_DOUBLES * a.n_T * row, a.xi[line]};
-        scan_line_slice(sv, &cfg->pt, a.table_idx ? a.table_idx[line] : -1, a.muq_MeV[line], a.xi[line], a.n_T, a.T_MeV, st,
-                        a.quantum, sink);
+        double* rows = a.records + (long long)PNJL_REC_DOUBLES * a.n_T * row;
+        const double muq_MeV = a.muq_MeV[line], xi = a.xi[line];
+        const int ti = a.table_idx ? a.table_idx[line] : -1;
+        const double mu_fm = muq_MeV / c_model.hbarc;
+        const int it_end = (st.it_next + a.quantum < a.n_T) ? st.it_next + a.quantum : a.n_T;
+        // ---- one time slice ----
+        while (st.it_next < it_end) {
+            const int it = st.it_next;
+            bool solved = false;
+#if PNJL_MARCH_LEAN
+            if (st.has_prev) {
+                // PhaseAwareContinuitySeed get_seed (SeedStrategies.jl:795-839) with a previous solution
+                const double Tm = a.T_MeV[it];
+                const double T = Tm / c_model.hbarc;
+                const int cur = current_phase(&cfg->pt, ti, T * 197.327, mu_fm * 197.327);
+                const bool flip = (st.prev_phase == PH_HADRON && cur == PH_QUARK) || (st.prev_phase == PH_QUARK && cur == PH_HADRON);
+                double x[5], xold[5], F[5], p[5];
+                if (flip) seed_const(cur == PH_HADRON ? 0 : 1, x);
+                else copy5(x, st.prev);
+                const int hint = flip ? 0 : st.its_hint;
+                // ---- NLsolve newton_ (Solver::newton), common case only: every state on the integrand's fast path, every closed
+                //      form tame, F finite.  One pass site: kind = Jacobian pass or fused final pass (predicted), a mispredicted
+                //      final pass is followed by a Jacobian pass at the same x ("refresh").  Anything else -> generic cascade.
+                Thermo th;
+                int n_fj = 0, n_th = 0, n_ft = 0, iters = 0, kind = WS_FJ;
+                bool xc = false, fc = false, have_th = false, nonsing = true, first = true, refresh = false, bail = false;
+                double res = 0.0;
+                const double k2max = c_mc.p2max + (xi > 0.0 ? xi * c_mc.pc2max : 0.0);
+                for (;;) {
+                    {
+                        double M[3];
+                        masses_of(c_model, x, M);
+                        const double M2[3] = {M[0] * M[0], M[1] * M[1], M[2] * M[2]};
+                        if (!fast_path_ok(T, mu_fm, x[3], x[4], k2max, M2)) { bail = true; break; }
+                    }
+                    march_pass(kind, T, mu_fm, xi, x[0], x[1], x[2], x[3], x[4]);
+                    if (kind == WS_FJ) {
+                        const int rc = lean_finish_fj(T, mu_fm, xi, x, F, p);
+                        if (rc < 0) { bail = true; break; }
+                        nonsing = rc != 0;
+                        ++n_fj;
+                    } else {
+                        if (!lean_finish_ft(T, mu_fm, xi, x, F, th)) { bail = true; break; }
+                        ++n_ft;
+                    }
+                    if (!all_finite5(F)) { bail = true; break; }
+                    if (refresh) {
+                        refresh = false;          // J(x) is known now; the convergence tests of this x were made on the fused pass
+                        have_th = false;
+                    } else {
+                        if (first) {
+                            first = false;
+                        } else {
+                            double dx = 0.0;
+#pragma unroll
+                            for (int i = 0; i < 5; ++i) dx = fmax(dx, fabs(x[i] - xold[i]));
+                            xc = dx <= sp.xtol;
+                            have_th = kind == WS_FT;
+                        }
+                        res = norm_inf5(F);
+                        fc = res <= sp.ftol;
+                        if (xc || fc || iters >= sp.max_iter) break;
+                        if (kind == WS_FT) { kind = WS_FJ; refresh = true; continue; }
+                    }
+                    ++iters;
+                    if (!nonsing) { bail = true; break; }
+                    if (sp.isospin && x[0] == x[1]) p[1] = p[0];      // keep the exact u<->d symmetry of the equations
+                    double pmax = 0.0;
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) { xold[i] = x[i]; x[i] = x[i] + p[i]; pmax = fmax(pmax, fabs(p[i])); }
+                    const bool by_history = hint > 0 && iters <= hint;
+                    const bool predict = sp.predict_tol > 0.0 && (pmax <= sp.xtol || (by_history ? iters == hint : res <= sp.predict_tol));
+                    kind = predict ? WS_FT : WS_FJ;
+                }
+                if (!bail) {
+                    const double rfin = norm_inf5(F);
+                    // _nlsolve_with_tr_fallback (ImplicitSolver.jl:103-151): the trust-region fallback runs unless the primary solve
+                    // is f-converged with a finite residual <= residual_norm_max and a physical state -> generic cascade
+                    if (fc && finite_d(rfin) && rfin <= sp.residual_norm_max) {
+                        bool have = have_th;
+                        if (!have) {
+                            march_pass(WS_TH, T, mu_fm, xi, x[0], x[1], x[2], x[3], x[4]);
+                            have = lean_finish_th(T, mu_fm, xi, x, th);
+                            ++n_th;
+                        }
+                        bool phys = have && finite_d(x[3]) && finite_d(x[4]) && (-sp.phi_tol <= x[3] && x[3] <= 1 + sp.phi_tol) &&
+                                    (-sp.phi_tol <= x[4] && x[4] <= 1 + sp.phi_tol);
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) phys = phys && finite_d(th.M[i]) && th.M[i] > 0.0;
+                        phys = phys && finite_d(th.omega) && finite_d(th.pressure) && finite_d(th.rho_norm) && finite_d(th.entropy) &&
+                               finite_d(th.energy);
+                        if (phys) {
+                            solved = true;
+                            PointRes r;
+                            copy5(r.x, x);
+                            r.th = th;
+                            r.res = rfin;
+                            r.it = iters;
+                            r.converged = true;
+                            r.status = PNJL_ST_CONVERGED | (flip ? PNJL_ST_PHASE_SWITCH : 0);
+                            double rec[PNJL_REC_DOUBLES];
+                            fill_record(r, T, mu_fm, xi, n_fj, n_th, n_ft, rec);
+                            march_store_row(rec, rows + (long long)PNJL_REC_DOUBLES * it);
+                            // tracker update! (SeedStrategies.jl:851-856) and the history for the next point
+                            copy5(st.prev, x);
+                            st.prev_phase = current_phase(&cfg->pt, ti, Tm, muq_MeV);
+                            st.its_hint = iters;
+                            st.it_next = it + 1;
+                        }
+                    }
+                }
+            }
+#endif
+            if (!solved) march_generic_point(&cfg->pt, ti, muq_MeV, xi, a.n_T, a.T_MeV, st, rows);
+        }
         // ---- park the line (or retire it) ----
         if (part == 0 && lane == 0) {
             if (st.it_next < a.n_T) {

@@ -1,14 +1,19 @@
-// hostsim.cpp — TEST-ONLY host build of the product's math/solver headers.
+// pnjl_analytic_cpu.cpp — TEST / BASELINE INFRASTRUCTURE: a host (g++, OpenMP) build of the product's own math and solver headers.
 //
-// Compiles julia_relaxtime_b200/csrc/pnjl_math.cuh + pnjl_solver.cuh with g++ (no CUDA) and a
-// sequential evaluation policy, so the analytic derivatives and the solve cascade that the CUDA
-// kernels run can be checked against the oracle on a machine without a GPU.  It is NOT part of
-// libpnjl_b200.so and nothing in the product package loads it: the product has no CPU path.
+// Compiles julia_relaxtime_b200/csrc/pnjl_math.cuh + pnjl_solver.cuh + pnjl_lean.cuh without CUDA and with a sequential
+// evaluation policy.  Two uses, both outside the product path:
+//   * tests (tests/hostsim/hostsim.py loads it): the analytic derivatives, the solve cascade, the resumable line march and the
+//     lane-parallel finish that the CUDA kernels run are checked against the AD oracle on a machine without a GPU;
+//   * bench.py's cpu_baseline leg: the "analytic-Jacobian CPU baseline" SURVEY.md §8d names — the same algorithm as the GPU
+//     kernel (closed-form Jacobian, isospin shortcut, fused final pass) on all host cores, next to the AD oracle that mirrors
+//     the reference's ForwardDiff arithmetic.
+// It is NOT part of libpnjl_b200.so and nothing in the package julia_relaxtime_b200/ loads it: the product has no CPU path.
 #include <cstdint>
 #include <cstring>
 #include <vector>
 
-#include "../../julia_relaxtime_b200/csrc/pnjl_solver.cuh"
+#include "../julia_relaxtime_b200/csrc/pnjl_solver.cuh"
+#include "../julia_relaxtime_b200/csrc/pnjl_lean.cuh"
 
 using namespace pnjl;
 
@@ -114,6 +119,59 @@ void hostsim_fj(const pnjl_config* c, const double* x, double T, double mu, doub
     HostMesh mesh = mesh_of(c);
     HostEval ev{&m, &mesh, c->isospin_symmetric};
     ev.fj(T, mu, xi, x, F, J);
+}
+
+// The lane-parallel finish + elimination of the line-march kernel (csrc/pnjl_lean.cuh), emulated lane by lane: phases run for
+// all 32 lanes one after the other, as the __syncwarp()s order them on the GPU.  out: F[5], p[5] (Newton direction), ok.
+int hostsim_lean_fj_step(const pnjl_config* c, const double* x, double T, double mu, double xi, double* F, double* pdir) {
+    Model m = model_of(c);
+    HostMesh mesh = mesh_of(c);
+    HostEval ev{&m, &mesh, c->isospin_symmetric};
+    PointCtx ctx;
+    make_ctx(m, T, mu, xi, x, ctx);
+    double W[LW_END] = {0};
+    double acc[kFJAcc];
+    const bool fast = fj_partial(m, c->isospin_symmetric != 0, ctx, x, ev.view(), 0, 1, acc);
+    for (int i = 0; i < kFJAcc; ++i) W[LW_S + i] = acc[i];
+    LeanConst k;
+    lean_consts(m, ctx.T, ctx.invT, k);
+    // phase A
+    for (int lane = 0; lane < 32; ++lane) {
+        if (lane < 3) { if (!lean_flavour_fj(lane, k, ctx.M[lane], ctx.M2[lane], fast, W)) return -1; }
+        else if (lane < 12) lean_dtable((lane - 3) / 3, (lane - 3) % 3, k, x, W);
+        if (lane == 0) {
+            if (!polyakov_tame(x[3], x[4])) return -2;
+            UTerms u;
+            polyakov_eval<true, false>(m, ctx.T, ctx.invT, x[3], x[4], u);
+            W[LW_U + 0] = u.U_P; W[LW_U + 1] = u.U_Pb; W[LW_U + 2] = u.U_PP; W[LW_U + 3] = u.U_PPb; W[LW_U + 4] = u.U_PbPb;
+            for (int q = 0; q < 5; ++q) W[LW_X + q] = x[q];
+        }
+    }
+    // phase B
+    double a[32] = {0};
+    for (int lane = 0; lane < 30; ++lane) a[lane] = lean_aug_entry(lane / 6, lane % 6, k, W, ACC_GP, ACC_GPB);
+    for (int lane = 0; lane < 30; ++lane) W[LW_AUG + lane] = a[lane];
+    for (int i = 0; i < 5; ++i) F[i] = W[LW_AUG + 6 * i + 5];
+    // phase C
+    bool ok = true;
+    for (int step = 0; step < 5; ++step) {
+        double nxt[32], inv = 0;
+        for (int lane = 0; lane < 30; ++lane) { bool okl = ok; nxt[lane] = lean_lu_step(step, lane / 6, lane % 6, W, a[lane], inv, okl); if (lane == 0) ok = okl; }
+        for (int lane = 0; lane < 30; ++lane) { a[lane] = nxt[lane]; W[LW_AUG + lane] = nxt[lane]; }
+        W[LW_INV + step] = inv;
+    }
+    double y[5];
+    lean_backsub(W, y);
+    for (int i = 0; i < 5; ++i) pdir[i] = -y[i];
+    return ok ? 1 : 0;
+}
+
+// The redundant-per-lane version of the same step (finish_fj + lu_solve5_regs), for comparison.
+int hostsim_fj_step(const pnjl_config* c, const double* x, double T, double mu, double xi, double* F, double* pdir) {
+    Model m = model_of(c);
+    HostMesh mesh = mesh_of(c);
+    HostEval ev{&m, &mesh, c->isospin_symmetric};
+    return ev.fj_step(T, mu, xi, x, F, pdir) ? 1 : 0;
 }
 
 void hostsim_thermo(const pnjl_config* c, const double* x, double T, double mu, double xi, double* out17) {

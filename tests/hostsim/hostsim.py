@@ -1,4 +1,4 @@
-"""Loader of the TEST-ONLY host build of the product's math/solver headers (see hostsim.cpp)."""
+"""Loader of the test-only host build of the product's math/solver headers (oracle/pnjl_analytic_cpu.cpp)."""
 import ctypes as C
 import os
 import subprocess
@@ -9,15 +9,16 @@ from julia_relaxtime_b200 import _abi
 from julia_relaxtime_b200.constants import DEFAULT
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = os.path.join(HERE, "hostsim.cpp")
-LIB = os.path.join(HERE, "_hostsim.so")
+SRC = os.path.join(HERE, "..", "..", "oracle", "pnjl_analytic_cpu.cpp")
+LIB = os.path.join(HERE, "..", "..", "oracle", "_build", "libpnjl_analytic_cpu.so")
 CSRC = os.path.join(HERE, "..", "..", "julia_relaxtime_b200", "csrc")
 
 
 def build():
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("pnjl_math.cuh", "pnjl_solver.cuh")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("pnjl_math.cuh", "pnjl_solver.cuh", "pnjl_lean.cuh")]
     if os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps):
         return LIB
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
     subprocess.check_call(["g++", "-std=c++17", "-O2", "-fno-fast-math", "-fopenmp", "-fPIC", "-shared",
                            "-Wno-unknown-pragmas", "-o", LIB, SRC])
     return LIB
@@ -46,6 +47,17 @@ class HostSim:
         self.lib.hostsim_fj(C.byref(self.cfg), _abi.dptr(x), C.c_double(T), C.c_double(mu), C.c_double(xi),
                             _abi.dptr(F), _abi.dptr(J))
         return F, J
+
+    def fj_step(self, x, T, mu, xi, lean=False):
+        """F and the Newton direction p = -J^{-1} F at x: redundant-per-lane version, or the lane-parallel one emulated lane by
+        lane (csrc/pnjl_lean.cuh).  Returns (F, p, rc) with rc 1 ok, 0 singular, < 0 not on the lean path."""
+        x = _abi.as_f64(x)
+        F = np.zeros(5)
+        p = np.zeros(5)
+        fn = self.lib.hostsim_lean_fj_step if lean else self.lib.hostsim_fj_step
+        fn.restype = C.c_int
+        rc = fn(C.byref(self.cfg), _abi.dptr(x), C.c_double(T), C.c_double(mu), C.c_double(xi), _abi.dptr(F), _abi.dptr(p))
+        return F, p, rc
 
     def thermo(self, x, T, mu, xi):
         x = _abi.as_f64(x)

@@ -29,13 +29,13 @@ def _oracle_compute(grid):
     return compute
 
 
-def _worker(rank, world, port, out_path):
+def _worker(rank, world, port, out_path, layout):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         grid = build_grid([0.0, 0.2], np.linspace(0, 1200, 5), np.linspace(100, 200, 6))
-        full, local = scan_sharded(grid, 2, 5, _oracle_compute(grid), rank, world)
+        full, local = scan_sharded(grid, 2, 5, _oracle_compute(grid), rank, world, layout=layout)
         if rank == 0:
             np.save(out_path, full.numpy())
         else:
@@ -45,12 +45,16 @@ def _worker(rank, world, port, out_path):
         dist.destroy_process_group()
 
 
-def test_two_rank_scan_equals_single_process(tmp_path):
+import pytest
+
+
+@pytest.mark.parametrize("layout", ["interleaved", "slab"])
+def test_two_rank_scan_equals_single_process(tmp_path, layout):
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     out = str(tmp_path / "gathered.npy")
-    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, out, layout), nprocs=2, join=True)
     got = np.load(out)
     grid = build_grid([0.0, 0.2], np.linspace(0, 1200, 5), np.linspace(100, 200, 6))
     ref = _oracle_compute(grid)(np.arange(grid.n_lines)).numpy()

@@ -170,8 +170,15 @@ def test_slab_partition():
         assert b[0][0] == 0 and b[-1][1] == n_mu and all(b[i][1] == b[i + 1][0] for i in range(w - 1))
         sizes = [hi - lo for lo, hi in b]
         assert max(sizes) - min(sizes) <= 1
-        allidx = np.concatenate([rank_line_indices(3, n_mu, r, w) for r in range(w)])
-        assert sorted(allidx.tolist()) == list(range(3 * n_mu))
+        for layout in ("interleaved", "slab"):
+            per_rank = [rank_line_indices(3, n_mu, r, w, layout) for r in range(w)]
+            assert sorted(np.concatenate(per_rank).tolist()) == list(range(3 * n_mu))
+            assert max(len(p) for p in per_rank) - min(len(p) for p in per_rank) <= 3
+        # interleaved: every rank gets a sample of the whole mu range (what balances the expensive 280-360 MeV band)
+        if n_mu >= 4 * w:
+            for r in range(w):
+                mu_idx = rank_line_indices(1, n_mu, r, w, "interleaved")
+                assert mu_idx.min() < w and mu_idx.max() >= n_mu - w
 
 
 # ---- the product's math/solver headers, built for the host (tests/hostsim), against the oracle -------------
@@ -345,3 +352,29 @@ def test_out_buffer_validation():
     ro.setflags(write=False)
     with pytest.raises(ValueError):
         A.check_records(ro, 4 * 3 * A.REC_DOUBLES)
+
+
+def test_lane_parallel_finish_and_elimination_match_redundant_version(sim_and_oracle):
+    """csrc/pnjl_lean.cuh (what the line-march kernel runs after every Jacobian pass: one matrix entry per lane, elimination
+    through a shared scratch line), emulated lane by lane on the CPU, against finish_fj + lu_solve5_regs: same F, same Newton
+    direction — on physical states, near-singular Jacobians (close to the CEP) and states with phi_u != phi_d."""
+    hs, o = sim_and_oracle
+    rng = np.random.default_rng(17)
+    worst_F = worst_p = 0.0
+    n_done = 0
+    for trial in range(300):
+        T, mu, xi = rng.uniform(40, 350) / HBARC, rng.uniform(0, 400) / HBARC, rng.choice([0.0, -0.4, 0.3, 0.8])
+        if trial < 20:
+            T, mu, xi = (130.94 + rng.normal(0, 0.3)) / HBARC, (291.21 + rng.normal(0, 0.3)) / HBARC, 0.0     # around the CEP
+        u = rng.uniform(-2.0, -0.05)
+        x = np.array([u, u if trial % 3 else rng.uniform(-2.0, -0.05), rng.uniform(-2.3, -0.4), rng.uniform(0.0, 0.98),
+                      rng.uniform(0.0, 0.98)])
+        F0, p0, rc0 = hs.fj_step(x, T, mu, xi)
+        F1, p1, rc1 = hs.fj_step(x, T, mu, xi, lean=True)
+        if rc1 < 0:
+            continue
+        n_done += 1
+        assert rc0 == rc1 == 1
+        worst_F = max(worst_F, np.abs(F0 - F1).max() / (np.abs(F0).max() + 1e-3))
+        worst_p = max(worst_p, np.abs(p0 - p1).max() / (np.abs(p0).max() + 1e-12))
+    assert n_done > 250 and worst_F <= 1e-14 and worst_p <= 1e-9, (n_done, worst_F, worst_p)
