@@ -124,48 +124,52 @@ def build_lines(w):
 # CPU arm: the oracle (C++ restatement of the reference algorithm, nested-dual AD like the reference) on all
 # host cores, on a bounded sample of the same workload.
 # ------------------------------------------------------------------------------------------------------------
-def _lines_sample(workload, n_lines):
-    """`n_lines` complete lines of the workload grid, stratified over (xi, mu) exactly like a GPU rank's share of an
-    interleaved n-rank run would be (every xi, mu spread over the whole range)."""
+def _lines_sample(workload, n_lines, offset=0):
+    """`n_lines` complete lines of the workload grid spread over (xi, mu) by a golden-ratio sequence (every xi, mu over
+    the whole range — what one rank of an interleaved multi-GPU run carries)."""
     xis, mus, T, p, t = build_lines(workload)
     n_mu = len(mus)
     total = len(xis) * n_mu
-    li = (np.arange(n_lines) * (total / float(n_lines)) + 0.5 * total / float(n_lines)).astype(int) % total
+    li = ((((np.arange(n_lines) + offset) * 0.6180339887498949) % 1.0) * total).astype(int) % total
     return li, np.array([xis[i // n_mu] for i in li], dtype=float), mus[li % n_mu], T
 
 
-def cpu_sample(workload, target_seconds=12.0, threads=None, engine="ad"):
-    """The path on the host CPU, SAME CONFIG as the GPU arm: complete lines of the workload grid marched over the complete T
-    grid (MultiSeed bootstrap at T[0], then PhaseAwareContinuitySeed — run_gap_transport_scan.jl:417-443), `threads` lines at a
-    time in parallel, as many as fit the time budget.
-      engine "ad"        oracle/pnjl_oracle.cpp: the reference's arithmetic (Omega once, F and J by nested dual numbers like
-                         ForwardDiff inside NLsolve's autodiff=:forward)
+def cpu_sample(workload, target_seconds=12.0, threads=None, engine="ad", step=0):
+    """The path on the host CPU, SAME CONFIG as the GPU arm: lines of the workload grid marched over the true T grid with the
+    reference's seeding (MultiSeed at T[0], then PhaseAwareContinuitySeed — run_gap_transport_scan.jl:417-443), `threads`
+    lines in parallel.
       engine "analytic"  oracle/pnjl_analytic_cpu.cpp: the GPU kernel's own algorithm (closed-form Jacobian, isospin shortcut,
-                         fused final pass) compiled for the host — the analytic-Jacobian CPU baseline of SURVEY.md §8d"""
+                         fused final pass) compiled for the host — the analytic-Jacobian CPU baseline of SURVEY.md §8d.  Fast
+                         enough to march complete lines.
+      engine "ad"        oracle/pnjl_oracle.cpp: the reference's arithmetic (Omega once, F and J by nested dual numbers like
+                         ForwardDiff inside NLsolve's autodiff=:forward).  A complete 1024-point line takes ~35 s per core, so a
+                         step marches one WINDOW of the T grid (a third of it; window `step` mod 3, so successive steps cover
+                         the whole range) started from the TRUE previous solution of each line (computed by the analytic engine,
+                         not timed): the seeds, and therefore the evaluations per point, are those of the complete line.  The
+                         first window starts at T[0] with the MultiSeed bootstrap like a line does."""
     from oracle.oracle import Oracle, load_phase_tables
+    from tests.hostsim.hostsim import HostSim
     kind, xis, n_mu, _, n_T, _, p, t = WORKLOADS[workload]
     xis, mus, T, p, t = build_lines(workload)
     threads = threads or len(os.sched_getaffinity(0))
     o = Oracle(p_num=p, t_num=t, max_iter=MAX_ITER, n_threads=threads)
     gdir = os.path.join(ROOT, "julia_relaxtime_b200", "data")
     tables, index = load_phase_tables(os.path.join(gdir, "boundary.csv"), os.path.join(gdir, "cep.csv"), xis)
-    hs = None
-    if engine == "analytic":
-        from tests.hostsim.hostsim import HostSim
-        os.environ["OMP_NUM_THREADS"] = str(threads)
-        hs = HostSim(o.p_nodes, o.p_w, o.c_nodes, o.c_w, max_iter=MAX_ITER)
-    rng = np.random.default_rng(0)
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    hs = HostSim(o.p_nodes, o.p_w, o.c_nodes, o.c_w, max_iter=MAX_ITER)
+    rng = np.random.default_rng(step)
+    conv_of = lambda rec: int(((rec[:, 21].astype(np.int64) & 1) != 0).sum())
+    evals_of = lambda rec: int(rec[:, 22].sum() + rec[:, 30].sum())          # Jacobian passes + fused final passes
     if kind == "points":
         def run(n):
             Tm = rng.choice(T, n); mm = rng.choice(mus, n); xx = rng.choice(xis, n)
             t0 = time.perf_counter()
-            if hs is None:
+            if engine == "ad":
                 r = o.solve_points(Tm / HBARC, mm / HBARC, xx, "multi")
                 conv, nfj = int(r.converged.sum()), int(r.n_fj.sum())
             else:
                 rec = hs.solve_points(Tm / HBARC, mm / HBARC, xx)
-                conv = int(((rec[:, 21].astype(np.int64) & 1) != 0).sum())
-                nfj = int(rec[:, 22].sum() + rec[:, 30].sum())
+                conv, nfj = conv_of(rec), evals_of(rec)
             return time.perf_counter() - t0, conv, nfj
         dt, _, _ = run(threads)
         n = int(max(threads, min(400000, threads * target_seconds / max(dt, 1e-3))))
@@ -173,28 +177,61 @@ def cpu_sample(workload, target_seconds=12.0, threads=None, engine="ad"):
         return dict(points=n, seconds=dt, converged=conv, n_fj=nfj, threads=threads, engine=engine,
                     sample="%d random grid points of the %s grid, MultiSeed each" % (n, workload))
 
-    def run(n_lines, n_t):
-        li, lx, lm, _ = _lines_sample(workload, n_lines)
-        tidx = np.array([index[x] for x in lx], dtype=np.int32)
-        t0 = time.perf_counter()
-        if hs is None:
-            r = o.scan_lines(lm, lx, T[:n_t], tables, tidx)
-            conv, nfj, tot = int(r.converged.sum()), int(r.n_fj.sum()), r.n
-        else:
+    if engine == "analytic":
+        def run(n_lines, n_t):
+            li, lx, lm, _ = _lines_sample(workload, n_lines, offset=step * n_lines)
+            tidx = np.array([index[x] for x in lx], dtype=np.int32)
+            t0 = time.perf_counter()
             rec = hs.scan_lines(lm, lx, T[:n_t], tables, tidx).reshape(-1, 32)
-            conv = int(((rec[:, 21].astype(np.int64) & 1) != 0).sum())
-            nfj, tot = int(rec[:, 22].sum() + rec[:, 30].sum()), rec.shape[0]
-        return time.perf_counter() - t0, tot, conv, nfj
+            return time.perf_counter() - t0, rec.shape[0], conv_of(rec), evals_of(rec)
+        dt, tot, _, _ = run(threads, min(n_T, 64))
+        per_line = dt * n_T / min(n_T, 64) / threads
+        n_lines = int(max(threads, min(4096, threads * round(target_seconds / max(per_line * threads, 1e-3)))))
+        dt, tot, conv, nfj = run(n_lines, n_T)
+        return dict(points=tot, seconds=dt, converged=conv, n_fj=nfj, threads=threads, engine=engine,
+                    sample="%d complete lines (spread over xi and mu) x all %d T of the %s grid" % (n_lines, n_T, workload))
 
-    # calibrate on a short prefix, then march whole lines: `groups` x `threads` of them
-    n_cal = min(n_T, 48)
-    dt, tot, _, _ = run(threads, n_cal)
-    per_line = dt * n_T / n_cal
-    groups = int(max(1, min(64, round(target_seconds / max(per_line, 1e-3)))))
-    dt, tot, conv, nfj = run(groups * threads, n_T)
+    n_win = 3 if n_T >= 96 else 1
+    wlen = (n_T + n_win - 1) // n_win
+    w0 = (step % n_win) * wlen
+    w1 = min(n_T, w0 + wlen)
+
+    def run(groups, t_lo, t_hi):
+        n_lines = groups * threads
+        li, lx, lm, _ = _lines_sample(workload, n_lines, offset=step * n_lines)
+        tidx = np.array([index[x] for x in lx], dtype=np.int32)
+        init = None
+        if t_lo > 0:     # the true state of every line at T[t_lo - 1] (analytic engine, untimed)
+            pre = hs.scan_lines(lm, lx, T[:t_lo], tables, tidx)
+            init = pre[:, -1, 0:5].copy()
+        t0 = time.perf_counter()
+        r = o.scan_lines(lm, lx, T[t_lo:t_hi], tables, tidx, init_x=init, init_T_MeV=float(T[t_lo - 1]) if t_lo > 0 else 0.0)
+        return time.perf_counter() - t0, r.n, int(r.converged.sum()), int(r.n_fj.sum())
+
+    dt, tot, _, _ = run(1, w0, min(w1, w0 + 24))
+    per_group = dt * (w1 - w0) / max(1, min(w1, w0 + 24) - w0)
+    groups = int(max(1, min(16, round(target_seconds / max(per_group, 1e-3)))))
+    dt, tot, conv, nfj = run(groups, w0, w1)
     return dict(points=tot, seconds=dt, converged=conv, n_fj=nfj, threads=threads, engine=engine,
-                sample="%d complete lines (stratified over xi and mu) x all %d T of the %s grid, %d lines at a time "
-                       "(MultiSeed bootstrap at T[0], then PhaseAwareContinuitySeed)" % (groups * threads, n_T, workload, threads))
+                sample="%d lines (spread over xi and mu) x the T window [%d, %d) of the %d-point T grid of %s (%.1f-%.1f MeV), "
+                       "%d lines at a time, each line started from its true previous solution%s" % (
+                           groups * threads, w0, w1, n_T, workload, T[w0], T[w1 - 1], threads,
+                           " (window 0: MultiSeed bootstrap at T[0])" if w0 == 0 else ""))
+
+
+def config_of(w, world, scaling, layout, extra=None):
+    """The `config` object both arms print (same keys, so that the driver can tell they ran the same workload)."""
+    kind, xis, n_mu, mr, n_T, tr, p, t = WORKLOADS[w]
+    c = {"workload": w, "description": DESCR[w], "points": int(len(xis) * n_mu * n_T), "lines": int(len(xis) * n_mu) if kind == "lines" else 0,
+         "n_T": int(n_T), "n_mu": int(n_mu), "xi": list(xis), "nodes": "%dx%d" % (p, t), "max_iter": MAX_ITER,
+         "seeding": ("MultiSeed at T[0] of every (xi, mu) line, then PhaseAwareContinuitySeed along T" if kind == "lines"
+                     else "MultiSeed at every point"),
+         "nodes_note": "64- and 16-point Gauss-Legendre rules by Newton iteration on the Legendre recurrence (the reference's "
+                       "FastGaussQuadrature switches to asymptotic formulas above n = 60; no full-precision golden output exists "
+                       "at this mesh, SURVEY.md §8c) — results at this mesh are pinned to the oracle, not to Julia output"}
+    if extra:
+        c.update(extra)
+    return c
 
 
 def run_reference(args):
@@ -203,21 +240,23 @@ def run_reference(args):
     if rank != 0:
         return
     w = args.workload
-    for _ in range(args.warmup):
-        cpu_sample(w, target_seconds=2.0)
-    tot_pts = tot_s = 0.0
+    for k in range(args.warmup):
+        cpu_sample(w, target_seconds=1.0, step=k)
+    tot_pts = tot_s = tot_ev = tot_n = 0.0
     last = None
-    for _ in range(args.steps):
-        last = cpu_sample(w, target_seconds=args.cpu_seconds)
+    for k in range(args.steps):
+        last = cpu_sample(w, target_seconds=args.cpu_seconds, step=k)
         tot_pts += last["converged"]
         tot_s += last["seconds"]
+        tot_ev += last["n_fj"]
+        tot_n += last["points"]
     val = tot_pts / tot_s
     out = {"impl": "reference", "metric": "converged PNJL gap points/sec", "value": val, "unit": "points/s",
            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps,
            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": w, "description": DESCR[w]},
+           "config": config_of(w, 1, args.scaling, args.layout),
            "cpu_baseline": {"value": val, "unit": "points/s", "cores": last["threads"], "kind": "port",
-                            "sample": last["sample"],
+                            "sample": last["sample"], "evals_per_point": tot_ev / max(1.0, tot_n),
                             "note": "C++ restatement of the reference algorithm (nested-dual AD Jacobian like "
                                     "ForwardDiff, NLsolve-faithful Newton/dogleg), OpenMP over lines; the Julia "
                                     "reference itself is single-threaded and cannot run in this image"},
@@ -239,10 +278,13 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-weak", action="store_true", help="skip the secondary weak-scaling measurement at N > 1")
     ap.add_argument("--gather", choices=("peer", "nccl"), default="peer",
                     help="multi-GPU result collection: peer = every rank's kernel stores its records straight into rank 0's buffer "
                          "over NVLink (CUDA IPC; falls back to nccl if the mapping cannot be set up); nccl = dist.gather after the kernel")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"])
+    ap.add_argument("--layout", default="interleaved", choices=["interleaved", "slab"],
+                    help="how the mu axis is dealt out over the ranks (results identical)")
     ap.add_argument("--no-flush", action="store_true", help="skip the L2 flush between steps (ncu traffic captures only)")
     ap.add_argument("--n-mu", type=int, default=0, help="override the mu density (profiling runs only; recorded in config)")
     ap.add_argument("--n-t", type=int, default=0, help="override the T density (profiling runs only; recorded in config)")
@@ -260,8 +302,7 @@ def main():
     import torch.distributed as dist
     from julia_relaxtime_b200 import _abi as A
     from julia_relaxtime_b200._lib import Engine
-    from julia_relaxtime_b200.boundary import default_tables
-    from julia_relaxtime_b200.distributed import PeerRecords, rank_line_indices, scan_sharded, scan_sharded_peer
+    from julia_relaxtime_b200.distributed import PeerRecords, rank_line_indices, scan_sharded
     from julia_relaxtime_b200.scan import build_grid
 
     rank = int(os.environ.get("RANK", "0"))
@@ -276,79 +317,16 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     w = args.workload
-    if args.scaling == "weak" and world > 1:
-        k_, xs_, nm_, mr_, nt_, tr_, pp_, tt_ = WORKLOADS[w]
-        WORKLOADS[w] = (k_, xs_, nm_ * world, mr_, nt_, tr_, pp_, tt_)
-        DESCR[w] += " [weak scaling: mu axis refined to %d points, one %d-mu slab per GPU]" % (nm_ * world, nm_)
-    kind, xis, n_mu, _, n_T, _, p, t = WORKLOADS[w]
-    xis, mus, T, p, t = build_lines(w)
+    kind = WORKLOADS[w][0]
+    base_workload = WORKLOADS[w]
+    p, t = base_workload[6], base_workload[7]
     n_nodes = p * t
-    lanes = args.lanes
-    if lanes == 0 and all(x == 0.0 for x in xis):
-        # all-isotropic workload: a pass sweeps p_num nodes (isotropic collapse), so use the layout the library itself
-        # picks for such batches in its host entry points (the device entry points cannot look at xi)
-        lanes = 8 if p <= 96 else (16 if p <= 256 else 32)
-    eng = Engine(p_num=p, t_num=t, max_iter=MAX_ITER, device=local_rank, lanes_per_solve=lanes)
+    all_iso = all(x == 0.0 for x in base_workload[1])
+    eng = Engine(p_num=p, t_num=t, max_iter=MAX_ITER, device=local_rank, lanes_per_solve=args.lanes)
+    if all_iso and args.lanes == 0:
+        eng.set_option("isotropic_batch", 1)     # the device entry points cannot look at xi: size the teams for p_num nodes
     stream = torch.cuda.current_stream().cuda_stream
-
     peak_burst, peak_sus = eng.measure_fp64_peak(1.0)
-
-    if kind == "lines":
-        grid = build_grid(xis, 3.0 * mus, T)          # muB = 3 muq
-        eng.set_boundaries(grid.tables)
-        mine = rank_line_indices(len(xis), n_mu, rank, world)
-        d_muq = torch.as_tensor(grid.muq_MeV[mine], device=dev)
-        d_xi = torch.as_tensor(grid.xi[mine], device=dev)
-        d_tidx = torch.as_tensor(grid.table_idx[mine], device=dev)
-        d_T = torch.as_tensor(grid.T_MeV, device=dev)
-        d_rec = torch.empty((len(mine), n_T, A.REC_DOUBLES), dtype=torch.float64, device=dev)
-        n_total = grid.n_lines * n_T
-
-        def compute(_lines):
-            eng.scan_lines_device(d_muq, d_xi, d_tidx, d_T, d_rec, stream)
-            return d_rec
-
-        peer = None
-        if world > 1 and args.gather == "peer":
-            try:
-                peer = PeerRecords(grid.n_lines, n_T, rank, world, dev)
-                peer_inputs = dict(muq=d_muq, xi=d_xi, tidx=d_tidx, T=d_T,
-                                   out_index=torch.as_tensor(mine.astype(np.int64), device=dev))
-            except Exception as exc:                                     # noqa: BLE001 - any failure -> NCCL gather
-                if rank == 0:
-                    print("peer gather unavailable (%s); using dist.gather" % exc, file=sys.stderr)
-                peer = None
-
-        def step():
-            if peer is not None:
-                full, _ = scan_sharded_peer(eng, grid, len(xis), n_mu, peer, rank, world, dev, stream, peer_inputs)
-                return full
-            full, _ = scan_sharded(grid, len(xis), n_mu, compute, rank, world)
-            return full
-    else:
-        gx, gm, gT = np.meshgrid(np.asarray(xis), mus, T, indexing="ij")
-        allp = np.stack([gT.ravel() / HBARC, gm.ravel() / HBARC, gx.ravel()], axis=0)
-        n_total = allp.shape[1]
-        lo = rank * n_total // world
-        hi = (rank + 1) * n_total // world
-        d_T = torch.as_tensor(allp[0, lo:hi].copy(), device=dev)
-        d_mu = torch.as_tensor(allp[1, lo:hi].copy(), device=dev)
-        d_xi = torch.as_tensor(allp[2, lo:hi].copy(), device=dev)
-        d_rec = torch.empty((hi - lo, A.REC_DOUBLES), dtype=torch.float64, device=dev)
-        gather_bufs = None
-        if world > 1 and rank == 0:
-            gather_bufs = [torch.empty(((r + 1) * n_total // world - r * n_total // world, A.REC_DOUBLES),
-                                       dtype=torch.float64, device=dev) for r in range(world)]
-
-        def step():
-            eng.solve_points_device(d_T, d_mu, d_xi, d_rec, A.SEED_MULTI, None, 6, stream)
-            if world > 1:
-                if n_total % world == 0:
-                    dist.gather(d_rec, gather_bufs if rank == 0 else None, dst=0)
-                else:
-                    raise SystemExit("points workload must divide evenly over ranks")
-            return d_rec
-
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float64, device=dev)   # 512 MB > 126 MB L2
 
     def barrier():
@@ -357,61 +335,169 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    step_ms, kern_ms = [], []
-    for _ in range(args.steps):
-        if not args.no_flush:
-            flush.fill_(1.0)                           # L2 flush between timed iterations (not timed)
-        barrier()
-        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        e0.record()
-        if kind == "lines" and peer is not None:
-            # the kernel writes into rank 0's array itself; e1 = this rank's kernel, e2 after the closing barrier
-            eng.scan_lines_device_indexed(d_muq, d_xi, d_tidx, d_T, peer.ptr, peer_inputs["out_index"], stream)
-            e1.record()
-            torch.cuda.synchronize()
-            dist.barrier()
-        elif kind == "lines":
-            compute(None)
-            e1.record()
-            full, _ = scan_sharded(grid, len(xis), n_mu, lambda _l: d_rec, rank, world)
+    def checksum(rec2d):
+        """Order-independent fingerprint of a record array: the 64-bit patterns added with wrap-around."""
+        return rec2d.contiguous().view(torch.int64).sum()
+
+    def run_job(mu_factor, steps, warmup, sample_clocks):
+        """One measurement of the workload with the mu axis refined mu_factor-fold (1 = the BASELINE grid).  Returns a dict."""
+        kind_, xs_, nm_, mr_, nt_, tr_, pp_, tt_ = base_workload
+        WORKLOADS[w] = (kind_, xs_, nm_ * mu_factor, mr_, nt_, tr_, pp_, tt_)
+        xis, mus, T, _, _ = build_lines(w)
+        n_mu, n_T = len(mus), len(T)
+        J = {}
+        peer = None
+        if kind == "lines":
+            grid = build_grid(xis, 3.0 * mus, T)          # muB = 3 muq
+            eng.set_boundaries(grid.tables)
+            mine = rank_line_indices(len(xis), n_mu, rank, world, args.layout)
+            d_muq = torch.as_tensor(grid.muq_MeV[mine], device=dev)
+            d_xi = torch.as_tensor(grid.xi[mine], device=dev)
+            d_tidx = torch.as_tensor(grid.table_idx[mine], device=dev)
+            d_T = torch.as_tensor(grid.T_MeV, device=dev)
+            d_out = torch.as_tensor(mine.astype(np.int64), device=dev)
+            d_rec = torch.empty((len(mine), n_T, A.REC_DOUBLES), dtype=torch.float64, device=dev)
+            n_total = grid.n_lines * n_T
+
+            def compute(_lines=None):
+                eng.scan_lines_device(d_muq, d_xi, d_tidx, d_T, d_rec, stream)
+                return d_rec
+
+            if world > 1 and args.gather == "peer":
+                try:
+                    peer = PeerRecords(grid.n_lines, n_T, rank, world, dev)
+                except Exception as exc:                                     # noqa: BLE001 - any failure -> NCCL gather
+                    if rank == 0:
+                        print("peer gather unavailable (%s); using dist.gather" % exc, file=sys.stderr)
+                    peer = None
+            full_holder = [None]
+
+            def timed_step(e1):
+                if peer is not None:
+                    # the kernel writes into rank 0's array itself; e1 = this rank's kernel, then only the closing barrier
+                    eng.scan_lines_device_indexed(d_muq, d_xi, d_tidx, d_T, peer.ptr, d_out, stream)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    if world > 1:
+                        dist.barrier()
+                else:
+                    compute()
+                    e1.record()
+                    if world > 1:
+                        full_holder[0], _ = scan_sharded(grid, len(xis), n_mu, lambda _l: d_rec, rank, world, layout=args.layout)
         else:
-            eng.solve_points_device(d_T, d_mu, d_xi, d_rec, A.SEED_MULTI, None, 6, stream)
-            e1.record()
-            if world > 1:
-                dist.gather(d_rec, gather_bufs if rank == 0 else None, dst=0)
-        e2.record()
+            gx, gm, gT = np.meshgrid(np.asarray(xis), mus, T, indexing="ij")
+            allp = np.stack([gT.ravel() / HBARC, gm.ravel() / HBARC, gx.ravel()], axis=0)
+            n_total = allp.shape[1]
+            if n_total % world:
+                raise SystemExit("points workload must divide evenly over ranks")
+            idx = np.arange(rank, n_total, world)              # interleaved over the ranks like the lines
+            d_T = torch.as_tensor(allp[0, idx].copy(), device=dev)
+            d_mu = torch.as_tensor(allp[1, idx].copy(), device=dev)
+            d_xi = torch.as_tensor(allp[2, idx].copy(), device=dev)
+            d_rec = torch.empty((len(idx), A.REC_DOUBLES), dtype=torch.float64, device=dev)
+            gather_bufs = [torch.empty_like(d_rec) for _ in range(world)] if (world > 1 and rank == 0) else None
+            J["host_inputs"] = (allp, idx)
+
+            def compute(_lines=None):
+                eng.solve_points_device(d_T, d_mu, d_xi, d_rec, A.SEED_MULTI, None, 6, stream)
+                return d_rec
+
+            def timed_step(e1):
+                compute()
+                e1.record()
+                if world > 1:
+                    dist.gather(d_rec, gather_bufs if rank == 0 else None, dst=0)
+
+        for _ in range(warmup):
+            timed_step(torch.cuda.Event(enable_timing=True))
         barrier()
-        step_ms.append(e0.elapsed_time(e2))
-        kern_ms.append(e0.elapsed_time(e1))
-    clocks = sampler.stop() if rank == 0 else None
-    tot = torch.tensor([sum(step_ms), sum(kern_ms)], dtype=torch.float64, device=dev)
-    # converged points / evaluation counts of this rank's slab (identical every step; counted once)
-    if kind == "lines" and peer is not None:
-        compute(None)                    # untimed: this rank's slab once more into its local buffer, for the counts below
-        torch.cuda.synchronize()
-    r2 = d_rec.reshape(-1, A.REC_DOUBLES)
-    conv = ((r2[:, A.REC_STATUS].to(torch.int64) & 1) != 0).sum().to(torch.float64)
-    # quadrature nodes a pass actually sweeps at each point: p_num when xi == 0 (isotropic collapse: the cos(theta) sum
-    # is pre-summed into the weights), p_num * t_num otherwise — the algorithmic FLOP count follows the evaluated nodes
-    nodes_pt = torch.where(r2[:, A.REC_XI] == 0.0, float(p if eng.isotropic_collapse else n_nodes), float(n_nodes))
-    unit = lambda col: (r2[:, col] * nodes_pt).sum()
-    cnt = torch.stack([conv, r2[:, A.REC_NEVAL].sum(), r2[:, A.REC_NTHERMO].sum(), r2[:, A.REC_NFUSED].sum(),
-                       unit(A.REC_NEVAL), unit(A.REC_NTHERMO), unit(A.REC_NFUSED)])
-    if world > 1:
-        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    total_ms, kernel_ms = float(tot[0]), float(tot[1])
-    n_conv, n_fj, n_th, n_ft, u_fj, u_th, u_ft = (float(v) for v in cnt)
+        sampler = ClockSampler(local_rank)
+        if rank == 0 and sample_clocks:
+            sampler.start()
+        step_ms, kern_ms = [], []
+        for _ in range(steps):
+            if not args.no_flush:
+                flush.fill_(1.0)                           # L2 flush between timed iterations (not timed)
+            barrier()
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record()
+            timed_step(e1)
+            e2.record()
+            barrier()
+            step_ms.append(e0.elapsed_time(e2))
+            kern_ms.append(e0.elapsed_time(e1))
+        J["clocks"] = sampler.stop() if (rank == 0 and sample_clocks) else None
+        # ---- counts of this rank's share (identical every step; counted once, outside the timed region) ----
+        if kind == "lines" and peer is not None:
+            compute()                    # this rank's lines once more into its local buffer
+            torch.cuda.synchronize()
+        r2 = d_rec.reshape(-1, A.REC_DOUBLES)
+        conv = ((r2[:, A.REC_STATUS].to(torch.int64) & 1) != 0).sum().to(torch.float64)
+        # quadrature nodes a pass actually sweeps at each point: p_num when xi == 0 (isotropic collapse: the cos(theta) sum
+        # is pre-summed into the weights), p_num * t_num otherwise — the algorithmic FLOP count follows the evaluated nodes
+        nodes_pt = torch.where(r2[:, A.REC_XI] == 0.0, float(p if eng.isotropic_collapse else n_nodes), float(n_nodes))
+        unit = lambda col: (r2[:, col] * nodes_pt).sum()
+        cnt = torch.stack([conv, r2[:, A.REC_NEVAL].sum(), r2[:, A.REC_NTHERMO].sum(), r2[:, A.REC_NFUSED].sum(),
+                           unit(A.REC_NEVAL), unit(A.REC_NTHERMO), unit(A.REC_NFUSED)])
+        tot = torch.tensor([sum(step_ms), sum(kern_ms)], dtype=torch.float64, device=dev)
+        mine_ms = torch.tensor([sum(kern_ms) / max(1, steps)], dtype=torch.float64, device=dev)
+        local_sum = checksum(r2)
+        all_ms = [torch.zeros_like(mine_ms) for _ in range(world)]
+        # ---- the gathered array on rank 0 against the per-rank results ----
+        verified, equal_nccl = None, None
+        if world > 1:
+            dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+            sums = torch.stack([conv.to(torch.int64), local_sum])
+            dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+            dist.all_gather(all_ms, mine_ms)
+            if kind == "lines":
+                gathered = peer.tensor if peer is not None else full_holder[0]
+                if rank == 0:
+                    g2 = gathered.reshape(-1, A.REC_DOUBLES)
+                    gconv = ((g2[:, A.REC_STATUS].to(torch.int64) & 1) != 0).sum()
+                    verified = bool(gconv == sums[0]) and bool(checksum(g2) == sums[1])
+                if peer is not None:
+                    # once per run: the peer-stored array against a plain NCCL gather of the same records (bit for bit)
+                    full, _ = scan_sharded(grid, len(xis), n_mu, lambda _l: d_rec, rank, world, layout=args.layout)
+                    if rank == 0:
+                        equal_nccl = bool(torch.equal(full.view(torch.int64), peer.tensor.view(torch.int64)))
+                    del full
+            elif rank == 0:
+                g2 = torch.cat(gather_bufs).reshape(-1, A.REC_DOUBLES)
+                gconv = ((g2[:, A.REC_STATUS].to(torch.int64) & 1) != 0).sum()
+                verified = bool(gconv == sums[0]) and bool(checksum(g2) == sums[1])
+        else:
+            all_ms = [mine_ms]
+        J.update(total_ms=float(tot[0]), kernel_ms=float(tot[1]), cnt=[float(v) for v in cnt], n_total=int(n_total),
+                 per_rank_kernel_ms=[float(v[0]) for v in all_ms], gather_verified=verified, gather_equals_nccl=equal_nccl,
+                 peer=peer is not None, stats=eng.stats(), n_mu=n_mu, n_T=n_T)
+        if kind == "lines":
+            J["host_lines"] = (grid, mine)
+        if peer is not None:
+            barrier()
+            peer.close()
+        WORKLOADS[w] = base_workload
+        return J
+
+    mu_factor = world if (args.scaling == "weak" and world > 1) else 1
+    J = run_job(mu_factor, args.steps, args.warmup, True)
+    total_ms, kernel_ms = J["total_ms"], J["kernel_ms"]
+    n_conv, n_fj, n_th, n_ft, u_fj, u_th, u_ft = J["cnt"]
+    n_total = J["n_total"]
     value = n_conv * args.steps / (total_ms * 1e-3)
     fl = alg_flops(1, u_fj, u_th, 2, u_ft)            # whole job, one step: evaluated nodes x flavours actually evaluated (u == d)
     fl_ref = alg_flops(n_nodes, n_fj, n_th, 3, n_ft)  # same passes counted the way the reference loops (full mesh, 3 flavours)
-    st = eng.stats()
+    st = J["stats"]
+
+    weak = None
+    if world > 1 and args.scaling == "strong" and not args.no_weak and kind == "lines":
+        Jw = run_job(world, min(args.steps, 2), 1, False)
+        weak = {"value": Jw["cnt"][0] * min(args.steps, 2) / (Jw["total_ms"] * 1e-3), "unit": "points/s",
+                "ms_per_step": Jw["total_ms"] / min(args.steps, 2), "points": Jw["n_total"],
+                "note": "mu axis refined %d-fold: every GPU carries a full BASELINE-sized share" % world,
+                "per_rank_kernel_ms": Jw["per_rank_kernel_ms"]}
 
     # ---- e2e: the reference-facing call with HOST buffers (pnjl_scan_lines_host / pnjl_solve_points_host):
     # H2D of the inputs, kernel, D2H of the records inside the timed region; pinned host memory.  With a page-locked
@@ -420,18 +506,20 @@ def main():
     e2e = None
     if not args.no_e2e:
         if kind == "lines":
+            grid, mine = J["host_lines"]
             h_muq = torch.as_tensor(grid.muq_MeV[mine]).pin_memory().numpy()
             h_xi = torch.as_tensor(grid.xi[mine]).pin_memory().numpy()
             h_T = torch.as_tensor(grid.T_MeV).pin_memory().numpy()
             h_tidx = grid.table_idx[mine]
-            h_rec = torch.empty((len(mine), n_T, A.REC_DOUBLES), dtype=torch.float64).pin_memory().numpy()
+            h_rec = torch.empty((len(mine), J["n_T"], A.REC_DOUBLES), dtype=torch.float64).pin_memory().numpy()
             call = lambda: eng.scan_lines(h_muq, h_xi, h_T, h_tidx, out=h_rec)
             h2d = h_muq.nbytes + h_xi.nbytes + h_T.nbytes + h_tidx.nbytes
         else:
-            h_T = torch.as_tensor(allp[0, lo:hi].copy()).pin_memory().numpy()
-            h_mu = torch.as_tensor(allp[1, lo:hi].copy()).pin_memory().numpy()
-            h_xi = torch.as_tensor(allp[2, lo:hi].copy()).pin_memory().numpy()
-            h_rec = torch.empty((hi - lo, A.REC_DOUBLES), dtype=torch.float64).pin_memory().numpy()
+            allp, idx = J["host_inputs"]
+            h_T = torch.as_tensor(allp[0, idx].copy()).pin_memory().numpy()
+            h_mu = torch.as_tensor(allp[1, idx].copy()).pin_memory().numpy()
+            h_xi = torch.as_tensor(allp[2, idx].copy()).pin_memory().numpy()
+            h_rec = torch.empty((len(idx), A.REC_DOUBLES), dtype=torch.float64).pin_memory().numpy()
             call = lambda: eng.solve_points(h_T, h_mu, h_xi, A.SEED_MULTI, out=h_rec)
             h2d = h_T.nbytes + h_mu.nbytes + h_xi.nbytes
         call()                                          # warm-up (buffers inside the handle are grown here)
@@ -455,50 +543,66 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        s = cpu_sample(w, target_seconds=args.cpu_seconds)
+        s = cpu_sample(w, target_seconds=args.cpu_seconds, engine="ad", step=1)
+        sa = cpu_sample(w, target_seconds=min(args.cpu_seconds, 6.0), engine="analytic")
         cpu = {"value": s["converged"] / s["seconds"], "unit": "points/s", "cores": s["threads"], "kind": "port",
-               "sample": s["sample"], "seconds": s["seconds"],
-               "evals_per_point": s["n_fj"] / max(1, s["points"])}
+               "sample": s["sample"], "seconds": s["seconds"], "evals_per_point": s["n_fj"] / max(1, s["points"]),
+               "note": "oracle/pnjl_oracle.cpp: the reference's arithmetic (nested-dual AD Jacobian like ForwardDiff inside NLsolve)",
+               "analytic_jacobian": {"value": sa["converged"] / sa["seconds"], "unit": "points/s", "cores": sa["threads"],
+                                     "kind": "port", "sample": sa["sample"], "seconds": sa["seconds"],
+                                     "evals_per_point": sa["n_fj"] / max(1, sa["points"]),
+                                     "note": "oracle/pnjl_analytic_cpu.cpp: the GPU kernel's algorithm (closed-form Jacobian, isospin "
+                                             "shortcut, fused final pass) compiled for the host, OpenMP over lines (SURVEY.md §8d)"}}
 
     if rank == 0:
         traffic = None
         pj = os.path.join(ROOT, "profiles", "top_kernel.json")
-        extra = {}
-        if os.path.exists(pj):
+        static = None
+        if os.path.exists(pj) and world == 1:
             try:
                 prof = json.load(open(pj))
                 if prof.get("dram_bytes_per_point") is not None:
-                    traffic = prof["dram_bytes_per_point"] * float(n_total) / world   # per launch (one per GPU)
-                extra = {k: prof[k] for k in ("fp64_pipe_util_pct", "issue_active_pct", "profile") if k in prof}
+                    traffic = prof["dram_bytes_per_point"] * float(n_total)          # per launch
+                static = {k: prof[k] for k in ("fp64_pipe_util_pct", "issue_active_pct", "profile", "commit", "kernel") if k in prof}
+                static["source"] = "static: ncu capture committed under profiles/ (not measured in this run)"
             except Exception:
                 pass
         achieved = fl * args.steps / (kernel_ms * 1e-3) / 1e12
+        per_rank = J["per_rank_kernel_ms"]
         out = {
             "metric": "converged PNJL gap points/sec", "value": value, "unit": "points/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": w, "description": DESCR[w], "points": int(n_total), "converged": int(n_conv),
-                       "nodes": "%dx%d" % (p, t), "max_iter": MAX_ITER, "sharding": "contiguous mu-slabs, %d rank(s)" % world + ("" if world == 1 else (
-                      "; records stored by every rank's kernel directly into rank 0's array (CUDA IPC, NVLink), closing barrier only"
-                      if (kind == "lines" and peer is not None) else "; dist.gather to rank 0 after the kernel")),
-                       "l2": "512 MB buffer written between timed steps (L2 flush); inputs are O(100 KB), outputs 256 B/point",
-                       "lanes_per_solve": st["lanes_per_solve"], "blocks": st["blocks"], "threads": st["threads"],
-                       "regs_per_thread": st["regs_per_thread"]},
-            "roofline": dict({"bound": "fp64", "achieved": achieved, "peak": peak_sus * world, "unit": "TFLOP/s",
-                              "frac": achieved / (peak_sus * world), "traffic": traffic,
-                              "peak_source": "DFMA microbenchmark run in this process (pnjl_measure_fp64_peak): sustained %.2f, "
-                                             "burst %.2f TFLOP/s per GPU; MEASURED_PEAKS.json has no FP64 figure" % (peak_sus, peak_burst),
-                              "algorithmic_flop_per_step": fl, "flavours_evaluated": 2,
-                              "node_evaluations_per_step": u_fj + u_th + u_ft,
-                              "isotropic_collapse": bool(eng.isotropic_collapse),
-                              "reference_equivalent_tflops": fl_ref * args.steps / (kernel_ms * 1e-3) / 1e12,
-                              "fj_passes_per_point": n_fj / max(1.0, float(n_total)),
-                              "thermo_passes_per_point": n_th / max(1.0, float(n_total)),
-                              "fused_final_passes_per_point": n_ft / max(1.0, float(n_total)),
-                              "kernel_ms_per_step": kernel_ms / args.steps}, **extra),
-            "gpu_launches": int(args.steps) * world,
-            "clocks": clocks,
+            "config": config_of(w, world, args.scaling, args.layout, {
+                "points": int(n_total), "converged": int(n_conv), "n_mu": int(J["n_mu"]),
+                "sharding": "mu dealt out %s over %d rank(s)" % ("round-robin" if args.layout == "interleaved" else "in contiguous slabs", world) + (
+                    "" if world == 1 else ("; records stored by every rank's kernel directly into rank 0's array (CUDA IPC, NVLink), "
+                                           "closing barrier only" if J["peer"] else "; dist.gather to rank 0 after the kernel")),
+                "l2": "512 MB buffer written between timed steps (L2 flush); inputs are O(100 KB), outputs 256 B/point",
+                "lanes_per_solve": st["lanes_per_solve"], "blocks": st["blocks"], "threads": st["threads"],
+                "regs_per_thread": st["regs_per_thread"]}),
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_sus * world, "unit": "TFLOP/s",
+                         "frac": achieved / (peak_sus * world), "traffic": traffic,
+                         "peak_source": "DFMA microbenchmark run in this process (pnjl_measure_fp64_peak): sustained %.2f, "
+                                        "burst %.2f TFLOP/s per GPU; MEASURED_PEAKS.json has no FP64 figure" % (peak_sus, peak_burst),
+                         "algorithmic_flop_per_step": fl, "flavours_evaluated": 2,
+                         "node_evaluations_per_step": u_fj + u_th + u_ft,
+                         "isotropic_collapse": bool(eng.isotropic_collapse),
+                         "reference_equivalent_tflops": fl_ref * args.steps / (kernel_ms * 1e-3) / 1e12,
+                         "fj_passes_per_point": n_fj / max(1.0, float(n_total)),
+                         "thermo_passes_per_point": n_th / max(1.0, float(n_total)),
+                         "fused_final_passes_per_point": n_ft / max(1.0, float(n_total)),
+                         "passes_per_point": (n_fj + n_th + n_ft) / max(1.0, float(n_total)),
+                         "kernel_ms_per_step": kernel_ms / args.steps,
+                         "static_profile": static},
+            "per_rank_kernel_ms": per_rank,
+            "rank_imbalance_max_over_mean": max(per_rank) / (sum(per_rank) / len(per_rank)),
+            "gather_verified": J["gather_verified"], "gather_equals_nccl": J["gather_equals_nccl"],
+            "gpu_launches": int(args.steps) * world * int(st["kernel_launches"]),
+            "clocks": J["clocks"],
         }
+        if weak is not None:
+            out["weak"] = weak
         if e2e is not None:
             out["e2e"] = e2e
         if cpu is not None:
@@ -506,8 +610,6 @@ def main():
         print(json.dumps(out))
     if world > 1:
         dist.barrier()
-        if kind == "lines" and peer is not None:
-            peer.close()
         dist.destroy_process_group()
 
 

@@ -120,13 +120,15 @@ typedef struct pnjl_config {
                                        keep Newton/dogleg steps u<->d symmetric (a <= 1 ulp change of the step).  0: three
                                        independent flavours everywhere, like the reference's loop (Integrals.jl:250-257). */
     int32_t schedule;               /* kernel organisation for the 32-lane layout.
-                                       0 (default): continuity lines are marched by the line-march kernel — a warp (or a team of
-                                       warps when the GPU holds few lines) keeps a line's Newton solve in its registers, lines
-                                       are time-sliced through a global queue; independent points use organisation 2.
+                                       0 (default): automatic.  Continuity lines go to the line-march kernel (3) when a pass is
+                                       short (all-isotropic batch) or the GPU holds few lines, else to the warp-specialised
+                                       kernel (2); independent points use 2.
                                        1: every warp owns a line/point, CTAs phase-aligned by named barriers.
                                        2: warp-specialised — worker warps run only quadrature loops, controller lanes own one
                                        line/point each and run the solve cascade in SIMT, passes are handed over through
                                        shared-memory mailboxes.
+                                       3: line march — a warp (or a team of warps when the GPU holds few lines) keeps a line's
+                                       Newton solve in its registers, lines are time-sliced through a global queue.
                                        Results agree to round-off; the 8- and 16-lane layouts always use organisation 1. */
     int32_t isotropic_collapse;     /* 1 (default): for xi == 0 exactly the integrand does not depend on cos(theta)
                                        (E = sqrt(p^2 + M^2), Integrals.jl:178-180), so a pass sums over the p_num momentum
@@ -167,7 +169,7 @@ void pnjl_destroy(pnjl_handle* h);
 int pnjl_gauleg(double a, double b, int32_t n, double* nodes, double* weights);
 
 /* Run-time options of a handle (launch geometry, nothing that changes results beyond round-off):
- *   "schedule"        0 default, 1, 2: as pnjl_config.schedule
+ *   "schedule"        0 (automatic), 1, 2, 3: as pnjl_config.schedule
  *   "march_parts"     warps per line in the line-march kernel: 0 automatic, 1, 2, 4, 8, 16
  *   "march_quantum"   points per time slice of a line in the line-march kernel (0 automatic)
  *   "isotropic_batch" 1: the caller promises xi == 0 on every line of the following *_device calls (the host entry points

@@ -18,8 +18,10 @@ const LIB = get(ENV, "PNJL_B200_LIB", joinpath(@__DIR__, "..", "julia_relaxtime_
 
 const REC = 32                       # doubles per result record (PNJL_REC_DOUBLES)
 const AUX = 16                       # doubles per couplings record (PNJL_AUX_DOUBLES)
+const ABI_VERSION = 12               # PNJL_ABI_VERSION this file was written against (checked in __init__)
 const ST_CONVERGED = 1
 const ST_ALL_SEEDS_FAILED = 512
+const ST_MASS_INVERSION = 32768      # converged on the high-Omega root with M_s <= M_u (flagged, values unchanged)
 const SEED_EXPLICIT, SEED_AUTO, SEED_MULTI = Int32(0), Int32(1), Int32(2)
 
 # struct pnjl_config (field order and types as in the header)
@@ -49,6 +51,30 @@ end
 
 last_error() = unsafe_string(ccall((:pnjl_last_error, LIB), Cstring, ()))
 check(rc, what) = rc == 0 ? nothing : error("$what failed ($rc): $(last_error())")
+
+"""
+Layout self-check, run when the module loads: the hand-written `Config` / `Boundary` mirrors must have the size and the
+field offsets of the C structs of the library that was found (pnjl_sizeof_config, pnjl_config_field_offset), and the
+library must speak the ABI version this file was written against.  A mismatch is an error here, not a silent
+mis-read of the options inside `pnjl_create`.
+"""
+function check_layout()
+    v = ccall((:pnjl_abi_version, LIB), Cint, ())
+    v == ABI_VERSION || error("libpnjl_b200.so has ABI version $v, PNJLB200.jl was written for $ABI_VERSION")
+    sizeof(Config) == ccall((:pnjl_sizeof_config, LIB), Int64, ()) ||
+        error("sizeof(Config) = $(sizeof(Config)) differs from the library's pnjl_config")
+    sizeof(Boundary) == ccall((:pnjl_sizeof_boundary, LIB), Int64, ()) || error("struct Boundary differs from pnjl_boundary")
+    for (i, name) in enumerate(fieldnames(Config))
+        off = ccall((:pnjl_config_field_offset, LIB), Int64, (Cstring,), String(name))
+        off == Int64(fieldoffset(Config, i)) || error("Config.$name at offset $(fieldoffset(Config, i)), pnjl_config.$name at $off")
+    end
+    return true
+end
+__init__() = check_layout()
+
+"""Run-time option of a handle (pnjl_set_option): "schedule", "march_parts", "march_quantum", "isotropic_batch"."""
+set_option!(e, key::AbstractString, value::Integer) =
+    check(ccall((:pnjl_set_option, LIB), Cint, (Ptr{Cvoid}, Cstring, Int64), e.handle, String(key), Int64(value)), "pnjl_set_option($key)")
 
 """
     Engine(; p_num=64, t_num=8, iterations=1000, trust_region_fallback=true, auto_multiseed_fallback=true,

@@ -338,16 +338,42 @@ __global__ void __launch_bounds__(512, 1) k_scan_lines(const DeviceConfig* __res
 // line assembles F/J, does the 5x5 elimination and posts the next request: the FP64 pipe never waits for scalar
 // code.  Hand-off is a sequence number per mailbox (volatile shared + __threadfence_block, short __nanosleep
 // polls); there are no CTA barriers after the prologue, so divergent controller lanes cannot dead-lock.
-enum { WS_FJ = 0, WS_FT = 1, WS_TH = 2, WS_EXIT = 3 };
+// WS_FJ: Jacobian pass whose finish and 5x5 elimination run in the worker (lane-parallel, pnjl_lean.cuh) with the closed
+// forms the controller lane ships in the mailbox: the worker returns F and the Newton direction.  WS_FJ_SUMS: the same
+// pass returning the 20 sums (the trust-region method wants J itself).
+enum { WS_FJ = 0, WS_FT = 1, WS_TH = 2, WS_EXIT = 3, WS_FJ_SUMS = 4 };
 constexpr int kWsR = 21;   // doubles per result block: up to 20 sums + the fast-path flag
+constexpr int kWsCf = 12;  // closed forms of a Jacobian pass: dI/dM, d2I/dM2 per flavour (6), U_P, U_Pb, U_PP, U_PPb, U_PbPb (5), pad
 
 struct WsSlot {
     double d[9];        // T, mu, xi, x[5]
-    double r[kWsR];     // reduced sums (20 FJ | 5 + 8 fused | 8 thermo) ; r[20] = fast-path flag
+    double r[kWsR];     // WS_FJ: F[5], p[5], ok ; otherwise reduced sums (20 FJ | 5 + 8 fused | 8 thermo), r[20] = fast-path flag
+    double cf[kWsCf];   // closed forms for WS_FJ (written by the controller lane while the worker sweeps)
     int type;
     int parts_done;     // parts of the current pass finished so far (atomic; only when a pass is split)
-    int pad[2];
+    volatile int cf_seq;  // round number for which cf[] is valid
+    int pad;
 };
+
+// Closed forms with their libm fall-backs out of line (one copy each; the per-pass code of the controllers stays small).
+__device__ __noinline__ void vacuum_terms_cold(double Lam, double M, double& I0, double& I1, double& I2) {
+    vacuum_terms_t<false>(Lam, M, I0, I1, I2);
+}
+__device__ __noinline__ void polyakov_cold(const Model& m, double T, double iT, double P, double Pb, UTerms& u) {
+    polyakov_eval<false, true>(m, T, iT, P, Pb, u);
+}
+__device__ __noinline__ void ctrl_vacuum(double Lam, double M, double& I0, double& I1, double& I2) {
+    if (vacuum_tame(Lam, M)) vacuum_terms_t<true>(Lam, M, I0, I1, I2);
+    else vacuum_terms_cold(Lam, M, I0, I1, I2);
+}
+__device__ __noinline__ void ctrl_polyakov(const Model& m, double T, double iT, double P, double Pb, bool with_value, UTerms& u) {
+    if (polyakov_tame(P, Pb)) {
+        if (with_value) polyakov_eval<true, true>(m, T, iT, P, Pb, u);
+        else polyakov_eval<true, false>(m, T, iT, P, Pb, u);
+    } else {
+        polyakov_cold(m, T, iT, P, Pb, u);
+    }
+}
 
 // One request queue per controller warp ("group"): its lanes fill their mailboxes, lane 0 publishes the round,
 // any idle worker pulls the next work item, and the lanes resume when all mailboxes of the round are served.
@@ -374,6 +400,7 @@ struct WsTask {
     const double* T_fm; const double* mu_fm; int seed_mode; int n_seeds; const double* seeds;
     double* records;
     const long long* out_index;   // optional: task t writes its rows at record line out_index[t] instead of t (lines modes)
+    int worker_solve;             // see CtrlEval::worker_solve
 };
 
 struct CtrlEval {
@@ -385,20 +412,22 @@ struct CtrlEval {
     unsigned grp;     // lanes of this controller warp that own a mailbox
     bool leader;      // lowest lane of the group
     bool finished;    // this lane has no task left
+    bool worker_solve;   // Jacobian passes are finished and eliminated by the worker (WS_FJ) instead of by this lane
     double p2max, pc2max;
 #ifdef PNJL_PROFILE_PHASES
     unsigned long long* dbg;
-    long long t_ret;
+    long long t_ret, t_in;
 #endif
 
-    // Post one request and wait for the workers.  One code location for every caller (noinline) and one wait group
-    // per controller warp: all its lanes meet here once per round (lanes without tasks come from retire()), poll
-    // with one instruction stream and leave together, so the scalar code between passes runs SIMT-converged.
-    // Returns true (without posting anything) once every task of the group is finished.
-    __device__ __noinline__ bool request(int type, double T, double mu, double xi, const double x[5]) {
+    // Post one request / wait for the workers.  One code location each for every caller (noinline) and one wait group per
+    // controller warp: all its lanes meet in post() once per round (lanes without tasks come from retire()), and again in
+    // wait(), where they poll with one instruction stream and leave together, so the scalar code between passes runs
+    // SIMT-converged.  Between the two the lane computes what does not depend on the sums (the closed forms of x), so that
+    // work hides behind the workers' sweep.  post() returns true (without posting) once every task of the group is finished.
+    __device__ __noinline__ bool post(int type, double T, double mu, double xi, const double x[5]) {
 #ifdef PNJL_PROFILE_PHASES
         if (dbg && t_ret) { atomicAdd(dbg + 4, (unsigned long long)(clock64() - t_ret)); atomicAdd(dbg + 5, 1ULL); }
-        const long long t_in = clock64();
+        t_in = clock64();
 #endif
         slot->d[0] = T; slot->d[1] = mu; slot->d[2] = xi;
 #pragma unroll
@@ -413,17 +442,24 @@ struct CtrlEval {
             __threadfence_block();
             group->round = seq;                // publish the round to the workers
         }
-        const int target = seq * group->n_slots;
+        return false;
+    }
+    __device__ __noinline__ void wait() {
+        const unsigned target = (unsigned)seq * (unsigned)group->n_slots;
         for (;;) {
-            const bool ready = (*((volatile int*)&group->done) >= target);
+            const bool ready = (int)(*((volatile unsigned*)&group->done) - target) >= 0;     // wrap-safe
             if (__all_sync(grp, ready)) break;
-            __nanosleep(256);
+            __nanosleep(64);
         }
         __threadfence_block();
 #ifdef PNJL_PROFILE_PHASES
         t_ret = clock64();
         if (dbg) atomicAdd(dbg + 6, (unsigned long long)(t_ret - t_in));
 #endif
+    }
+    __device__ __forceinline__ bool request(int type, double T, double mu, double xi, const double x[5]) {
+        if (post(type, T, mu, xi, x)) return true;
+        wait();
         return false;
     }
     // A lane without tasks left keeps posting empty requests so that the round size stays fixed; returns when the
@@ -437,54 +473,102 @@ struct CtrlEval {
             group->exit_flag = 1;
         }
     }
+    // closed forms of the three flavours (M_d taken from M_u when the masses coincide bitwise)
+    __device__ __forceinline__ void vacuum_all(const PointCtx& c, double I0v[3], double I1v[3], double I2v[3]) const {
+        ctrl_vacuum(m->Lambda, c.M[0], I0v[0], I1v[0], I2v[0]);
+        if (c.M[1] == c.M[0]) { I0v[1] = I0v[0]; I1v[1] = I1v[0]; I2v[1] = I2v[0]; }
+        else ctrl_vacuum(m->Lambda, c.M[1], I0v[1], I1v[1], I2v[1]);
+        ctrl_vacuum(m->Lambda, c.M[2], I0v[2], I1v[2], I2v[2]);
+    }
     __device__ __noinline__ void fj(double T, double mu, double xi, const double x[5], double F[5], double J[25]) {
         PointCtx c;
         make_ctx(*m, T, mu, xi, x, c);
-        request(WS_FJ, T, mu, xi, x);
+        post(WS_FJ_SUMS, T, mu, xi, x);
+        double I0v[3], I1v[3], I2v[3];
+        vacuum_all(c, I0v, I1v, I2v);
+        UTerms u;
+        ctrl_polyakov(*m, c.T, c.invT, c.Phi, c.Phib, false, u);
+        wait();
         double acc[kFJAcc];
 #pragma unroll
         for (int i = 0; i < kFJAcc; ++i) acc[i] = slot->r[i];
-        finish_fj(*m, c, x, acc, F, J, slot->r[20] != 0.0);
+        finish_fj_pre(*m, c, x, acc, I1v, I2v, u, F, J, slot->r[20] != 0.0);
     }
+    // F(x) and the Newton direction: the worker that sweeps the mesh also assembles [J | F] and eliminates (lane-parallel);
+    // this lane contributes the closed forms, computed while the sweep runs.
     __device__ __noinline__ bool fj_step(double T, double mu, double xi, const double x[5], double F[5], double p[5]) {
         PointCtx c;
         make_ctx(*m, T, mu, xi, x, c);
-        request(WS_FJ, T, mu, xi, x);
-        double acc[kFJAcc];
+        if (!worker_solve) {
+            // the sums come back and this lane assembles J and eliminates in registers (cheap when many lines share the
+            // controller warp's instruction stream); the closed forms are still computed while the workers sweep
+            post(WS_FJ_SUMS, T, mu, xi, x);
+            double I0v[3], I1v[3], I2v[3];
+            vacuum_all(c, I0v, I1v, I2v);
+            UTerms u;
+            ctrl_polyakov(*m, c.T, c.invT, c.Phi, c.Phib, false, u);
+            wait();
+            double acc[kFJAcc], J[25], b[5];
 #pragma unroll
-        for (int i = 0; i < kFJAcc; ++i) acc[i] = slot->r[i];
-        double J[25], b[5];
-        finish_fj(*m, c, x, acc, F, J, slot->r[20] != 0.0);
+            for (int i = 0; i < kFJAcc; ++i) acc[i] = slot->r[i];
+            finish_fj_pre(*m, c, x, acc, I1v, I2v, u, F, J, slot->r[20] != 0.0);
 #pragma unroll
-        for (int i = 0; i < 5; ++i) b[i] = F[i];
-        const bool ok = lu_solve5_regs(J, b, p);     // J and the elimination stay in registers
+            for (int i = 0; i < 5; ++i) b[i] = F[i];
+            const bool ok = lu_solve5_regs(J, b, p);
 #pragma unroll
-        for (int i = 0; i < 5; ++i) p[i] = -p[i];
-        return ok;
+            for (int i = 0; i < 5; ++i) p[i] = -p[i];
+            return ok;
+        }
+        post(WS_FJ, T, mu, xi, x);
+        {
+            double I0v[3], I1v[3], I2v[3];
+            vacuum_all(c, I0v, I1v, I2v);
+            UTerms u;
+            ctrl_polyakov(*m, c.T, c.invT, c.Phi, c.Phib, false, u);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) { slot->cf[2 * i] = I1v[i]; slot->cf[2 * i + 1] = I2v[i]; }
+            slot->cf[6] = u.U_P; slot->cf[7] = u.U_Pb; slot->cf[8] = u.U_PP; slot->cf[9] = u.U_PPb; slot->cf[10] = u.U_PbPb;
+            __threadfence_block();
+            slot->cf_seq = seq;
+        }
+        wait();
+#pragma unroll
+        for (int i = 0; i < 5; ++i) { F[i] = slot->r[i]; p[i] = slot->r[5 + i]; }
+        return slot->r[10] != 0.0;
     }
     __device__ __noinline__ bool f_thermo(double T, double mu, double xi, const double x[5], double F[5], Thermo& th) {
         PointCtx c;
         make_ctx(*m, T, mu, xi, x, c);
         const double k2max = p2max + (xi > 0.0 ? xi * pc2max : 0.0);
         if (!fast_path_ok(c.T, c.mu, c.Phi, c.Phib, k2max, c.M2)) return false;
-        request(WS_FT, T, mu, xi, x);
+        post(WS_FT, T, mu, xi, x);
+        double I0v[3], I1v[3], I2v[3];
+        vacuum_all(c, I0v, I1v, I2v);
+        UTerms u;
+        ctrl_polyakov(*m, c.T, c.invT, c.Phi, c.Phib, true, u);
+        wait();
         double facc[kFtAcc], tacc[kThAcc];
 #pragma unroll
         for (int i = 0; i < kFtAcc; ++i) facc[i] = slot->r[i];
 #pragma unroll
         for (int i = 0; i < kThAcc; ++i) tacc[i] = slot->r[kFtAcc + i];
-        finish_f(*m, c, x, facc, F);
-        finish_thermo(*m, c, x, tacc, th);
+        finish_f_pre(*m, c, x, facc, I1v, u, F);
+        finish_thermo_pre(*m, c, x, tacc, I0v, u, th);
         return true;
     }
     __device__ __noinline__ void thermo(double T, double mu, double xi, const double x[5], Thermo& th) {
         PointCtx c;
         make_ctx(*m, T, mu, xi, x, c);
-        request(WS_TH, T, mu, xi, x);
+        post(WS_TH, T, mu, xi, x);
+        double I0v[3], I1v[3], I2v[3];
+        vacuum_all(c, I0v, I1v, I2v);
+        UTerms u;
+        ctrl_polyakov(*m, c.T, c.invT, c.Phi, c.Phib, true, u);
+        wait();
         double tacc[kThAcc];
 #pragma unroll
         for (int i = 0; i < kThAcc; ++i) tacc[i] = slot->r[i];
-        finish_thermo(*m, c, x, tacc, th);
+        finish_thermo_pre(*m, c, x, tacc, I0v, u, th);
     }
 };
 
@@ -568,6 +652,61 @@ __device__ __noinline__ void ws_worker_pass(const DeviceConfig* cfg, const MeshV
     }
 }
 
+// The finish of a WS_FJ pass in the worker warp that swept the mesh (or that added up the last part): [J | F] one entry per
+// lane from the sums in W[LW_S ..] and the closed forms of the mailbox, elimination and back substitution (pnjl_lean.cuh).
+// Leaves F[5], p[5] = -J^{-1} F and the non-singular flag in the mailbox.
+__device__ __noinline__ void ws_worker_solve(const DeviceConfig* cfg, WsSlot* sl, double* W, int lane, int round) {
+    while (sl->cf_seq != round) __nanosleep(32);      // the controller lane writes them while we sweep: normally long there
+    __threadfence_block();
+    const double T = sl->d[0], mu = sl->d[1], xi = sl->d[2];
+    double x[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) x[i] = sl->d[3 + i];
+    PointCtx c;
+    make_ctx(cfg->m, T, mu, xi, x, c);
+    LeanConst k;
+    lean_consts(cfg->m, c.T, c.invT, k);
+    if (lane < 3) {
+        const double Mf = lane == 0 ? c.M[0] : (lane == 1 ? c.M[1] : c.M[2]);
+        const double M2f = lane == 0 ? c.M2[0] : (lane == 1 ? c.M2[1] : c.M2[2]);
+        lean_flavour_fj_pre(lane, k, Mf, M2f, W[LW_S + 20] != 0.0, sl->cf[2 * lane], sl->cf[2 * lane + 1], W);
+    } else if (lane < 12) {
+        const int r = (lane - 3) / 3, j = (lane - 3) - 3 * r;
+        lean_dtable(r, j, k, x, W);
+    } else if (lane == 12) {
+#pragma unroll
+        for (int q = 0; q < 5; ++q) { W[LW_X + q] = x[q]; W[LW_U + q] = sl->cf[6 + q]; }
+    }
+    __syncwarp();
+    const int li = lane / 6, lc = lane - 6 * li;
+    double a = 0.0;
+    if (lane < 30) {
+        a = lean_aug_entry(li, lc, k, W, ACC_GP, ACC_GPB);
+        W[LW_AUG + lane] = a;
+    }
+    __syncwarp();
+    double F[5], y[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) F[i] = W[LW_AUG + 6 * i + 5];
+    bool ok = true;
+#pragma unroll 1
+    for (int step = 0; step < 5; ++step) {
+        double inv = 0.0, nxt = a;
+        if (lane < 30) nxt = lean_lu_step(step, li, lc, W, a, inv, ok);
+        __syncwarp();
+        if (lane < 30) { a = nxt; W[LW_AUG + lane] = a; }
+        if (lane == 0) W[LW_INV + step] = inv;
+        __syncwarp();
+    }
+    lean_backsub(W, y);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) { sl->r[i] = F[i]; sl->r[5 + i] = -y[i]; }
+        sl->r[10] = ok ? 1.0 : 0.0;
+    }
+    __syncwarp();
+}
+
 constexpr int kWsMaxGroups = 8;
 #ifndef PNJL_WS_MAX_THREADS
 #define PNJL_WS_MAX_THREADS 512   // 16 warps x 128 registers fill the register file of an SM
@@ -586,8 +725,9 @@ __global__ void __launch_bounds__(PNJL_WS_MAX_THREADS, 1) k_solve_ws(const Devic
     const int n = cfg->n_nodes;
     double* s_mesh = s_dyn;
     const int n_mesh = 3 * n + 2 * cfg->n_iso;
-    WsSlot* s_slots = reinterpret_cast<WsSlot*>(s_dyn + n_mesh);
+    WsSlot* s_slots = reinterpret_cast<WsSlot*>(s_dyn + ((n_mesh + 1) & ~1));
     double* s_part = reinterpret_cast<double*>(s_slots + n_slots);
+    double* s_work = s_part + (parts > 1 ? (size_t)kWsR * n_slots * parts : 0) + (parts > 1 ? ((kWsR * n_slots * parts) & 1) : 0);
     for (int i = threadIdx.x; i < n_mesh; i += blockDim.x) s_mesh[i] = g_mesh[i];
     // One request group per controller warp.  (Two independent groups per warp — divergent half-warps with shorter rounds —
     // were measured 16 % slower on cfg5: the halves serialise their scalar phases.)
@@ -609,6 +749,7 @@ __global__ void __launch_bounds__(PNJL_WS_MAX_THREADS, 1) k_solve_ws(const Devic
     for (int i = threadIdx.x; i < n_slots; i += blockDim.x) {
         s_slots[i].type = WS_EXIT;
         s_slots[i].parts_done = 0;
+        s_slots[i].cf_seq = 0;
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -648,6 +789,7 @@ __global__ void __launch_bounds__(PNJL_WS_MAX_THREADS, 1) k_solve_ws(const Devic
                 idx = __shfl_sync(0xffffffffu, idx, 0);
                 if (idx >= gr->n_slots * parts) continue;    // somebody else took the last item
                 __threadfence_block();
+                const int round = gr->round;                 // cannot advance before this item is served
                 const int si = gr->first_slot + idx / parts, part = idx % parts;
                 WsSlot* sl = &s_slots[si];
                 const int type = sl->type;
@@ -656,12 +798,18 @@ __global__ void __launch_bounds__(PNJL_WS_MAX_THREADS, 1) k_solve_ws(const Devic
                 if (lane == 0 && cfg->dbg && t_idle) atomicAdd(cfg->dbg + 3, (unsigned long long)(tp0 - t_idle));
 #endif
                 bool slot_complete = true;
+                const int ptype = type == WS_FJ_SUMS ? WS_FJ : type;     // kind of sweep
+                double* Wl = s_work + (size_t)warp * LW_END;             // this worker's scratch line (WS_FJ finish)
                 if (type != WS_EXIT) {
                     if (parts == 1) {
-                        ws_worker_pass(cfg, mv, sl->d, type, lane, 0, 1, sl->r);
+                        ws_worker_pass(cfg, mv, sl->d, ptype, lane, 0, 1, type == WS_FJ ? Wl + LW_S : sl->r);
+                        if (type == WS_FJ) {
+                            __syncwarp();
+                            ws_worker_solve(cfg, sl, Wl, lane, round);
+                        }
                     } else {
                         double* mine = s_part + ((size_t)si * parts + part) * kWsR;
-                        ws_worker_pass(cfg, mv, sl->d, type, lane, part, parts, mine);
+                        ws_worker_pass(cfg, mv, sl->d, ptype, lane, part, parts, mine);
                         __syncwarp();
                         __threadfence_block();
                         int c = 0;
@@ -675,9 +823,15 @@ __global__ void __launch_bounds__(PNJL_WS_MAX_THREADS, 1) k_solve_ws(const Devic
                                 const double* base = s_part + (size_t)si * parts * kWsR + lane;
                                 double v = base[0];
                                 for (int q = 1; q < parts; ++q) v += base[q * kWsR];
-                                sl->r[lane] = (lane == 20) ? base[0] : v;
+                                v = (lane == 20) ? base[0] : v;
+                                if (type == WS_FJ) Wl[LW_S + lane] = v;
+                                else sl->r[lane] = v;
                             }
                             if (lane == 0) sl->parts_done = 0;
+                            if (type == WS_FJ) {
+                                __syncwarp();
+                                ws_worker_solve(cfg, sl, Wl, lane, round);
+                            }
                         }
                     }
                 } else if (parts > 1) {
@@ -714,6 +868,7 @@ __global__ void __launch_bounds__(PNJL_WS_MAX_THREADS, 1) k_solve_ws(const Devic
     ev.grp = gr->n_slots >= 32 ? 0xffffffffu : ((1u << gr->n_slots) - 1u);
     ev.leader = lane == 0;
     ev.finished = false;
+    ev.worker_solve = task.worker_solve != 0;
     ev.p2max = cfg->p2max;
     ev.pc2max = cfg->pc2max;
 #ifdef PNJL_PROFILE_PHASES
@@ -956,10 +1111,12 @@ struct pnjl_handle {
     int block_threads = 128;
     bool block_threads_forced = false;   // PNJL_BLOCK_THREADS given
     int schedule = 2;             // 0: every warp owns a line (phase-aligned CTAs); 1: worker/controller warps (k_solve_ws);
-                                  // 2: line march in registers, time-sliced lines (k_march; lines only — points use 1)
+                                  // 2: automatic — k_march or k_solve_ws for lines by batch shape (dispatch_lines), k_solve_ws for
+                                  // points; 3: line march in registers, time-sliced lines (k_march) for every line batch
     int ws_workers = 14, ws_ctrl_warps = 2, ws_spw = 4, ws_slots = 0;
     int march_parts = 0;          // warps per team in k_march (0 = automatic)
     int march_quantum = 0;        // points per time slice in k_march (0 = automatic)
+    int march_lockstep = 0;       // phase alignment of the teams of a CTA in k_march (experiments: PNJL_MARCH_LOCKSTEP=1)
     bool iso_batch = false;       // option "isotropic_batch": the caller promises xi == 0 on every line (device entry points)
     bool iso_next = false;        // the next launch is all-isotropic (set by the host entry points, which see xi)
     DevBuf march_state, march_slots, march_counters;
@@ -1053,6 +1210,7 @@ int launch_ws(pnjl_handle* h, const WsTask& task_in, cudaStream_t st) {
     // varies smoothly with the line index: SM load max/mean 1.017 on cfg5 against 1.035 for a pseudo-random order
     // (scripts/line_balance.py data).  The golden-ratio permutation dates from the contiguous hand-out (PNJL_WS_PERM=1 restores it).
     task.perm_mult = (getenv("PNJL_WS_PERM") && atoi(getenv("PNJL_WS_PERM")) != 0) ? coprime_multiplier(task.n_tasks) : 1;
+    task.worker_solve = getenv("PNJL_WS_WSOLVE") ? atoi(getenv("PNJL_WS_WSOLVE")) : 0;
     int nw = h->ws_workers, nc = h->ws_ctrl_warps, spw = h->ws_spw, parts = 1;
     const long long per_sm = (task.n_tasks + h->sm_count - 1) / h->sm_count;   // tasks an SM has to carry at least
     long long n_slots = h->ws_slots > 0 ? h->ws_slots : (long long)spw * nw;
@@ -1072,9 +1230,14 @@ int launch_ws(pnjl_handle* h, const WsTask& task_in, cudaStream_t st) {
     while ((n_slots + nc - 1) / nc > 32 && nc < kWsMaxGroups) ++nc;
     if (nc > (int)n_slots) nc = (int)n_slots;
     if (nw + nc > kWsMaxWarps) nw = kWsMaxWarps - nc;
+    // protocol limits: a controller warp owns at most 32 mailboxes (one per lane), there are at most kWsMaxGroups of them
+    // and at least one worker must remain; anything else (PNJL_WS_* experiments) would wait for mailboxes nobody serves
+    if (nw < 1 || nc < 1 || nc > kWsMaxGroups || (n_slots + nc - 1) / nc > 32)
+        return fail(PNJL_ERR_ARG, "warp-specialised kernel: impossible mailbox layout (PNJL_WS_SLOTS / PNJL_WS_CTRL / PNJL_WS_WORKERS)");
     const int threads = 32 * (nw + nc);
-    const size_t smem = sizeof(double) * (3 * h->n_nodes + 2 * h->host_cfg.n_iso) + sizeof(WsSlot) * (size_t)n_slots +
-                        (parts > 1 ? sizeof(double) * kWsR * (size_t)n_slots * parts : 0);
+    const size_t smem = sizeof(double) * (size_t)(((3 * h->n_nodes + 2 * h->host_cfg.n_iso) + 1) & ~1) + sizeof(WsSlot) * (size_t)n_slots +
+                        (parts > 1 ? sizeof(double) * (((size_t)kWsR * n_slots * parts + 1) & ~(size_t)1) : 0) +
+                        sizeof(double) * (size_t)LW_END * (size_t)nw;
     cudaFuncAttributes fa;
     CUDA_TRY(cudaFuncGetAttributes(&fa, k_solve_ws));
     if (smem > 40 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_solve_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1155,7 +1318,8 @@ int launch_march(pnjl_handle* h, long long n_lines, const double* muq, const dou
     mc.n = h->n_nodes; mc.n_iso = h->host_cfg.n_iso;
     mc.p2max = h->host_cfg.p2max; mc.pc2max = h->host_cfg.pc2max;
     mc.sp = h->host_cfg.sp;
-    const size_t smem = sizeof(double) * (size_t)(mc.int0 + kMarchWarps);     // 2 x 16 ints at the end
+    mc.lockstep = h->march_lockstep > 0 ? 1 : 0;     // measured (profiles/r02_*): no gain with few lines, large loss otherwise
+    const size_t smem = sizeof(double) * (size_t)(mc.int0 + kMarchWarps + 2);     // 2 x 16 + 2 ints at the end
     cudaFuncAttributes fa;
     CUDA_TRY(cudaFuncGetAttributes(&fa, k_march));
     if (smem > 40 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_march, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1175,6 +1339,52 @@ int launch_march(pnjl_handle* h, long long n_lines, const double* muq, const dou
     k_march<<<blocks, 32 * kMarchWarps, smem, st>>>(h->d_mesh, a);
     CUDA_TRY(cudaGetLastError());
     h->stats.kernel_launches += 2;
+    return PNJL_OK;
+}
+
+// Independent points through the line-march machinery (one team per point, no controller warps).
+int launch_march_points(pnjl_handle* h, long long n, const double* T, const double* mu, const double* xi, int seed_mode,
+                        int n_seeds, const double* seeds, double* rec, cudaStream_t st) {
+    const long long total_warps = (long long)h->sm_count * kMarchWarps;
+    int parts = 1;
+    while (parts < kMarchWarps && n * 2 * parts <= total_warps && h->n_nodes / (64 * parts) >= 2) parts *= 2;
+    if (h->march_parts > 0) parts = h->march_parts;
+    if (parts != 1 && parts != 2 && parts != 4 && parts != 8 && parts != 16) return fail(PNJL_ERR_ARG, "march_parts must be 1, 2, 4, 8 or 16");
+    MarchPointArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.n = n; a.T_fm = T; a.mu_fm = mu; a.xi = xi; a.seed_mode = seed_mode; a.n_seeds = n_seeds; a.seeds = seeds; a.records = rec;
+    a.counter = h->d_counter;
+    const int n_mesh = 3 * h->n_nodes + 2 * h->host_cfg.n_iso;
+    MarchConst mc;
+    std::memset(&mc, 0, sizeof(mc));
+    mc.cfg = h->d_cfg;
+    mc.parts = parts;
+    mc.stage0 = (n_mesh + 1) & ~1;
+    mc.lean0 = mc.stage0 + kMarchWarps * kStageDoubles;
+    mc.team0 = mc.lean0 + kMarchWarps * LW_END;
+    mc.int0 = mc.team0 + 2 * kMarchWarps * kBufStride;
+    mc.n = h->n_nodes; mc.n_iso = h->host_cfg.n_iso;
+    mc.p2max = h->host_cfg.p2max; mc.pc2max = h->host_cfg.pc2max;
+    mc.sp = h->host_cfg.sp;
+    mc.lockstep = 0;
+    const size_t smem = sizeof(double) * (size_t)(mc.int0 + kMarchWarps + 2);
+    cudaFuncAttributes fa;
+    CUDA_TRY(cudaFuncGetAttributes(&fa, k_march_points));
+    if (smem > 40 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_march_points, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long teams_per_cta = kMarchWarps / parts;
+    const long long need = (n + teams_per_cta - 1) / teams_per_cta;
+    const int blocks = (int)(need < h->sm_count ? need : h->sm_count);
+    h->stats.regs_per_thread = fa.numRegs;
+    h->stats.smem_bytes = (int)smem;
+    h->stats.blocks = blocks;
+    h->stats.threads = 32 * kMarchWarps;
+    h->stats.lanes_per_solve = 32 * parts;
+    CUDA_TRY(cudaMemcpyToSymbolAsync(c_model, &h->host_cfg.m, sizeof(Model), 0, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyToSymbolAsync(c_mc, &mc, sizeof(MarchConst), 0, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned long long), st));
+    k_march_points<<<blocks, 32 * kMarchWarps, smem, st>>>(h->d_mesh, a);
+    CUDA_TRY(cudaGetLastError());
+    h->stats.kernel_launches += 1;
     return PNJL_OK;
 }
 
@@ -1215,9 +1425,13 @@ int launch_fj(pnjl_handle* h, long long n, const double* T, const double* mu, co
         }                                        \
     } while (0)
 
-int take_layout(pnjl_handle* h) {
+// The layout chosen for the next launch only (host entry points), consumed at the very start of every *_device entry so that
+// an early error return cannot leak it into a later call.
+int take_layout(pnjl_handle* h, bool* iso_hint = nullptr) {
     const int g = h->G_next ? h->G_next : h->G;
     h->G_next = 0;
+    if (iso_hint) *iso_hint = h->iso_next;
+    h->iso_next = false;
     return g;
 }
 
@@ -1230,7 +1444,7 @@ void choose_layout_for_batch(pnjl_handle* h, long long n, const double* xi, bool
     if (h->G_user != 0 || h->host_cfg.n_iso == 0) return;
     for (long long i = 0; i < n; ++i)
         if (xi[i] != 0.0) return;
-    if (march_lines && h->schedule == 2 && h->G == 32) {
+    if (march_lines && h->schedule >= 2 && h->G == 32) {
         h->iso_next = true;      // the line-march kernel keeps its layout and only sizes its teams for p_num nodes
         return;
     }
@@ -1238,25 +1452,35 @@ void choose_layout_for_batch(pnjl_handle* h, long long n, const double* xi, bool
     h->G_next = n_eff <= 96 ? 8 : (n_eff <= 256 ? 16 : 32);
 }
 
-int dispatch_points(pnjl_handle* h, long long n, const double* T, const double* mu, const double* xi, int seed_mode,
+int dispatch_points(pnjl_handle* h, int layout, long long n, const double* T, const double* mu, const double* xi, int seed_mode,
                     int n_seeds, const double* seeds, double* rec, cudaStream_t st) {
-    switch (take_layout(h)) {
+    switch (layout) {
         case 8: return launch_points<8>(h, n, T, mu, xi, seed_mode, n_seeds, seeds, rec, st);
         case 16: return launch_points<16>(h, n, T, mu, xi, seed_mode, n_seeds, seeds, rec, st);
         default:
+            if (h->schedule == 3 || (getenv("PNJL_POINTS_MARCH") && atoi(getenv("PNJL_POINTS_MARCH")) != 0))
+                return launch_march_points(h, n, T, mu, xi, seed_mode, n_seeds, seeds, rec, st);
             if (h->schedule >= 1) return launch_points_ws(h, n, T, mu, xi, seed_mode, n_seeds, seeds, rec, st);
             return launch_points<32>(h, n, T, mu, xi, seed_mode, n_seeds, seeds, rec, st);
     }
 }
-int dispatch_lines(pnjl_handle* h, long long n_lines, const double* muq, const double* xi, const int* tidx, int n_T,
+int dispatch_lines(pnjl_handle* h, int layout, long long n_lines, const double* muq, const double* xi, const int* tidx, int n_T,
                    const double* T, double* rec, cudaStream_t st, int mode = 0) {
-    switch (take_layout(h)) {
+    switch (layout) {
         case 8: return launch_lines<8>(h, n_lines, muq, xi, tidx, n_T, T, rec, st, mode);
         case 16: return launch_lines<16>(h, n_lines, muq, xi, tidx, n_T, T, rec, st, mode);
-        default:
-            if (h->schedule == 2 && mode == 0) return launch_march(h, n_lines, muq, xi, tidx, n_T, T, rec, st);
+        default: {
+            // Which organisation marches the lines (measured on cfg5 / cfg4 shares, profiles/r02_*): the line-march kernel when
+            // a pass is short (all-isotropic batch: p_num nodes) or the GPU holds few lines (<= 10 per SM: multi-GPU shares of a
+            // fixed grid), where the latency of a pass decides; the warp-specialised kernel when there are enough lines to hide
+            // its controller step (its workers' small code stays inside the instruction cache).
+            const bool iso = (h->iso_next || h->iso_batch) && h->host_cfg.n_iso > 0;
+            const bool march = mode == 0 && (h->schedule == 3 || (h->schedule == 2 && (iso || n_lines <= 10LL * h->sm_count)));
+            if (march) return launch_march(h, n_lines, muq, xi, tidx, n_T, T, rec, st);
+            h->iso_next = false;
             if (h->schedule >= 1) return launch_lines_ws(h, n_lines, muq, xi, tidx, n_T, T, rec, st, mode);
             return launch_lines<32>(h, n_lines, muq, xi, tidx, n_T, T, rec, st, mode);
+        }
     }
 }
 int dispatch_fj(pnjl_handle* h, long long n, const double* T, const double* mu, const double* xi, const double* x,
@@ -1441,9 +1665,10 @@ int pnjl_create(const pnjl_config* c, pnjl_handle** out) {
         if (h->block_threads < 32 || h->block_threads > 512 || (h->block_threads & 31)) h->block_threads = 128;
         // internal numbering: 1 = warp-specialised, 0 = one warp per line; PNJL_SCHEDULE overrides for experiments
         const char* es = getenv("PNJL_SCHEDULE");
-        h->schedule = es ? atoi(es) : (c->schedule == 1 ? 0 : (c->schedule == 2 ? 1 : 2));
+        h->schedule = es ? atoi(es) : (c->schedule == 1 ? 0 : (c->schedule == 2 ? 1 : (c->schedule == 3 ? 3 : 2)));
         if (getenv("PNJL_MARCH_PARTS")) h->march_parts = atoi(getenv("PNJL_MARCH_PARTS"));
         if (getenv("PNJL_MARCH_Q")) h->march_quantum = atoi(getenv("PNJL_MARCH_Q"));
+        if (getenv("PNJL_MARCH_LOCKSTEP")) h->march_lockstep = atoi(getenv("PNJL_MARCH_LOCKSTEP"));
         if (getenv("PNJL_WS_WORKERS")) h->ws_workers = atoi(getenv("PNJL_WS_WORKERS"));
         if (getenv("PNJL_WS_CTRL")) h->ws_ctrl_warps = atoi(getenv("PNJL_WS_CTRL"));
         if (getenv("PNJL_WS_SPW")) h->ws_spw = atoi(getenv("PNJL_WS_SPW"));
@@ -1577,8 +1802,8 @@ int pnjl_set_option(pnjl_handle* h, const char* key, int64_t value) {
     if (!h || !key) return fail(PNJL_ERR_ARG, "null argument");
     const std::string k(key);
     if (k == "schedule") {
-        if (value < 0 || value > 2) return fail(PNJL_ERR_ARG, "schedule: 0 line march, 1 one warp per line, 2 worker/controller warps");
-        h->schedule = value == 1 ? 0 : (value == 2 ? 1 : 2);
+        if (value < 0 || value > 3) return fail(PNJL_ERR_ARG, "schedule: 0 automatic, 1 one warp per line, 2 worker/controller warps, 3 line march");
+        h->schedule = value == 1 ? 0 : (value == 2 ? 1 : (value == 3 ? 3 : 2));
     } else if (k == "march_parts") {
         if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8 && value != 16)
             return fail(PNJL_ERR_ARG, "march_parts must be 0 (automatic), 1, 2, 4, 8 or 16");
@@ -1597,6 +1822,7 @@ int pnjl_set_option(pnjl_handle* h, const char* key, int64_t value) {
 int pnjl_solve_points_device(pnjl_handle* h, int64_t n, const double* d_T, const double* d_mu, const double* d_xi,
                              int32_t seed_mode, int32_t n_seeds, const double* d_seeds, double* d_records, void* stream) {
     if (!h) return fail(PNJL_ERR_ARG, "null handle");
+    const int layout = take_layout(h);
     if (n < 0) return fail(PNJL_ERR_ARG, "n < 0");
     if (seed_mode < 0 || seed_mode > 2) return fail(PNJL_ERR_ARG, "bad seed_mode");
     if (seed_mode == PNJL_SEED_EXPLICIT && (!d_seeds || n_seeds < 1 || n_seeds > 6))
@@ -1605,18 +1831,21 @@ int pnjl_solve_points_device(pnjl_handle* h, int64_t n, const double* d_T, const
     if (n == 0) return PNJL_OK;
     if (!d_T || !d_mu || !d_xi || !d_records) return fail(PNJL_ERR_ARG, "null buffer");
     DeviceGuard guard(h->device);
-    return dispatch_points(h, n, d_T, d_mu, d_xi, seed_mode, n_seeds, d_seeds, d_records, (cudaStream_t)stream);
+    return dispatch_points(h, layout, n, d_T, d_mu, d_xi, seed_mode, n_seeds, d_seeds, d_records, (cudaStream_t)stream);
 }
 
 int pnjl_scan_lines_device(pnjl_handle* h, int64_t n_lines, const double* d_muq, const double* d_xi,
                            const int32_t* d_tidx, int32_t n_T, const double* d_T, double* d_records, void* stream) {
     if (!h) return fail(PNJL_ERR_ARG, "null handle");
+    bool iso_hint = false;
+    const int layout = take_layout(h, &iso_hint);
     if (n_lines < 0 || n_T < 0) return fail(PNJL_ERR_ARG, "negative size");
     h->stats.kernel_launches = 0;
     if (n_lines == 0 || n_T == 0) return PNJL_OK;
     if (!d_muq || !d_xi || !d_T || !d_records) return fail(PNJL_ERR_ARG, "null buffer");
     DeviceGuard guard(h->device);
-    return dispatch_lines(h, n_lines, d_muq, d_xi, d_tidx, n_T, d_T, d_records, (cudaStream_t)stream);
+    h->iso_next = iso_hint;       // consumed by dispatch_lines / launch_march below
+    return dispatch_lines(h, layout, n_lines, d_muq, d_xi, d_tidx, n_T, d_T, d_records, (cudaStream_t)stream);
 }
 
 int pnjl_solve_points_host(pnjl_handle* h, int64_t n, const double* T, const double* mu, const double* xi,
@@ -1625,6 +1854,9 @@ int pnjl_solve_points_host(pnjl_handle* h, int64_t n, const double* T, const dou
     if (n < 0) return fail(PNJL_ERR_ARG, "n < 0");
     if (n == 0) { h->stats.kernel_launches = 0; return PNJL_OK; }
     if (!T || !mu || !xi || !records) return fail(PNJL_ERR_ARG, "null buffer");
+    if (seed_mode < 0 || seed_mode > 2) return fail(PNJL_ERR_ARG, "bad seed_mode");
+    if (seed_mode == PNJL_SEED_EXPLICIT && (!seeds || n_seeds < 1 || n_seeds > 6))
+        return fail(PNJL_ERR_ARG, "explicit seeds need 1..6 seeds per point");     // before anything is allocated or enqueued
     DeviceGuard guard(h->device);
     const size_t nb = sizeof(double) * (size_t)n;
     CUDA_TRY(h->in_T.reserve(nb));
@@ -1638,7 +1870,6 @@ int pnjl_solve_points_host(pnjl_handle* h, int64_t n, const double* T, const dou
     CUDA_TRY(cudaMemcpyAsync(h->in_xi.p, xi, nb, cudaMemcpyHostToDevice, st));
     const double* d_seeds = nullptr;
     if (seed_mode == PNJL_SEED_EXPLICIT) {
-        if (!seeds || n_seeds < 1 || n_seeds > 6) return fail(PNJL_ERR_ARG, "explicit seeds need 1..6 seeds per point");
         CUDA_TRY(h->in_seeds.reserve(nb * 5 * n_seeds));
         CUDA_TRY(cudaMemcpyAsync(h->in_seeds.p, seeds, nb * 5 * n_seeds, cudaMemcpyHostToDevice, st));
         d_seeds = (const double*)h->in_seeds.p;
@@ -1839,12 +2070,13 @@ int pnjl_ipc_free(void* dptr) {
 int pnjl_tmu_scan_device(pnjl_handle* h, int64_t n_lines, const double* d_T, const double* d_xi, const int32_t* d_tidx,
                          int32_t n_mu, const double* d_mu, double* d_records, void* stream) {
     if (!h) return fail(PNJL_ERR_ARG, "null handle");
+    const int layout = take_layout(h);
     if (n_lines < 0 || n_mu < 0) return fail(PNJL_ERR_ARG, "negative size");
     h->stats.kernel_launches = 0;
     if (n_lines == 0 || n_mu == 0) return PNJL_OK;
     if (!d_T || !d_xi || !d_mu || !d_records) return fail(PNJL_ERR_ARG, "null buffer");
     DeviceGuard guard(h->device);
-    return dispatch_lines(h, n_lines, d_T, d_xi, d_tidx, n_mu, d_mu, d_records, (cudaStream_t)stream, 1);
+    return dispatch_lines(h, layout, n_lines, d_T, d_xi, d_tidx, n_mu, d_mu, d_records, (cudaStream_t)stream, 1);
 }
 
 int pnjl_tmu_scan_host(pnjl_handle* h, int64_t n_lines, const double* T_MeV, const double* xi, const int32_t* tidx,
@@ -1888,12 +2120,13 @@ int pnjl_tmu_scan_host(pnjl_handle* h, int64_t n_lines, const double* T_MeV, con
 int pnjl_dual_branch_device(pnjl_handle* h, int64_t n_lines, const double* d_T, const double* d_xi, int32_t n_mu,
                             const double* d_mu, double* d_records, void* stream) {
     if (!h) return fail(PNJL_ERR_ARG, "null handle");
+    const int layout = take_layout(h);
     if (n_lines < 0 || n_mu < 0) return fail(PNJL_ERR_ARG, "negative size");
     h->stats.kernel_launches = 0;
     if (n_lines == 0 || n_mu == 0) return PNJL_OK;
     if (!d_T || !d_xi || !d_mu || !d_records) return fail(PNJL_ERR_ARG, "null buffer");
     DeviceGuard guard(h->device);
-    return dispatch_lines(h, 2 * n_lines, d_T, d_xi, nullptr, n_mu, d_mu, d_records, (cudaStream_t)stream, 2);
+    return dispatch_lines(h, layout, 2 * n_lines, d_T, d_xi, nullptr, n_mu, d_mu, d_records, (cudaStream_t)stream, 2);
 }
 int pnjl_dual_branch_host(pnjl_handle* h, int64_t n_lines, const double* T_MeV, const double* xi, int32_t n_mu,
                           const double* mu_MeV, double* records) {

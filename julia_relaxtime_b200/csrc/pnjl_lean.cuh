@@ -59,6 +59,21 @@ PNJL_HD bool lean_flavour_fj(int f, const LeanConst& k, double Mf, double M2f, b
     W[LW_PMPB + f] = k.twoT * S4;
     return true;
 }
+// Same with the vacuum derivatives I1 = dI/dM, I2 = d2I/dM2 supplied by the caller (the warp-specialised kernel: the
+// controller lane computes the closed forms of x while the worker sweeps the mesh, and ships them in the mailbox).
+PNJL_HD void lean_flavour_fj_pre(int f, const LeanConst& k, double Mf, double M2f, bool fast, double I1, double I2, double* W) {
+    const double* S = W + LW_S;
+    const double a1 = S[ACC_S1 + f], a2a = S[ACC_S2A + f], a2b = S[ACC_S2B + f], a3 = S[ACC_S3 + f], a4 = S[ACC_S4 + f];
+    const double S1 = -3.0 * k.invT * Mf * a1;
+    const double s2b = fast ? (a1 - M2f * a2b) : a2b;
+    const double S2 = 3.0 * k.invT * k.invT * M2f * a2a - 3.0 * k.invT * s2b;
+    const double S3 = -3.0 * k.invT * Mf * a3;
+    const double S4 = -3.0 * k.invT * Mf * a4;
+    W[LW_PM + f] = k.twoT * S1 + k.Nc2 * I1;
+    W[LW_PMM + f] = k.twoT * S2 + k.Nc2 * I2;
+    W[LW_PMP + f] = k.twoT * S3;
+    W[LW_PMPB + f] = k.twoT * S4;
+}
 // Fused final pass: PM of flavour f from the F sums (finish_f_pre) and the vacuum integral itself for the thermo finish.
 PNJL_HD bool lean_flavour_ft(int f, const LeanConst& k, double Mf, double* W) {
     if (!vacuum_tame(k.Lambda, Mf)) return false;

@@ -52,6 +52,7 @@ struct MarchConst {
     int stage0, lean0, team0, int0;   // offsets (in doubles) into the dynamic shared memory: staging lines [16][32] | scratch
                                       // lines [16][LW_END] | team buffers [2][16][24] | ints: popped line [16], pass parity [16]
     int n, n_iso;
+    int lockstep;                     // 1: the teams of a CTA start every quadrature pass together (few lines per GPU, see march_phase_sync)
     double p2max, pc2max;
     SolverParams sp;
 };
@@ -92,6 +93,36 @@ __device__ __forceinline__ void mc_team_sync() {
     else __syncwarp();
 }
 
+// Phase alignment of the teams of a CTA (few lines per GPU: every team marches one line from start to end).  Left alone,
+// the teams drift apart: at any moment some sweep the mesh and others run their scalar finish, and the union of the code
+// in flight (~60 KB) overflows the SM's instruction cache, so that even the quadrature loop misses on 2/3 of its fetches.
+// Here the teams that currently hold a line start every pass together (a counting barrier in shared memory with dynamic
+// membership: join when a line is taken, leave when it is parked): sweeps coincide, the scalar phases that follow coincide
+// too and are fetched once for all teams.  The word packs (active teams << 16 | arrived teams).
+__device__ __forceinline__ void march_phase_join() {
+    atomicAdd(mc_ints() + 2 * kMarchWarps, 1 << 16);
+}
+__device__ __forceinline__ void march_phase_release(int* word, volatile int* gen) {
+    atomicAnd(word, (int)0xffff0000);
+    __threadfence_block();
+    atomicAdd((int*)gen, 1);
+}
+__device__ __forceinline__ void march_phase_leave() {
+    int* word = mc_ints() + 2 * kMarchWarps;
+    volatile int* gen = mc_ints() + 2 * kMarchWarps + 1;
+    const int old = atomicSub(word, 1 << 16);
+    const int active = (old >> 16) - 1;
+    if (active > 0 && (old & 0xffff) == active) march_phase_release(word, gen);     // everybody else is already waiting
+}
+__device__ __forceinline__ void march_phase_arrive_and_wait() {
+    int* word = mc_ints() + 2 * kMarchWarps;
+    volatile int* gen = mc_ints() + 2 * kMarchWarps + 1;
+    const int g = *gen;
+    const int old = atomicAdd(word, 1);
+    if ((old & 0xffff) + 1 == (old >> 16)) march_phase_release(word, gen);
+    else while (*gen == g) __nanosleep(64);
+}
+
 // One quadrature pass of kind `type` at (T, mu, xi, x); afterwards the reduced sums of the whole mesh are in W[LW_S ..] of every
 // warp of the team.  Partial sums of the team's warps are added in part order (lane-parallel), so the result does not depend
 // on which warp is faster; the team buffers are double-buffered by pass parity, so one named barrier per pass suffices.
@@ -99,6 +130,10 @@ __device__ __noinline__ void march_pass(int type, double T, double mu, double xi
     const int lane = mc_lane();
     double* stage = mc_stage();
     double* W = mc_W();
+    if (c_mc.lockstep) {
+        if (lane == 0 && mc_part() == 0) march_phase_arrive_and_wait();
+        mc_team_sync();
+    }
     __syncwarp();
     if (lane == 0) {
         stage[0] = T; stage[1] = mu; stage[2] = xi;
@@ -352,7 +387,7 @@ __global__ void __launch_bounds__(32 * kMarchWarps, 1) k_march(const double* __r
     const DeviceConfig* cfg = c_mc.cfg;
     const int n_mesh = 3 * c_mc.n + 2 * c_mc.n_iso;
     for (int i = threadIdx.x; i < n_mesh; i += blockDim.x) g_smem[i] = g_mesh[i];
-    if (threadIdx.x < 2 * kMarchWarps) mc_ints()[threadIdx.x] = 0;
+    if (threadIdx.x < 2 * kMarchWarps + 2) mc_ints()[threadIdx.x] = 0;
     __syncthreads();
     const int lane = mc_lane();
     const int parts = c_mc.parts;
@@ -385,6 +420,7 @@ __global__ void __launch_bounds__(32 * kMarchWarps, 1) k_march(const double* __r
             mc_team_sync();          // everybody has read the slot before the leader can overwrite it
         }
         if (line < 0) break;
+        if (c_mc.lockstep && part == 0 && lane == 0) march_phase_join();
         // ---- this line's parameters and parked tracker state ----
         LineState st;
         {
@@ -511,6 +547,7 @@ __global__ void __launch_bounds__(32 * kMarchWarps, 1) k_march(const double* __r
             if (!solved) march_generic_point(&cfg->pt, ti, muq_MeV, xi, a.n_T, a.T_MeV, st, rows);
         }
         // ---- park the line (or retire it) ----
+        if (c_mc.lockstep && part == 0 && lane == 0) march_phase_leave();
         if (part == 0 && lane == 0) {
             if (st.it_next < a.n_T) {
                 LineState* g = a.state + line;
@@ -526,5 +563,66 @@ __global__ void __launch_bounds__(32 * kMarchWarps, 1) k_march(const double* __r
                 atomicAdd(a.counters + 2, 1ULL);
             }
         }
+    }
+}
+
+// ---- independent points, one warp (team) per point ----------------------------------------------------------------
+// PNJL.solve / solve_multi at n independent (T, mu, xi) triples (ImplicitSolver.jl:211-328, :532-559): a team pulls a point
+// from a global counter and runs the whole cascade — up to six seeds, Newton, trust-region fallback — in its own warp(s)
+// through Solver<WarpEval>.  Nothing waits for a controller: with MultiSeed at every point (config 3) the passes of the
+// warp-specialised kernel starve behind its two controller warps' scalar cascade; here 16 warps per SM run 16 cascades.
+struct MarchPointArgs {
+    long long n;
+    const double* T_fm; const double* mu_fm; const double* xi;
+    int seed_mode; int n_seeds; const double* seeds;
+    double* records;
+    unsigned long long* counter;
+};
+
+__global__ void __launch_bounds__(32 * kMarchWarps, 1) k_march_points(const double* __restrict__ g_mesh, MarchPointArgs a) {
+    const int n_mesh = 3 * c_mc.n + 2 * c_mc.n_iso;
+    for (int i = threadIdx.x; i < n_mesh; i += blockDim.x) g_smem[i] = g_mesh[i];
+    if (threadIdx.x < 2 * kMarchWarps + 2) mc_ints()[threadIdx.x] = 0;
+    __syncthreads();
+    const int lane = mc_lane();
+    const int parts = c_mc.parts;
+    const int part = mc_part();
+    WarpEval ev;
+    Solver<WarpEval> sv(c_model, c_mc.sp, ev);
+    for (;;) {
+        long long i = 0;
+        if (part == 0) {
+            if (lane == 0) i = (long long)atomicAdd(a.counter, 1ULL);
+            i = __shfl_sync(0xffffffffu, i, 0);
+            if (parts > 1 && lane == 0) mc_ints()[mc_team()] = (int)(i < a.n ? i : -1);
+        }
+        if (parts > 1) {
+            mc_team_sync();
+            const int v = mc_ints()[mc_team()];
+            mc_team_sync();
+            i = v < 0 ? a.n : (long long)v;
+        }
+        if (i >= a.n) break;
+        const double T = a.T_fm[i], mu = a.mu_fm[i], x_i = a.xi[i];
+        sv.set_point(T, mu, x_i);
+        sv.n_fj = 0; sv.n_th = 0; sv.n_ft = 0;
+        sv.its_hint = 0;
+        PointRes r;
+        if (a.seed_mode == PNJL_SEED_EXPLICIT && a.n_seeds == 1) {
+            double x0[5];
+            copy5(x0, a.seeds + 5 * i);
+            sv.solve_with_fallback(x0, r);
+        } else if (a.seed_mode == PNJL_SEED_EXPLICIT) {
+            sv.solve_multi(a.seeds + 5 * (long long)a.n_seeds * i, a.n_seeds, r);
+        } else if (a.seed_mode == PNJL_SEED_AUTO) {
+            double x0[5];
+            default_seed(2, T, mu, x0);
+            sv.solve_with_fallback(x0, r);
+        } else {
+            sv.solve_multi(nullptr, 6, r);
+        }
+        double rec[PNJL_REC_DOUBLES];
+        fill_record(r, T, mu, x_i, sv.n_fj, sv.n_th, sv.n_ft, rec);
+        march_store_row(rec, a.records + (long long)PNJL_REC_DOUBLES * i);
     }
 }

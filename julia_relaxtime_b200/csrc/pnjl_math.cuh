@@ -286,6 +286,7 @@ PNJL_HD void fj_node(const PointCtx& c, double k2, double coef, double acc[kFJAc
 // ------------------------------------------------------------------------------------------------
 struct FastCtx {
     double nInvT;         // -1/T
+    double nInvT_l2e;     // -log2(e)/T
     double kapP, kapM;    // e^{+mu/T}, e^{-mu/T}
     double Phi, Phib, Phi3, Phib3, Phi2, Phib2, Phi4, Phib4;
 };
@@ -302,6 +303,7 @@ PNJL_HD bool one_log_ok(double T, double mu) { return fabs(mu) <= 60.0 * T; }
 
 PNJL_HD void make_fast_ctx(const PointCtx& c, FastCtx& f) {
     f.nInvT = -c.invT;
+    f.nInvT_l2e = -c.invT * 1.4426950408889634;
     // |mu|/T <= 200 here, so e^{-|mu|/T} is a normal number and its reciprocal is safe
     const double km = fast_exp_nonpos(-fabs(c.mu) * c.invT);
     const double kp = fast_rcp(km);
@@ -426,10 +428,12 @@ PNJL_HD void v_rsqrt(const double x[W], double y[W]) {
     for (int j = 0; j < W; ++j) e[j] = fma(-t[j], y[j], 1.0);
 #pragma unroll
     for (int j = 0; j < W; ++j) p[j] = fma(0.375, e[j], 0.5);
+    // y (1 + e p): the correction factor is a two-register DFMA (e, p, immediate 1) and the update a DMUL, where
+    // y + (y e) p needs a DFMA with three distinct register operands (3 FP64-pipe cycles instead of 2, see the note above)
 #pragma unroll
-    for (int j = 0; j < W; ++j) t[j] = y[j] * e[j];
+    for (int j = 0; j < W; ++j) t[j] = fma(e[j], p[j], 1.0);
 #pragma unroll
-    for (int j = 0; j < W; ++j) y[j] = fma(t[j], p[j], y[j]);
+    for (int j = 0; j < W; ++j) y[j] = y[j] * t[j];
 #else
     for (int j = 0; j < W; ++j) y[j] = 1.0 / sqrt(x[j]);
 #endif
@@ -454,13 +458,15 @@ PNJL_HD void v_rcp(const double x[W], double y[W]) {
 
 // (A table-driven exp — 32-entry 2^(j/32) table in shared memory + degree-6 polynomial, 11 FP64 instructions instead of
 // 15 — was measured 3 % SLOWER on cfg5: the LDS and the index arithmetic sit on the critical chain of the front end.)
+// exp(t[j]) for t[j] = E[j] * slope (<= 0); slope_l2e = slope * log2(e) is supplied by the caller (a per-pass constant), so that
+// the rounding step k = rint(t log2 e) is a DFMA of two registers and a constant instead of three registers.
 template <int W>
-PNJL_HD void v_exp_nonpos(const double t[W], double out[W]) {
+PNJL_HD void v_exp_nonpos(const double t[W], const double E[W], double slope_l2e, double out[W]) {
 #if defined(__CUDA_ARCH__)
     double kd[W], r[W], p[W];
     int k[W];
 #pragma unroll
-    for (int j = 0; j < W; ++j) kd[j] = fma(t[j], kExpR[0], kExpR[1]);
+    for (int j = 0; j < W; ++j) kd[j] = fma(E[j], slope_l2e, kExpR[1]);
 #pragma unroll
     for (int j = 0; j < W; ++j) k[j] = __double2loint(kd[j]);
 #pragma unroll
@@ -490,13 +496,18 @@ struct Species4 {
 };
 PNJL_HD void species4_fast(const FastCtx& fc, const double Y[4], Species4& o, bool need_q) {
     double g[4], q[4], inv[4];
+    // species visited in the order quark u, quark s, antiquark u, antiquark s: consecutive DFMAs then share their
+    // loop-invariant addend (3 Phi, then 3 Phibar; Phi, then Phibar) in the same operand slot, where the register reuse cache
+    // serves it and the instruction reads two fresh registers instead of three (2 pipe cycles instead of 3)
 #pragma unroll
-    for (int s = 0; s < 4; ++s) {
+    for (int q4 = 0; q4 < 4; ++q4) {
+        const int s = (q4 >> 1) | ((q4 & 1) << 1);
         const double P13 = (s & 1) ? fc.Phib3 : fc.Phi3, P2 = (s & 1) ? fc.Phi : fc.Phib;
         o.f[s] = f_fma(Y[s], f_fma(Y[s], f_fma(3.0, P2, Y[s]), P13), 1.0);
     }
 #pragma unroll
-    for (int s = 0; s < 4; ++s) {
+    for (int q4 = 0; q4 < 4; ++q4) {
+        const int s = (q4 >> 1) | ((q4 & 1) << 1);
         const double P1 = (s & 1) ? fc.Phib : fc.Phi, P2 = (s & 1) ? fc.Phi : fc.Phib;
         g[s] = f_fma(Y[s], f_fma(2.0, P2, Y[s]), P1);
     }
@@ -530,7 +541,7 @@ PNJL_HD void pair_front(const FastCtx& fc, double M2u, double M2s, double k2, do
     for (int j = 0; j < 2; ++j) E[j] = E2[j] * rE[j];
 #pragma unroll
     for (int j = 0; j < 2; ++j) t[j] = E[j] * fc.nInvT;
-    v_exp_nonpos<2>(t, e1);
+    v_exp_nonpos<2>(t, E, fc.nInvT_l2e, e1);
 #pragma unroll
     for (int j = 0; j < 2; ++j) { Y[2 * j] = e1[j] * fc.kapP; Y[2 * j + 1] = e1[j] * fc.kapM; }
 }
@@ -541,12 +552,10 @@ PNJL_HD void fj_pair_back(const FastCtx& fc, const double rE[2], const double Y[
                           double sh[5]) {
     Species4 sp;
     species4_fast(fc, Y, sp, true);
-    double nsum[2], Q[2], crE[2], crE2[2], u[4], v[4], s3[2], s4[2], gp[2], gpb[2], hpp[2], hppb[2], hpbpb[2];
-    // u = 1 - 3 n, v = 2 - 3 n = u + 1;  (q - 3 g n)/f = q/f - 3 n^2 = u n + (q - g)/f
+    double nsum[2], Q[2], crE[2], crE2[2], u[4], s3[2], s4[2], gp[2], gpb[2], hpp[2], hppb[2], hpbpb[2];
+    // u = 1 - 3 n, v = 2 - 3 n = u + 1;  (q - 3 g n)/f = q/f - 3 n^2 = u n + (q - g)/f;  r v = r u + r (one DFMA of two registers)
 #pragma unroll
     for (int s = 0; s < 4; ++s) u[s] = f_fma(-3.0, sp.n[s], 1.0);
-#pragma unroll
-    for (int s = 0; s < 4; ++s) v[s] = u[s] + 1.0;
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
         const int a = 2 * j, b = 2 * j + 1;   // quark, antiquark
@@ -554,8 +563,8 @@ PNJL_HD void fj_pair_back(const FastCtx& fc, const double rE[2], const double Y[
         Q[j] = f_fma(u[a], sp.n[a], sp.qf[a]) + f_fma(u[b], sp.n[b], sp.qf[b]);
         crE[j] = coef * rE[j];
         crE2[j] = crE[j] * rE[j];
-        s3[j] = f_fma(sp.r1[a], u[a], sp.r2[b] * v[b]);
-        s4[j] = f_fma(sp.r2[a], v[a], sp.r1[b] * u[b]);
+        s3[j] = f_fma(sp.r1[a], u[a], f_fma(sp.r2[b], u[b], sp.r2[b]));
+        s4[j] = f_fma(sp.r1[b], u[b], f_fma(sp.r2[a], u[a], sp.r2[a]));
         gp[j] = sp.r1[a] + sp.r2[b];
         gpb[j] = sp.r2[a] + sp.r1[b];
         hpp[j] = f_fma(sp.r1[a], sp.r1[a], sp.r2[b] * sp.r2[b]);

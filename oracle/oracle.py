@@ -115,6 +115,9 @@ class Oracle:
         L.oracle_scan_lines.argtypes = [C.POINTER(Config), C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                         C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_double), C.c_int32,
                                         C.POINTER(Table), C.POINTER(Out)]
+        L.oracle_scan_lines_from.argtypes = [C.POINTER(Config), C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                             C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_double), C.c_int32,
+                                             C.POINTER(Table), C.POINTER(C.c_double), C.c_double, C.POINTER(Out)]
         L.oracle_tmu_scan.argtypes = [C.POINTER(Config), C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                       C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_double), C.c_int32,
                                       C.POINTER(Table), C.POINTER(Out)]
@@ -196,8 +199,10 @@ class Oracle:
             out.per_seed = ps
         return out
 
-    def scan_lines(self, muq_MeV, xi, T_MeV, tables=None, table_idx=None):
-        """tables: list of (T_MeV[], mu_c_MeV[], T_CEP); table_idx[line] = index into tables or -1."""
+    def scan_lines(self, muq_MeV, xi, T_MeV, tables=None, table_idx=None, init_x=None, init_T_MeV=0.0):
+        """tables: list of (T_MeV[], mu_c_MeV[], T_CEP); table_idx[line] = index into tables or -1.
+        init_x [n_lines, 5] (optional): converged solutions of the point just before T_MeV[0] (at init_T_MeV) — the march
+        then starts in the middle of a line with the tracker state the full march would have there."""
         muq_MeV = np.ascontiguousarray(muq_MeV, dtype=np.float64)
         n_lines = muq_MeV.size
         xi = np.ascontiguousarray(np.broadcast_to(np.atleast_1d(xi), (n_lines,)), dtype=np.float64)
@@ -215,8 +220,12 @@ class Oracle:
         table_idx = np.ascontiguousarray(table_idx, dtype=np.int32)
         out = Result(n_lines * T_MeV.size)
         cs = out.c_struct()
-        self.lib.oracle_scan_lines(C.byref(self.cfg), n_lines, _dp(muq_MeV), _dp(xi), _ip(table_idx), T_MeV.size,
-                                   _dp(T_MeV), len(tables), ctabs, C.byref(cs))
+        ix = None
+        if init_x is not None:
+            init_x = np.ascontiguousarray(init_x, dtype=np.float64).reshape(n_lines, 5)
+            ix = _dp(init_x)
+        self.lib.oracle_scan_lines_from(C.byref(self.cfg), n_lines, _dp(muq_MeV), _dp(xi), _ip(table_idx), T_MeV.size,
+                                        _dp(T_MeV), len(tables), ctabs, ix, float(init_T_MeV), C.byref(cs))
         out.n_lines, out.n_T = n_lines, T_MeV.size
         return out
 

@@ -1180,9 +1180,23 @@ int32_t oracle_solve_points(const oracle_config* c, int64_t n, const double* T_f
 // T ascending; MultiSeed while the tracker has no previous (converged) solution, then
 // PhaseAwareContinuitySeed.  Units follow the script: T_fm = T_MeV/ħc, muq_fm = muq_MeV/ħc (:425-427);
 // tracker update! gets (T_MeV, muq_MeV) (:441).  Output index = line * n_T + iT.
+int32_t oracle_scan_lines_from(const oracle_config* c, int64_t n_lines, const double* muq_MeV, const double* xi,
+                               const int32_t* table_idx, int32_t n_T, const double* T_MeV, int32_t n_tables,
+                               const oracle_table* tables, const double* init_x, double init_T_MeV, const oracle_out* out);
+
 int32_t oracle_scan_lines(const oracle_config* c, int64_t n_lines, const double* muq_MeV, const double* xi,
                           const int32_t* table_idx, int32_t n_T, const double* T_MeV, int32_t n_tables,
                           const oracle_table* tables, const oracle_out* out) {
+    return oracle_scan_lines_from(c, n_lines, muq_MeV, xi, table_idx, n_T, T_MeV, n_tables, tables, nullptr, 0.0, out);
+}
+
+// The same march started in the middle of a line: init_x [n_lines][5] is the converged solution of the point just before
+// T_MeV[0] (at temperature init_T_MeV), handed to the tracker with update! (SeedStrategies.jl:851-856) exactly as the full
+// march would have left it.  Lets a timing sample cover a window of the T grid with the seeds — and therefore the evaluation
+// counts — of the complete line (bench.py's CPU arm).  init_x == NULL: a fresh line.
+int32_t oracle_scan_lines_from(const oracle_config* c, int64_t n_lines, const double* muq_MeV, const double* xi,
+                               const int32_t* table_idx, int32_t n_T, const double* T_MeV, int32_t n_tables,
+                               const oracle_table* tables, const double* init_x, double init_T_MeV, const oracle_out* out) {
     Consts k = consts_of(c);
     Mesh m = mesh_of(c);
     SolverOpts o = opts_of(c);
@@ -1201,6 +1215,7 @@ int32_t oracle_scan_lines(const oracle_config* c, int64_t n_lines, const double*
         Tracker tk;
         int ti = table_idx ? table_idx[l] : -1;
         tk.table = (ti >= 0 && ti < n_tables) ? &pts[ti] : &pts[n_tables];
+        if (init_x) tracker_update(tk, init_x + 5 * l, init_T_MeV, muq_MeV[l]);
         for (int it = 0; it < n_T; ++it) {
             double T_fm = T_MeV[it] / k.hbarc;
             double mu_fm = muq_MeV[l] / k.hbarc;

@@ -338,12 +338,15 @@ def test_isotropic_collapse_equals_full_mesh(p_num, t_num):
         assert err.max() <= 1e-9, (q, err.max(), int(err.argmax()), a[err.argmax(), q], b[err.argmax(), q])
     res = o.scan_lines(muq, np.zeros(16), Tg, tables, tidx)
     assert_state_parity(a, res, label="collapse-lines")
-    # an all-isotropic host batch is run in the layout that fits p_num nodes; a mixed batch keeps the handle's layout
-    # (the warp-specialised kernel reports 32 x parts lanes when it splits passes over several workers)
-    full_layout = (lambda v: v == 8) if p_num * t_num <= 96 else (lambda v: v >= 32)
-    assert ec.stats()["lanes_per_solve"] == 8 and full_layout(ef.stats()["lanes_per_solve"])
-    ec.scan_lines(muq[:4], np.array([0.0, 0.0, 0.2, 0.0]), Tg[:4], tidx[:4])
-    assert full_layout(ec.stats()["lanes_per_solve"])
+    # layouts: a small mesh runs in the 8-lane layout; at 64x16 lines go to the line-march kernel (512-thread CTAs), which
+    # sizes its teams for p_num nodes when the whole host batch is isotropic (16 lines on 2368 warps: one warp per line, as
+    # 64 nodes give a warp two nodes per lane) and for the full mesh otherwise (teams of several warps)
+    if p_num * t_num <= 96:
+        assert ec.stats()["lanes_per_solve"] == 8 and ef.stats()["lanes_per_solve"] == 8
+    else:
+        assert ec.stats()["threads"] == 512 and ec.stats()["lanes_per_solve"] == 32 and ef.stats()["lanes_per_solve"] > 32
+        ec.scan_lines(muq[:4], np.array([0.0, 0.0, 0.2, 0.0]), Tg[:4], tidx[:4])
+        assert ec.stats()["lanes_per_solve"] > 32
 
 
 @pytest.mark.parametrize("schedule,parts", [(0, 1), (0, 2), (0, 4), (0, 16), (1, 1), (2, 1), (2, 2)])

@@ -142,7 +142,9 @@ def test_gpu_thermo_derivatives_match_oracle_and_reference_tables(orc):
     assert abs(bulk["masses"][0, 0] * HBARC - 363.909334) < 1e-6 and abs(bulk["masses"][0, 2] * HBARC - 546.453381) < 1e-6
     assert abs(thr["dEpsilon_dT"][1] - 2.415916) < 2e-6
     one = td.bulk_viscosity_coefficients(T[1], mu[1], engine=e)
-    assert np.ndim(one["v_n_sq"]) == 0 and abs(one["v_n_sq"] - bulk["v_n_sq"][1]) < 1e-14
+    # scalar call vs the same point inside a batch: the host algebra (numpy reductions, batched 5x5 solves) groups its
+    # additions differently for different batch lengths, so the two agree to round-off of the difference quotients, not bitwise
+    assert np.ndim(one["v_n_sq"]) == 0 and abs(one["v_n_sq"] - bulk["v_n_sq"][1]) < 1e-12 * abs(bulk["v_n_sq"][1]) + 1e-13
     md = td.mass_derivatives(T[:2], mu[:2], engine=e)
     assert np.allclose(md["dM_dT"], bulk["dM_dT"][:2], rtol=0, atol=1e-13)
     with pytest.raises(NotImplementedError):
