@@ -283,6 +283,15 @@ int pnjl_eval_fj_host(pnjl_handle* h, int64_t n, const double* T_fm, const doubl
 int pnjl_eval_state_host(pnjl_handle* h, int64_t n, const double* T_fm, const double* mu_fm, const double* xi,
                          const double* x /* [n][5] */, double* out);
 
+/* The same plus the partial derivatives in (T, mu) at fixed x that the implicit differentiation of the gap equations needs
+ * (ThermoDerivatives.jl:80-109: dx/dtheta = -J^{-1} dF/dtheta; :186-250, :342-467), as closed-form quadrature sums over the
+ * same mesh (the reference gets them from ForwardDiff): out: [n][64] = the 48 doubles above, then
+ * dF/dT[5] 48, dF/dmu[5] 53, ds/dT 58, ds/dmu 59, dn_B/dT 60, dn_B/dmu 61 (n_B = sum_i rho_i / 3), 0, 0.
+ * julia_relaxtime_b200/thermo_derivatives.py solves the 5x5 systems and applies the reference's algebra. */
+#define PNJL_DERIV_DOUBLES 64
+int pnjl_eval_derivs_host(pnjl_handle* h, int64_t n, const double* T_fm, const double* mu_fm, const double* xi,
+                          const double* x /* [n][5] */, double* out);
+
 /* Accuracy self-test of the kernels' branch-free FP64 primitives (test hook):
  * which = 0: exp(x) for x in [-708, 0];  1: 1/x;  2: 1/sqrt(x)  (x normal, positive for 1 and 2). */
 int pnjl_selftest_math(pnjl_handle* h, int64_t n, const double* x, int32_t which, double* out);

@@ -94,6 +94,7 @@ def load():
     L.pnjl_scan_lines_couplings_host.argtypes = [H, C.c_int64, dp, dp, ip, C.c_int32, dp, dp, dp]
     L.pnjl_eval_fj_host.argtypes = [H, C.c_int64, dp, dp, dp, dp, dp]
     L.pnjl_eval_state_host.argtypes = [H, C.c_int64, dp, dp, dp, dp, dp]
+    L.pnjl_eval_derivs_host.argtypes = [H, C.c_int64, dp, dp, dp, dp, dp]
     L.pnjl_selftest_math.argtypes = [H, C.c_int64, dp, C.c_int32, dp]
     L.pnjl_get_stats.argtypes = [H, C.POINTER(_abi.PnjlStats)]
     L.pnjl_measure_fp64_peak.argtypes = [H, C.c_double, dp, dp]
@@ -113,7 +114,7 @@ EXPORTED_SYMBOLS = [
     "pnjl_scan_lines_device", "pnjl_scan_lines_device_indexed", "pnjl_ipc_alloc", "pnjl_ipc_open", "pnjl_ipc_close",
     "pnjl_ipc_free", "pnjl_set_oneloop_rule", "pnjl_effective_couplings_host",
     "pnjl_effective_couplings_device", "pnjl_scan_lines_couplings_host", "pnjl_dual_branch_host", "pnjl_dual_branch_device", "pnjl_tmu_scan_host", "pnjl_tmu_scan_device", "pnjl_eval_fj_host", "pnjl_eval_state_host", "pnjl_selftest_math", "pnjl_get_stats", "pnjl_measure_fp64_peak",
-    "pnjl_set_option", "pnjl_sizeof_config", "pnjl_sizeof_boundary", "pnjl_sizeof_stats", "pnjl_config_field_offset"]
+    "pnjl_eval_derivs_host", "pnjl_set_option", "pnjl_sizeof_config", "pnjl_sizeof_boundary", "pnjl_sizeof_stats", "pnjl_config_field_offset"]
 
 
 class PinnedArray:
@@ -339,6 +340,22 @@ class Engine:
                     pressure=out[:, 31].copy(), rho_norm=out[:, 32].copy(), entropy=out[:, 33].copy(),
                     energy=out[:, 34].copy(), rho=out[:, 35:38].copy(), n_q=out[:, 38:41].copy(),
                     n_qbar=out[:, 41:44].copy(), masses=out[:, 44:47].copy())
+
+    def eval_derivs(self, T_fm, mu_fm, xi, x):
+        """eval_state plus the closed-form partial derivatives in (T, mu) at fixed x (pnjl_eval_derivs_host): adds dF_dT [n, 5],
+        dF_dmu [n, 5], s_T, s_mu, nB_T, nB_mu."""
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, 5)
+        n = x.shape[0]
+        T_fm, mu_fm, xi = _abi.as_f64(T_fm, n), _abi.as_f64(mu_fm, n), _abi.as_f64(xi, n)
+        out = np.empty((n, 64))
+        self._check(self.L.pnjl_eval_derivs_host(self.h, n, _abi.dptr(T_fm), _abi.dptr(mu_fm), _abi.dptr(xi), _abi.dptr(x),
+                                                 _abi.dptr(out)), "pnjl_eval_derivs_host")
+        return dict(F=out[:, :5].copy(), J=out[:, 5:30].reshape(n, 5, 5).copy(), omega=out[:, 30].copy(),
+                    pressure=out[:, 31].copy(), rho_norm=out[:, 32].copy(), entropy=out[:, 33].copy(),
+                    energy=out[:, 34].copy(), rho=out[:, 35:38].copy(), n_q=out[:, 38:41].copy(),
+                    n_qbar=out[:, 41:44].copy(), masses=out[:, 44:47].copy(), dF_dT=out[:, 48:53].copy(),
+                    dF_dmu=out[:, 53:58].copy(), s_T=out[:, 58].copy(), s_mu=out[:, 59].copy(), nB_T=out[:, 60].copy(),
+                    nB_mu=out[:, 61].copy())
 
     # ---- device-pointer entry points (torch tensors are only used for their data_ptr) --------------
     def solve_points_device(self, d_T, d_mu, d_xi, d_records, seed_mode=_abi.SEED_MULTI, d_seeds=None, n_seeds=6,

@@ -123,7 +123,7 @@ struct GroupEval {
         return v;
     }
 
-    __device__ __noinline__ void fj(double T, double mu, double xi, const double x[5], double F[5], double J[25]) {
+    __device__ __noinline__ void fj(double T, double mu, double xi, const double x[5], double F[5], double J[25], double* gp2 = nullptr) {
         PointCtx c;
         make_ctx(*m, T, mu, xi, x, c);
         double acc[kFJAcc];
@@ -133,6 +133,20 @@ struct GroupEval {
 #pragma unroll
         for (int i = 0; i < kFJAcc; ++i) acc[i] = gsum(acc[i]);
         finish_fj(*m, c, x, acc, F, J, fast);
+        if (gp2) { gp2[0] = acc[ACC_GP]; gp2[1] = acc[ACC_GPB]; }
+    }
+
+    // Derivative pass (ThermoDerivatives.jl:80-109, :186-250): dF/dT, dF/dmu, ds/dtheta, dn_B/dtheta at fixed x -> out[16].
+    __device__ __noinline__ void dtheta(double T, double mu, double xi, const double x[5], double gp, double gpb, double out[16]) {
+        PointCtx c;
+        make_ctx(*m, T, mu, xi, x, c);
+        double acc[kDtAcc];
+        pass_begin();
+        dtheta_partial(c, mv, lane, G, acc);
+        pass_end();
+#pragma unroll
+        for (int i = 0; i < kDtAcc; ++i) acc[i] = gsum(acc[i]);
+        finish_dtheta(*m, c, x, acc, gp, gpb, out);
     }
 
     // Fused pass: F(x) and the Newton direction p = -J^{-1} F, with J and the 5x5 elimination in registers.
@@ -942,13 +956,13 @@ __global__ void __launch_bounds__(512, 1) k_eval_fj(const DeviceConfig* __restri
     __shared__ int s_done;
     stage_mesh<G>(g_mesh, 3 * cfg->n_nodes + 2 * cfg->n_iso, s_mesh, &s_done);
     GroupEval<G> ev = make_eval<G>(cfg, s_mesh, &s_done);
-    const int stride = with_thermo ? PNJL_STATE_DOUBLES : 30;
+    const int stride = with_thermo == 2 ? PNJL_DERIV_DOUBLES : (with_thermo ? PNJL_STATE_DOUBLES : 30);
     for (;;) {
         const long long i = next_task<G>(counter, ev);
         if (i >= n) break;
-        double xs[5], F[5], J[25];
+        double xs[5], F[5], J[25], gp2[2];
         copy5(xs, x + 5 * i);
-        ev.fj(T_fm[i], mu_fm[i], xi[i], xs, F, J);
+        ev.fj(T_fm[i], mu_fm[i], xi[i], xs, F, J, gp2);
         double* o = FJ + (long long)stride * i;
         if (ev.lane == 0) {
             for (int q = 0; q < 5; ++q) o[q] = F[q];
@@ -962,6 +976,13 @@ __global__ void __launch_bounds__(512, 1) k_eval_fj(const DeviceConfig* __restri
                 o[30] = th.omega; o[31] = th.pressure; o[32] = th.rho_norm; o[33] = th.entropy; o[34] = th.energy;
                 for (int q = 0; q < 3; ++q) { o[35 + q] = th.rho[q]; o[38 + q] = th.nq[q]; o[41 + q] = th.nqb[q]; o[44 + q] = th.M[q]; }
                 o[47] = 0.0;
+            }
+        }
+        if (with_thermo == 2) {
+            double d[16];
+            ev.dtheta(T_fm[i], mu_fm[i], xi[i], xs, gp2[0], gp2[1], d);
+            if (ev.lane == 0) {
+                for (int q = 0; q < 16; ++q) o[48 + q] = d[q];
             }
         }
     }
@@ -2162,7 +2183,7 @@ int pnjl_dual_branch_host(pnjl_handle* h, int64_t n_lines, const double* T_MeV, 
 
 static int eval_state_impl(pnjl_handle* h, int64_t n, const double* T, const double* mu, const double* xi, const double* x,
                            double* FJ, int with_thermo) {
-    const size_t stride = with_thermo ? PNJL_STATE_DOUBLES : 30;
+    const size_t stride = with_thermo == 2 ? PNJL_DERIV_DOUBLES : (with_thermo ? PNJL_STATE_DOUBLES : 30);
     if (!h) return fail(PNJL_ERR_ARG, "null handle");
     if (n <= 0) return n == 0 ? PNJL_OK : fail(PNJL_ERR_ARG, "n < 0");
     if (!T || !mu || !xi || !x || !FJ) return fail(PNJL_ERR_ARG, "null buffer");
@@ -2198,6 +2219,10 @@ int pnjl_eval_fj_host(pnjl_handle* h, int64_t n, const double* T, const double* 
 int pnjl_eval_state_host(pnjl_handle* h, int64_t n, const double* T, const double* mu, const double* xi, const double* x,
                          double* out) {
     return eval_state_impl(h, n, T, mu, xi, x, out, 1);
+}
+int pnjl_eval_derivs_host(pnjl_handle* h, int64_t n, const double* T, const double* mu, const double* xi, const double* x,
+                          double* out) {
+    return eval_state_impl(h, n, T, mu, xi, x, out, 2);
 }
 
 int pnjl_selftest_math(pnjl_handle* h, int64_t n, const double* x, int32_t which, double* out) {

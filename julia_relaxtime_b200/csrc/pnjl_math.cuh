@@ -1098,6 +1098,119 @@ PNJL_HD void finish_thermo(const Model& m, const PointCtx& c, const double x[5],
 }
 
 // ------------------------------------------------------------------------------------------------
+// Derivative pass: the partial derivatives in (T, mu) at FIXED x that the implicit differentiation of the gap equations
+// needs (ThermoDerivatives.jl:80-109: dx/dtheta = -J^{-1} dF/dtheta; :186-250, :342-467: ds/dtheta, dn/dtheta).  The
+// reference gets them from ForwardDiff through calculate_omega; here they are closed-form sums over the same mesh.
+// With a = (mu - E)/T, b = -(E + mu)/T:  da/dT = -a/T, db/dT = -b/T, da/dmu = 1/T, db/dmu = -1/T, and per species
+// dn/da = Q = q/f - 3 n^2,  d(y/f)/da = r1 (1 - 3n),  d(y^2/f)/da = r2 (2 - 3n)   (same pieces as the Jacobian pass).
+//   per flavour i:  A1_i = sum c (a Q+ + b Q-)/E,   B1_i = sum c (Q+ - Q-)/E          -> d(dP/dM_i)/dT, d(dP/dM_i)/dmu
+//   shared:         AG  = sum c (a r1+ u+ + b r2- v-),   BG  = sum c (r1+ u+ - r2- v-)  -> dF_Phi/dT,    dF_Phi/dmu
+//                   AGB = sum c (a r2+ v+ + b r1- u-),   BGB = sum c (r2+ v+ - r1- u-)  -> dF_Phibar/dT, dF_Phibar/dmu
+//                   A2Q = sum c (a^2 Q+ + b^2 Q-)   -> ds/dT,   AQD = sum c (a Q+ - b Q-)   -> ds/dmu = d(sum rho)/dT,
+//                   QQ  = sum c (Q+ + Q-)           -> d(sum rho)/dmu
+// (shared sums run over the three flavours).  General path only (floors and the a > 0 rescaling live): this pass runs once per
+// requested point, not inside the solve.
+// ------------------------------------------------------------------------------------------------
+constexpr int kDtAcc = 13;
+enum { DT_A1 = 0, DT_B1 = 3, DT_AG = 6, DT_BG = 7, DT_AGB = 8, DT_BGB = 9, DT_A2Q = 10, DT_AQD = 11, DT_QQ = 12 };
+
+template <int FL>
+PNJL_HD void dtheta_node(const PointCtx& c, double k2, double coef, double acc[kDtAcc]) {
+    const double E2 = k2 + c.M2[FL];
+    const double rE = f_rsqrt(E2);
+    const double E = E2 * rE;
+    const double a = (c.mu - E) * c.invT;
+    const double b = -(E + c.mu) * c.invT;
+    const Species sp = species_eval(a, c.Phi3, c.Phib3);
+    const Species sm = species_eval(b, c.Phib3, c.Phi3);
+    const double np = f_fma(c.Phi, sp.r1, f_fma(2.0 * c.Phib, sp.r2, sp.r3));
+    const double nm = f_fma(c.Phib, sm.r1, f_fma(2.0 * c.Phi, sm.r2, sm.r3));
+    const double qp = f_fma(c.Phi, sp.r1, f_fma(4.0 * c.Phib, sp.r2, 3.0 * sp.r3));
+    const double qm = f_fma(c.Phib, sm.r1, f_fma(4.0 * c.Phi, sm.r2, 3.0 * sm.r3));
+    const double Qp = f_fma(-3.0 * np, np, qp), Qm = f_fma(-3.0 * nm, nm, qm);
+    const double up = f_fma(-3.0, np, 1.0), vp = f_fma(-3.0, np, 2.0);
+    const double um = f_fma(-3.0, nm, 1.0), vm = f_fma(-3.0, nm, 2.0);
+    const double crE = coef * rE;
+    acc[DT_A1 + FL] = f_fma(crE, a * Qp + b * Qm, acc[DT_A1 + FL]);
+    acc[DT_B1 + FL] = f_fma(crE, Qp - Qm, acc[DT_B1 + FL]);
+    const double gP = sp.r1 * up, gM = sm.r2 * vm;      // d/da of the Phi-derivative pieces (quark, antiquark)
+    const double hP = sp.r2 * vp, hM = sm.r1 * um;      // same for Phibar
+    acc[DT_AG] = f_fma(coef, a * gP + b * gM, acc[DT_AG]);
+    acc[DT_BG] = f_fma(coef, gP - gM, acc[DT_BG]);
+    acc[DT_AGB] = f_fma(coef, a * hP + b * hM, acc[DT_AGB]);
+    acc[DT_BGB] = f_fma(coef, hP - hM, acc[DT_BGB]);
+    acc[DT_A2Q] = f_fma(coef, (a * a) * Qp + (b * b) * Qm, acc[DT_A2Q]);
+    acc[DT_AQD] = f_fma(coef, a * Qp - b * Qm, acc[DT_AQD]);
+    acc[DT_QQ] = f_fma(coef, Qp + Qm, acc[DT_QQ]);
+}
+
+PNJL_HD void dtheta_partial(const PointCtx& c, const MeshView& mv_in, int lane, int stride, double acc[kDtAcc]) {
+    const MeshView mv = select_mesh(mv_in, c.xi);
+#pragma unroll
+    for (int i = 0; i < kDtAcc; ++i) acc[i] = 0.0;
+    for (int k = lane; k < mv.n; k += stride) {
+        const double k2 = f_fma(c.xi, mv.pc2[k], mv.p2[k]);
+        const double cf = mv.coef[k];
+        dtheta_node<0>(c, k2, cf, acc);
+        dtheta_node<1>(c, k2, cf, acc);
+        dtheta_node<2>(c, k2, cf, acc);
+    }
+}
+
+// out[16]: dF/dT [5], dF/dmu [5], ds/dT, ds/dmu, dn_B/dT, dn_B/dmu (n_B = sum_i rho_i / 3), all at fixed x; [14], [15] = 0.
+// gp / gpb: the sums sum c (r1+ + r2-), sum c (r2+ + r1-) of the Jacobian pass at the same state (ACC_GP, ACC_GPB).
+PNJL_HD void finish_dtheta(const Model& m, const PointCtx& c, const double x[5], const double acc[kDtAcc], double gp, double gpb,
+                           double out[16]) {
+    const double T = c.T, iT = c.invT;
+    // d(dP/dM_i)/dtheta = -6 M_i dS1_i/dtheta,  dS1/dT = -A1/T,  dS1/dmu = B1/T
+    double PMT[3], PMm[3];
+    for (int i = 0; i < 3; ++i) {
+        PMT[i] = 6.0 * c.M[i] * iT * acc[DT_A1 + i];
+        PMm[i] = -6.0 * c.M[i] * iT * acc[DT_B1 + i];
+    }
+    const double g4 = -4.0 * m.G, k2 = 2.0 * m.K;
+    const double D[3][3] = {{g4, k2 * x[2], k2 * x[1]}, {k2 * x[2], g4, k2 * x[0]}, {k2 * x[1], k2 * x[0], g4}};
+    for (int j = 0; j < 3; ++j) {
+        out[j] = PMT[0] * D[0][j] + PMT[1] * D[1][j] + PMT[2] * D[2][j];
+        out[5 + j] = PMm[0] * D[0][j] + PMm[1] * D[1][j] + PMm[2] * D[2][j];
+    }
+    // U(T, Phi, Phibar) = T^4 [-1/2 A Phi Phibar + B ln v]: T-derivatives of U_Phi, U_Phibar and the second T-derivative of U
+    const double P = x[3], Pb = x[4];
+    const double t = m.T0 * iT;
+    const double A = m.a0 + m.a1 * t + m.a2 * (t * t);
+    const double B = m.b3 * (t * t * t);
+    const double iT2 = iT * iT;
+    const double dA = -m.a1 * m.T0 * iT2 - 2 * m.a2 * (m.T0 * m.T0) * (iT2 * iT);
+    const double dB = -3 * m.b3 * (m.T0 * m.T0 * m.T0) * (iT2 * iT2);
+    const double d2A = 2 * m.a1 * m.T0 * (iT2 * iT) + 6 * m.a2 * (m.T0 * m.T0) * (iT2 * iT2);
+    const double d2B = 12 * m.b3 * (m.T0 * m.T0 * m.T0) * (iT2 * iT2 * iT);
+    const double PPb = Pb * P;
+    const double v = 1 - 6 * PPb + 4 * (Pb * Pb * Pb + P * P * P) - 3 * (PPb * PPb);
+    const bool live = !(v <= 0.0) && !(v < kPolyakovEps);
+    const double lv = live ? log(v) : log(kPolyakovEps);
+    const double iv = live ? 1.0 / v : 0.0;
+    const double vP = -6 * Pb + 12 * P * P - 6 * P * Pb * Pb;
+    const double vPb = -6 * P + 12 * Pb * Pb - 6 * P * P * Pb;
+    const double T2 = T * T, T3 = T2 * T, T4 = T2 * T2;
+    const double gP0 = -0.5 * A * Pb + B * vP * iv, gPb0 = -0.5 * A * P + B * vPb * iv;         // U_Phi / T^4, U_Phibar / T^4
+    const double U_PT = 4 * T3 * gP0 + T4 * (-0.5 * dA * Pb + dB * vP * iv);
+    const double U_PbT = 4 * T3 * gPb0 + T4 * (-0.5 * dA * P + dB * vPb * iv);
+    const double w0 = -0.5 * A * PPb + B * lv, w1 = -0.5 * dA * PPb + dB * lv, w2 = -0.5 * d2A * PPb + d2B * lv;
+    const double U_TT = 12 * T2 * w0 + 8 * T3 * w1 + T4 * w2;
+    // F_Phi = 6 T GP - U_Phi:  dGP/dT = -AG/T, dGP/dmu = BG/T
+    out[3] = 6.0 * gp - 6.0 * acc[DT_AG] - U_PT;
+    out[4] = 6.0 * gpb - 6.0 * acc[DT_AGB] - U_PbT;
+    out[8] = 6.0 * acc[DT_BG];
+    out[9] = 6.0 * acc[DT_BGB];
+    out[10] = -U_TT + 6.0 * iT * acc[DT_A2Q];          // ds/dT at fixed x
+    out[11] = -6.0 * iT * acc[DT_AQD];                 // ds/dmu at fixed x
+    out[12] = -2.0 * iT * acc[DT_AQD];                 // dn_B/dT = (1/3) d(sum rho)/dT   (Maxwell: = (1/3) ds/dmu)
+    out[13] = 2.0 * iT * acc[DT_QQ];                   // dn_B/dmu = (1/3) (6/T) QQ
+    out[14] = 0.0;
+    out[15] = 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // 5x5 dense algebra
 // ------------------------------------------------------------------------------------------------
 // Solve A y = b by LU with partial pivoting.  false on an exactly-zero pivot.  Deliberately compact

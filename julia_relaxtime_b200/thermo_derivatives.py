@@ -1,18 +1,21 @@
-"""Host mirror of src/pnjl/derivatives/ThermoDerivatives.jl (first-order functions):
+"""Host mirror of src/pnjl/derivatives/ThermoDerivatives.jl:
 
-    mass_derivatives(T_fm, mu_fm; order=1, xi, p_num, t_num)                 :132-150
+    mass_derivatives(T_fm, mu_fm; order=1|2, xi, p_num, t_num)               :132-175
     thermo_derivatives(T_fm, mu_fm; xi, p_num, t_num)                        :186-250
     bulk_derivative_coeffs(T_fm, mu_fm; ...)                                 :252-262
     bulk_viscosity_coefficients(T_fm, mu_fm; xi, p_num, t_num)               :342-467
 
 The reference differentiates through the solve with ImplicitDifferentiation.jl (dx/dtheta = -J^-1 dF/dtheta, :80-109) and
-ForwardDiff on calculate_thermo / calculate_rho.  Here every quadrature runs on the GPU: one `solve` batch for the states,
-then ONE batch of `pnjl_eval_state_host` at the nine states (T, mu), (T +- h, +- 2h, mu), (T, mu +- k, +- 2k) per point with x
-held fixed; F, J, s and rho there give
-    J = dF/dx (analytic),   dF/dT, dF/dmu, ds/dT|x, ds/dmu|x, dn/dT|x, dn/dmu|x  (fourth-order central differences),
-    ds/dx = dF/dT and dn/dx = (1/3) dF/dmu  (symmetry of the mixed partials of P),
-and the rest is the reference's algebra.  Agreement with exact AD (the oracle): ~1e-10 relative (tests/test_thermo_derivatives.py).
-All functions take scalars or arrays (batched over points); xi may be an array too.
+ForwardDiff on calculate_thermo / calculate_rho.  Here every quadrature runs on the GPU and every first derivative is
+ANALYTIC: one `solve` batch for the states, then one `pnjl_eval_derivs_host` call at the solutions, whose derivative pass
+sums the closed-form partial derivatives of the integrand in (T, mu) at fixed x over the same mesh (csrc/pnjl_math.cuh,
+dtheta_node):
+    J = dF/dx,   dF/dT, dF/dmu,   ds/dT|x, ds/dmu|x, dn_B/dT|x, dn_B/dmu|x,
+    ds/dx = dF/dT and dn_B/dx = (1/3) dF/dmu  (symmetry of the mixed partials of P),
+and the rest is the reference's algebra (5x5 solves on the host).  Agreement with exact AD (the oracle): <= 1e-10 relative
+(tests/test_thermo_derivatives.py).  The second derivatives of mass_derivatives(order = 2) are fourth-order central
+differences of those analytic first derivatives along T and mu (re-solved at the shifted points, continuity-seeded):
+~1e-8 relative.  All functions take scalars or arrays (batched over points); xi may be an array too.
 """
 import numpy as np
 
@@ -40,40 +43,18 @@ def compute_masses_from_state(x, consts):
                      m_s0 - 4 * G * x[..., 2] + 2 * K * x[..., 0] * x[..., 1]], axis=-1)
 
 
-def _d4(f, h):
-    """f: [5, n, ...] at offsets (-2h, -h, 0, +h, +2h) -> fourth-order central first derivative."""
-    h = h.reshape((-1,) + (1,) * (f.ndim - 2))
-    return (f[0] - 8.0 * f[1] + 8.0 * f[3] - f[4]) / (12.0 * h)
-
-
-def implicit_derivatives(engine, T_fm, mu_fm, xi, x, rel_step=2e-4):
-    """Everything the functions below need at states x [n, 5] (normally the converged solutions)."""
+def implicit_derivatives(engine, T_fm, mu_fm, xi, x):
+    """Everything the functions below need at states x [n, 5] (normally the converged solutions): one batched GPU call."""
     x = np.ascontiguousarray(x, dtype=float).reshape(-1, 5)
     n = x.shape[0]
     T, mu, xi = A.as_f64(T_fm, n), A.as_f64(mu_fm, n), A.as_f64(xi, n)
-    hT = rel_step * T
-    hM = rel_step * np.maximum(T, np.abs(mu))
-    offs = (-2.0, -1.0, 0.0, 1.0, 2.0)
-    Ts = np.concatenate([T + o * hT for o in offs] + [T for o in offs])
-    Ms = np.concatenate([mu for o in offs] + [mu + o * hM for o in offs])
-    st = engine.eval_state(Ts, Ms, np.tile(xi, 10), np.tile(x, (10, 1)))
-
-    def grid(key):
-        a = st[key].reshape((10, n) + st[key].shape[1:])
-        return a[:5], a[5:]
-
-    FT, FM = grid("F")
-    sT, sM = grid("entropy")
-    rT, rM = grid("rho")
-    nT, nM = rT.sum(axis=-1) / 3.0, rM.sum(axis=-1) / 3.0
-    base = {k: v.reshape((10, n) + v.shape[1:])[2] for k, v in st.items()}
-    dF_dT, dF_dmu = _d4(FT, hT), _d4(FM, hM)
-    J = base["J"]
-    dx_dT = np.linalg.solve(J, -dF_dT[..., None])[..., 0]
-    dx_dmu = np.linalg.solve(J, -dF_dmu[..., None])[..., 0]
-    return dict(x=x, T=T, mu=mu, F=base["F"], J=J, P=base["pressure"], s=base["entropy"], rho_sum=base["rho"].sum(axis=-1),
-                rho_norm=base["rho_norm"], dF_dT=dF_dT, dF_dmu=dF_dmu, dx_dT=dx_dT, dx_dmu=dx_dmu,
-                s_T=_d4(sT, hT), s_mu=_d4(sM, hM), n_T=_d4(nT, hT), n_mu=_d4(nM, hM))
+    st = engine.eval_derivs(T, mu, xi, x)
+    J = st["J"]
+    dx_dT = np.linalg.solve(J, -st["dF_dT"][..., None])[..., 0]
+    dx_dmu = np.linalg.solve(J, -st["dF_dmu"][..., None])[..., 0]
+    return dict(x=x, T=T, mu=mu, F=st["F"], J=J, P=st["pressure"], s=st["entropy"], rho_sum=st["rho"].sum(axis=-1),
+                rho_norm=st["rho_norm"], dF_dT=st["dF_dT"], dF_dmu=st["dF_dmu"], dx_dT=dx_dT, dx_dmu=dx_dmu,
+                s_T=st["s_T"], s_mu=st["s_mu"], n_T=st["nB_T"], n_mu=st["nB_mu"])
 
 
 def _solve_states(engine, T, mu, xi):
@@ -111,12 +92,42 @@ def _out(scalar, res):
     return {k: (v[0] if isinstance(v, np.ndarray) else v) for k, v in res.items()}
 
 
-def mass_derivatives(T_fm, mu_fm, order=1, xi=0.0, p_num=64, t_num=8, engine=None):
-    if order != 1:
-        raise NotImplementedError("order must be 1 here (the reference's order = 2 nests ForwardDiff once more)")
+def _first_order_at(e, T, mu, xi, seeds):
+    """dM/dT, dM/dmu [n, 3] at (T, mu) with the solve started from `seeds` (continuity: neighbours of a solved point)."""
+    rec = e.solve_points(T, mu, xi, A.SEED_EXPLICIT, seeds.reshape(-1, 1, 5))
+    d = implicit_derivatives(e, T, mu, xi, rec[:, A.REC_X:A.REC_X + 5])
+    d["consts"] = e.consts
+    return _dM(d)
+
+
+def mass_derivatives(T_fm, mu_fm, order=1, xi=0.0, p_num=64, t_num=8, engine=None, rel_step=1e-3):
+    """order = 1: masses, dM_dT, dM_dmu.  order = 2 (ThermoDerivatives.jl:150-172) adds d2M_dT2, d2M_dTdmu, d2M_dmu2:
+    fourth-order central differences of the analytic first derivatives at (T +- h, +- 2h) and (mu +- k, +- 2k), each of the
+    eight neighbours re-solved from the centre's solution."""
+    if order not in (1, 2):
+        raise ValueError("order must be 1 or 2, got %r" % (order,))          # the reference: error("order must be 1 or 2, ...")
     scalar, d = _prepare(T_fm, mu_fm, xi, p_num, t_num, engine)
     dM_dT, dM_dmu = _dM(d)
-    return _out(scalar, dict(masses=compute_masses_from_state(d["x"], d["consts"]), dM_dT=dM_dT, dM_dmu=dM_dmu))
+    res = dict(masses=compute_masses_from_state(d["x"], d["consts"]), dM_dT=dM_dT, dM_dmu=dM_dmu)
+    if order == 2:
+        e = engine or _engine(p_num, t_num)
+        T, mu, x = d["T"], d["mu"], d["x"]
+        n = T.size
+        xi_a = A.as_f64(xi, n)
+        hT = rel_step * T
+        hM = rel_step * np.maximum(T, np.abs(mu))
+        offs = (-2.0, -1.0, 1.0, 2.0)
+        Ts = np.concatenate([T + o * hT for o in offs] + [T for _ in offs])
+        Ms = np.concatenate([mu for _ in offs] + [mu + o * hM for o in offs])
+        gT, gM = _first_order_at(e, Ts, Ms, np.tile(xi_a, 8), np.tile(x, (8, 1)))
+        gT, gM = gT.reshape(8, n, 3), gM.reshape(8, n, 3)
+
+        def d4(f, h):         # f at offsets (-2, -1, +1, +2) h
+            return (f[0] - 8.0 * f[1] + 8.0 * f[2] - f[3]) / (12.0 * h[:, None])
+        res["d2M_dT2"] = d4(gT[:4], hT)
+        res["d2M_dTdmu"] = 0.5 * (d4(gM[:4], hT) + d4(gT[4:], hM))       # both orders of differentiation, averaged
+        res["d2M_dmu2"] = d4(gM[4:], hM)
+    return _out(scalar, res)
 
 
 def _totals(d):

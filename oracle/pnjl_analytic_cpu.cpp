@@ -174,6 +174,20 @@ int hostsim_fj_step(const pnjl_config* c, const double* x, double T, double mu, 
     return ev.fj_step(T, mu, xi, x, F, pdir) ? 1 : 0;
 }
 
+// The derivative pass (dtheta_node / finish_dtheta of csrc/pnjl_math.cuh) at one state: out16 as pnjl_eval_derivs_host's tail.
+void hostsim_derivs(const pnjl_config* c, const double* x, double T, double mu, double xi, double* out16) {
+    Model m = model_of(c);
+    HostMesh mesh = mesh_of(c);
+    HostEval ev{&m, &mesh, c->isospin_symmetric};
+    PointCtx ctx;
+    make_ctx(m, T, mu, xi, x, ctx);
+    double acc[kFJAcc], dacc[kDtAcc], F[5], J[25];
+    const bool fast = fj_partial(m, c->isospin_symmetric != 0, ctx, x, ev.view(), 0, 1, acc);
+    finish_fj(m, ctx, x, acc, F, J, fast);
+    dtheta_partial(ctx, ev.view(), 0, 1, dacc);
+    finish_dtheta(m, ctx, x, dacc, acc[ACC_GP], acc[ACC_GPB], out16);
+}
+
 void hostsim_thermo(const pnjl_config* c, const double* x, double T, double mu, double xi, double* out17) {
     Model m = model_of(c);
     HostMesh mesh = mesh_of(c);

@@ -59,6 +59,13 @@ class HostSim:
         rc = fn(C.byref(self.cfg), _abi.dptr(x), C.c_double(T), C.c_double(mu), C.c_double(xi), _abi.dptr(F), _abi.dptr(p))
         return F, p, rc
 
+    def derivs(self, x, T, mu, xi):
+        """Closed-form partial derivatives in (T, mu) at fixed x: dF_dT[5], dF_dmu[5], s_T, s_mu, nB_T, nB_mu."""
+        x = _abi.as_f64(x)
+        o = np.zeros(16)
+        self.lib.hostsim_derivs(C.byref(self.cfg), _abi.dptr(x), C.c_double(T), C.c_double(mu), C.c_double(xi), _abi.dptr(o))
+        return dict(dF_dT=o[0:5].copy(), dF_dmu=o[5:10].copy(), s_T=o[10], s_mu=o[11], nB_T=o[12], nB_mu=o[13])
+
     def thermo(self, x, T, mu, xi):
         x = _abi.as_f64(x)
         o = np.zeros(17)

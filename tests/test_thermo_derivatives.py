@@ -1,7 +1,7 @@
 """ThermoDerivatives: the oracle (exact AD over (x, T, mu)) against the reference's committed
 data/outputs/results/pnjl/{bulk_viscosity,derivatives}_xi0.0.csv (p_num=24, t_num=8; the T = 150 MeV rows — the T = 160 MeV
 rows of those files sit on an unphysical root, M_u = -636 MeV, of the solver version that wrote them), and the GPU path
-(pnjl_eval_state_host + fourth-order differences) against the oracle."""
+(pnjl_eval_derivs_host: analytic partial derivatives in (T, mu) summed over the mesh, then -J^-1 dF/dtheta) against the oracle."""
 import numpy as np
 import pytest
 
@@ -72,18 +72,22 @@ class _HostEngine:
         self.hs = HostSim(orc.p_nodes, orc.p_w, orc.c_nodes, orc.c_w, max_iter=1000)
         self.consts = DEFAULT
 
-    def solve_points(self, T, mu, xi, seed_mode):
-        return self.hs.solve_points(T, mu, xi, seed_mode)
+    def solve_points(self, T, mu, xi, seed_mode, seeds=None):
+        return self.hs.solve_points(T, mu, xi, seed_mode, seeds)
 
-    def eval_state(self, T, mu, xi, x):
+    def eval_derivs(self, T, mu, xi, x):
         x = np.asarray(x, dtype=float).reshape(-1, 5)
         n = x.shape[0]
         out = dict(F=np.zeros((n, 5)), J=np.zeros((n, 5, 5)), entropy=np.zeros(n), pressure=np.zeros(n), rho=np.zeros((n, 3)),
-                   rho_norm=np.zeros(n))
+                   rho_norm=np.zeros(n), dF_dT=np.zeros((n, 5)), dF_dmu=np.zeros((n, 5)), s_T=np.zeros(n), s_mu=np.zeros(n),
+                   nB_T=np.zeros(n), nB_mu=np.zeros(n))
         for i in range(n):
             out["F"][i], out["J"][i] = self.hs.fj(x[i], T[i], mu[i], xi[i])
             th = self.hs.thermo(x[i], T[i], mu[i], xi[i])
             out["entropy"][i], out["pressure"][i], out["rho"][i], out["rho_norm"][i] = th["entropy"], th["pressure"], th["rho"], th["rho_norm"]
+            d = self.hs.derivs(x[i], T[i], mu[i], xi[i])
+            for k in ("dF_dT", "dF_dmu", "s_T", "s_mu", "nB_T", "nB_mu"):
+                out[k][i] = d[k]
         return out
 
 
@@ -98,15 +102,34 @@ def test_host_algebra_of_thermo_derivatives_matches_oracle_on_cpu(orc):
     thr = td.thermo_derivatives(T, mu, xi=xi, engine=e)
     _, d = _oracle_at(orc, T_MeV, mu_MeV, xi)
     nz = mu_MeV > 0
-    assert np.allclose(bulk["v_n_sq"], d["v_n_sq"], rtol=2e-8, atol=0)
-    assert np.allclose(bulk["dmuB_dT_sigma"][nz], d["dmuB_dT_sigma"][nz], rtol=2e-8, atol=0)
+    # every first derivative is analytic now: 1e-10 against the oracle's exact AD (2e-8 with the finite differences of round 1)
+    assert np.allclose(bulk["v_n_sq"], d["v_n_sq"], rtol=1e-10, atol=0)
+    assert np.allclose(bulk["dmuB_dT_sigma"][nz], d["dmuB_dT_sigma"][nz], rtol=1e-10, atol=0)
     for i, f in enumerate("uds"):
-        assert np.allclose(bulk["dM_dT"][:, i], d["dM_%s_dT" % f], rtol=2e-8, atol=1e-12)
-        assert np.allclose(thr["dM_dmu"][:, i], d["dM_%s_dmu" % f], rtol=2e-8, atol=1e-12)
+        assert np.allclose(bulk["dM_dT"][:, i], d["dM_%s_dT" % f], rtol=1e-10, atol=1e-13)
+        assert np.allclose(thr["dM_dmu"][:, i], d["dM_%s_dmu" % f], rtol=1e-10, atol=1e-13)
         assert np.allclose(bulk["masses"][:, i], d["M_" + f], rtol=1e-10, atol=0)
-    for a, b in (("dP_dT", "dP_dT"), ("dEpsilon_dT", "dEps_dT"), ("dEpsilon_dmu", "dEps_dmu"), ("dn_dmu", "dn_dmu"), ("energy", "eps")):
-        assert np.allclose(thr[a], d[b], rtol=2e-8, atol=1e-11), a
+    for a, b in (("dP_dT", "dP_dT"), ("dP_dmu", "dP_dmu"), ("dEpsilon_dT", "dEps_dT"), ("dEpsilon_dmu", "dEps_dmu"), ("dn_dT", "dn_dT"),
+                 ("dn_dmu", "dn_dmu"), ("energy", "eps")):
+        assert np.allclose(thr[a], d[b], rtol=1e-10, atol=1e-12), a
     assert abs(bulk["v_n_sq"][1] - 7.951898e-02) < 6e-9          # the reference's printed value
+    # order = 2 (ThermoDerivatives.jl:150-172): against central differences of the ORACLE's exact first derivatives
+    md = td.mass_derivatives(T[1:3], mu[1:3], order=2, xi=xi[1:3], engine=e)
+    h = 2e-4 * T[1:3]
+    k = 2e-4 * np.maximum(T[1:3], mu[1:3])
+    _, dp = _oracle_at(orc, (T[1:3] + h) * HBARC, mu_MeV[1:3], xi[1:3])
+    _, dm = _oracle_at(orc, (T[1:3] - h) * HBARC, mu_MeV[1:3], xi[1:3])
+    _, ep = _oracle_at(orc, T_MeV[1:3], (mu[1:3] + k) * HBARC, xi[1:3])
+    _, em = _oracle_at(orc, T_MeV[1:3], (mu[1:3] - k) * HBARC, xi[1:3])
+    for i, f in enumerate("uds"):
+        ref_TT = (dp["dM_%s_dT" % f] - dm["dM_%s_dT" % f]) / (2 * h)
+        ref_mm = (ep["dM_%s_dmu" % f] - em["dM_%s_dmu" % f]) / (2 * k)
+        ref_Tm = (dp["dM_%s_dmu" % f] - dm["dM_%s_dmu" % f]) / (2 * h)
+        assert np.allclose(md["d2M_dT2"][:, i], ref_TT, rtol=2e-5, atol=1e-8), (f, md["d2M_dT2"][:, i], ref_TT)
+        assert np.allclose(md["d2M_dmu2"][:, i], ref_mm, rtol=2e-5, atol=1e-8), (f, md["d2M_dmu2"][:, i], ref_mm)
+        assert np.allclose(md["d2M_dTdmu"][:, i], ref_Tm, rtol=2e-5, atol=1e-8), (f, md["d2M_dTdmu"][:, i], ref_Tm)
+    with pytest.raises(ValueError):
+        td.mass_derivatives(T[0], mu[0], order=3, engine=e)
 
 
 @pytest.mark.gpu
@@ -122,20 +145,21 @@ def test_gpu_thermo_derivatives_match_oracle_and_reference_tables(orc):
     thr = td.thermo_derivatives(T, mu, xi=xi, engine=e)
     x, d = _oracle_at(orc, T_MeV, mu_MeV, xi)
 
-    def close(a, b, rel=2e-8, floor=1e-9):
+    def close(a, b, rel=1e-10, floor=1e-3):
         return (np.abs(a - b) <= rel * np.abs(b) + floor * rel).all()
 
     nz = mu_MeV > 0
-    assert close(bulk["v_n_sq"], d["v_n_sq"]) and close(bulk["dmuB_dT_sigma"][nz], d["dmuB_dT_sigma"][nz])
+    # the two ratios divide by differences of products of derivatives: an order of magnitude of slack over the 1e-10 below
+    assert close(bulk["v_n_sq"], d["v_n_sq"], 1e-9) and close(bulk["dmuB_dT_sigma"][nz], d["dmuB_dT_sigma"][nz], 1e-9)
     assert close(bulk["s"], d["s"], 1e-10) and close(bulk["n_B"], d["n_B"], 1e-9, 1e-3)
     for i, f in enumerate("uds"):
         assert close(bulk["masses"][:, i], d["M_" + f], 1e-10)
-        assert close(bulk["dM_dT"][:, i], d["dM_%s_dT" % f], 2e-8, 1e-4)
-        assert close(bulk["dM_dmuB"][:, i], d["dM_%s_dmuB" % f], 2e-8, 1e-4)
-        assert close(thr["dM_dmu"][:, i], d["dM_%s_dmu" % f], 2e-8, 1e-4)
+        assert close(bulk["dM_dT"][:, i], d["dM_%s_dT" % f], 1e-10, 1e-3)
+        assert close(bulk["dM_dmuB"][:, i], d["dM_%s_dmuB" % f], 1e-10, 1e-3)
+        assert close(thr["dM_dmu"][:, i], d["dM_%s_dmu" % f], 1e-10, 1e-3)
     for a, b in (("dP_dT", "dP_dT"), ("dP_dmu", "dP_dmu"), ("dEpsilon_dT", "dEps_dT"), ("dEpsilon_dmu", "dEps_dmu"),
                  ("dn_dT", "dn_dT"), ("dn_dmu", "dn_dmu"), ("pressure", "P"), ("energy", "eps")):
-        assert close(thr[a], d[b], 2e-8, 1e-3), a
+        assert close(thr[a], d[b], 1e-10, 1e-2), a
     assert thr["converged"].all()
     # the reference's own numbers, straight from the GPU path
     assert abs(bulk["v_n_sq"][1] - 7.951898e-02) < 6e-9 and abs(bulk["dmuB_dT_sigma"][1] + 2.179307) < 2e-6
@@ -147,5 +171,12 @@ def test_gpu_thermo_derivatives_match_oracle_and_reference_tables(orc):
     assert np.ndim(one["v_n_sq"]) == 0 and abs(one["v_n_sq"] - bulk["v_n_sq"][1]) < 1e-12 * abs(bulk["v_n_sq"][1]) + 1e-13
     md = td.mass_derivatives(T[:2], mu[:2], engine=e)
     assert np.allclose(md["dM_dT"], bulk["dM_dT"][:2], rtol=0, atol=1e-13)
-    with pytest.raises(NotImplementedError):
-        td.mass_derivatives(T[0], mu[0], order=2, engine=e)
+    # order = 2: central differences of the oracle's exact first derivatives as the yardstick
+    m2 = td.mass_derivatives(T[1:4], mu[1:4], order=2, xi=xi[1:4], engine=e)
+    h = 2e-4 * T[1:4]
+    _, dp = _oracle_at(orc, (T[1:4] + h) * HBARC, mu_MeV[1:4], xi[1:4])
+    _, dm = _oracle_at(orc, (T[1:4] - h) * HBARC, mu_MeV[1:4], xi[1:4])
+    for i, f in enumerate("uds"):
+        ref_TT = (dp["dM_%s_dT" % f] - dm["dM_%s_dT" % f]) / (2 * h)
+        assert np.allclose(m2["d2M_dT2"][:, i], ref_TT, rtol=2e-5, atol=1e-8), (f, m2["d2M_dT2"][:, i], ref_TT)
+    assert set(m2) == {"masses", "dM_dT", "dM_dmu", "d2M_dT2", "d2M_dTdmu", "d2M_dmu2"}
