@@ -22,7 +22,8 @@ namespace pnjl {
 // Scratch line of one warp (doubles).  LW_S: the reduced sums of the pass in the layout the pass wrote them
 // (FJ: kFJAcc sums + fast flag at 20; fused: 5 F sums + 8 thermo sums).
 enum { LW_S = 0, LW_PM = 24, LW_PMM = 27, LW_PMP = 30, LW_PMPB = 33, LW_D = 36, LW_X = 45, LW_U = 50, LW_I0 = 56, LW_INV = 59,
-       LW_AUG = 64, LW_END = 96 };
+       LW_AUG = 64, LW_F = 96, LW_P = 101, LW_END = 112 };
+// LW_F: F[5] of the pass, LW_P: the Newton direction p[5] (results of the unified finish of the line-march kernel)
 // LW_U: U_P, U_Pb, U_PP, U_PPb, U_PbPb, (pad)     LW_I0: I(Lambda, M_f) per flavour (fused / thermo passes)
 
 struct LeanConst {           // per-pass uniform scalars every phase needs

@@ -162,114 +162,194 @@ __device__ __noinline__ void march_pass(int type, double T, double mu, double xi
     __syncwarp();
 }
 
-// ---- lane-parallel finishes (pnjl_lean.cuh) of the three kinds of pass; the sums are in W[LW_S ..] ----
-// Phase A.  KIND 0: Jacobian pass, 1: fused final pass, 2: thermo pass.  Returns false (uniformly) when a closed form is not
-// tame (Polyakov argument at its floor, absurd masses): the caller then takes the redundant cold version.
-template <int KIND>
-__device__ __forceinline__ bool lean_phase_a(const PointCtx& c, const double x[5], const LeanConst& k, UTerms& u) {
+// ---- the hot sweep ---------------------------------------------------------------------------------------------------
+// A Jacobian pass (WS_FJ) or a fused final pass (WS_FT) for the state every continuity point is in: on the integrand's fast
+// path, phi_u == phi_d bitwise, |mu|/T <= 60 (one logarithm per node) — the caller checks.  Same inline loops as
+// ws_worker_pass (fj_pair_fast / th_pair_fast<true, true>: identical sums), but ONE small function for both kinds with one
+// copy of the warp reduction, the per-point constants e^{+-mu/T} supplied by the caller, and everything in registers: what
+// the 16 desynchronised warps of an SM execute per pass has to stay inside the 32 KB instruction cache.
+__device__ __noinline__ void march_sweep(int type, double T, double mu, double xi, double x0, double x1, double x2, double x3, double x4,
+                                         double kapP, double kapM) {
+    const int lane = mc_lane();
+    const double x[5] = {x0, x1, x2, x3, x4};
+    PointCtx c;
+    make_ctx(c_model, T, mu, xi, x, c);
+    FastCtx fc;
+    fc.nInvT = -c.invT;
+    fc.nInvT_l2e = -c.invT * 1.4426950408889634;
+    fc.kapP = kapP; fc.kapM = kapM;
+    fc.Phi = c.Phi; fc.Phib = c.Phib;
+    fc.Phi3 = c.Phi3; fc.Phib3 = c.Phib3;
+    fc.Phi2 = 2.0 * c.Phi; fc.Phib2 = 2.0 * c.Phib;
+    fc.Phi4 = 4.0 * c.Phi; fc.Phib4 = 4.0 * c.Phib;
+    const int n = c_mc.n;
+    const bool iso = xi == 0.0 && c_mc.n_iso > 0;
+    const double* p2 = iso ? g_smem + 3 * n : g_smem;
+    const double* pc2 = iso ? p2 : g_smem + n;
+    const double* coef = iso ? g_smem + 3 * n + c_mc.n_iso : g_smem + 2 * n;
+    const int nn = iso ? c_mc.n_iso : n;
+    const int parts = c_mc.parts, part = mc_part();
+    const int stride = 32 * parts;
+    double acc[kFJAcc];
+    if (type == WS_FJ) {
+        double fu[5] = {0, 0, 0, 0, 0}, fs[5] = {0, 0, 0, 0, 0}, sh[5] = {0, 0, 0, 0, 0};
+#pragma unroll 1
+        for (int k = lane + 32 * part; k < nn; k += stride) {
+            const double k2 = f_fma(xi, pc2[k], p2[k]);
+            fj_pair_fast(fc, c.M2[0], c.M2[2], k2, coef[k], fu, fs, sh);
+        }
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            acc[3 * q + 0] = fu[q];
+            acc[3 * q + 1] = fu[q];
+            acc[3 * q + 2] = fs[q];
+            acc[15 + q] = sh[q];
+        }
+    } else {
+        double tu[4] = {0, 0, 0, 0}, ts[4] = {0, 0, 0, 0}, s1u = 0, s1s = 0, gsh[2] = {0, 0};
+#pragma unroll 1
+        for (int k = lane + 32 * part; k < nn; k += stride) {
+            const double k2 = f_fma(xi, pc2[k], p2[k]);
+            th_pair_fast<true, true>(fc, mu, c.M2[0], c.M2[2], k2, coef[k], tu, ts, s1u, s1s, gsh);
+        }
+        th_pair_finish(mu, tu, ts);
+        acc[0] = s1u; acc[1] = s1u; acc[2] = s1s; acc[3] = gsh[0]; acc[4] = gsh[1];
+        acc[kFtAcc + TH_NP + 0] = tu[0]; acc[kFtAcc + TH_NP + 1] = tu[0]; acc[kFtAcc + TH_NP + 2] = ts[0];
+        acc[kFtAcc + TH_NM + 0] = tu[1]; acc[kFtAcc + TH_NM + 1] = tu[1]; acc[kFtAcc + TH_NM + 2] = ts[1];
+        acc[kFtAcc + TH_L] = f_fma(2.0, tu[2], ts[2]);
+        acc[kFtAcc + TH_T] = f_fma(2.0, tu[3], ts[3]);
+#pragma unroll
+        for (int q = kFtAcc + kThAcc; q < kFJAcc; ++q) acc[q] = 0.0;
+    }
+    double* W = mc_W();
+    int* parity = mc_ints() + kMarchWarps + mc_warp();
+    double* base = g_smem + c_mc.team0 + (mc_team() * 2 + *parity) * parts * kBufStride;
+    __syncwarp();
+    warp_sum_store(acc, lane, parts == 1 ? W + LW_S : base + part * kBufStride);      // one copy of the shuffle network
+    if (parts == 1) {
+        if (lane == 0) W[LW_S + 20] = 1.0;
+        __syncwarp();
+        return;
+    }
+    mc_team_sync();
+    if (lane < kFJAcc) {
+        double v = base[lane];
+        for (int q = 1; q < parts; ++q) v += base[q * kBufStride + lane];
+        W[LW_S + lane] = v;
+    }
+    if (lane == 0) { W[LW_S + 20] = 1.0; *parity ^= 1; }
+    __syncwarp();
+}
+
+// ---- the unified lean finish -----------------------------------------------------------------------------------------
+// One function (one copy of every closed form) for the three kinds of pass whose sums are in W[LW_S ..]:
+//   kind 0 (Jacobian pass)  F -> W[LW_F ..], Newton direction p = -J^{-1} F -> W[LW_P ..]; returns 1, or 0 if a pivot was zero
+//   kind 1 (fused final)    F -> W[LW_F ..] and the thermodynamic functions straight into the record staging line
+//   kind 2 (thermo pass)    the thermodynamic functions only
+// Lane-parallel (pnjl_lean.cuh): lane f < 3 flavour f, lanes 3..11 the dM/dphi table, lane e < 30 one entry of [J | F], one
+// elimination step per pivot.  kinds 1, 2 return 1 when every thermodynamic function is finite (part of the physicality test).
+// Returns -1 (uniformly) when a closed form is not tame: the caller then takes the redundant cold versions.
+__device__ __noinline__ int march_finish(int kind, double T, double mu, double xi, double x0, double x1, double x2, double x3, double x4) {
     const int lane = mc_lane();
     double* W = mc_W();
+    const double x[5] = {x0, x1, x2, x3, x4};
+    PointCtx c;
+    make_ctx(c_model, T, mu, xi, x, c);
+    LeanConst k;
+    lean_consts(c_model, c.T, c.invT, k);
+    // phase A
     bool tame = polyakov_tame(c.Phi, c.Phib);
     if (lane < 3) {
         const double Mf = lane == 0 ? c.M[0] : (lane == 1 ? c.M[1] : c.M[2]);
         const double M2f = lane == 0 ? c.M2[0] : (lane == 1 ? c.M2[1] : c.M2[2]);
-        if (KIND == 0) tame = lean_flavour_fj(lane, k, Mf, M2f, W[LW_S + 20] != 0.0, W) && tame;
-        else if (KIND == 1) tame = lean_flavour_ft(lane, k, Mf, W) && tame;
-        else tame = lean_flavour_th(lane, k, Mf, W) && tame;
+        if (vacuum_tame(k.Lambda, Mf)) {
+            double I0, I1, I2;
+            vacuum_terms_t<true>(k.Lambda, Mf, I0, I1, I2);
+            if (kind == 0) lean_flavour_fj_pre(lane, k, Mf, M2f, W[LW_S + 20] != 0.0, I1, I2, W);
+            else if (kind == 1) W[LW_PM + lane] = k.twoT * (-3.0 * k.invT * Mf * W[LW_S + lane]) + k.Nc2 * I1;
+            W[LW_I0 + lane] = I0;
+        } else {
+            tame = false;
+        }
     } else if (lane < 12) {
         const int r = (lane - 3) / 3, j = (lane - 3) - 3 * r;
-        if (KIND != 2) lean_dtable(r, j, k, x, W);
+        if (kind != 2) lean_dtable(r, j, k, x, W);
     } else if (lane == 12) {
-        if (KIND != 2) {
+        if (kind != 2) {
 #pragma unroll
             for (int q = 0; q < 5; ++q) W[LW_X + q] = x[q];
         }
     }
     tame = __all_sync(0xffffffffu, tame);
-    if (!tame) return false;
-    polyakov_eval<true, KIND != 0>(c_model, c.T, c.invT, c.Phi, c.Phib, u);
-    if (KIND != 2 && lane == 13) {
-        W[LW_U + 0] = u.U_P; W[LW_U + 1] = u.U_Pb;
-        if (KIND == 0) { W[LW_U + 2] = u.U_PP; W[LW_U + 3] = u.U_PPb; W[LW_U + 4] = u.U_PbPb; }
-    }
-    __syncwarp();
-    return true;
-}
-
-// Jacobian pass: F(x) and the Newton direction p = -J^{-1} F.  1: ok, 0: a pivot was exactly zero, -1: not tame.
-__device__ __forceinline__ int lean_finish_fj(double T, double mu, double xi, const double x[5], double F[5], double p[5]) {
-    const int lane = mc_lane();
-    double* W = mc_W();
-    PointCtx c;
-    make_ctx(c_model, T, mu, xi, x, c);
-    LeanConst k;
-    lean_consts(c_model, c.T, c.invT, k);
+    if (!tame) return -1;
     UTerms u;
-    if (!lean_phase_a<0>(c, x, k, u)) return -1;
-    const int li = lane / 6, lc = lane - 6 * li;
-    double a = 0.0;
-    if (lane < 30) {
-        a = lean_aug_entry(li, lc, k, W, ACC_GP, ACC_GPB);
-        W[LW_AUG + lane] = a;
+    if (kind == 0) polyakov_eval<true, false>(c_model, c.T, c.invT, c.Phi, c.Phib, u);
+    else polyakov_eval<true, true>(c_model, c.T, c.invT, c.Phi, c.Phib, u);
+    if (kind != 2 && lane == 13) {
+        W[LW_U + 0] = u.U_P; W[LW_U + 1] = u.U_Pb; W[LW_U + 2] = u.U_PP; W[LW_U + 3] = u.U_PPb; W[LW_U + 4] = u.U_PbPb;
     }
     __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 5; ++i) F[i] = W[LW_AUG + 6 * i + 5];
-    bool ok = true;
+    int rc = 1;
+    if (kind != 2) {
+        // phase B: kind 0 all 30 entries of [J | F], kind 1 the right-hand side only (same code, other sum offsets)
+        const int li = lane / 6, lc = lane - 6 * li;
+        double a = 0.0;
+        if (lane < 30 && (kind == 0 || lc == 5)) {
+            a = lean_aug_entry(li, lc, k, W, kind == 0 ? ACC_GP : 3, kind == 0 ? ACC_GPB : 4);
+            W[LW_AUG + lane] = a;
+            if (lc == 5) W[LW_F + li] = a;
+        }
+        __syncwarp();
+        if (kind == 0) {
+            // phase C
+            bool ok = true;
 #pragma unroll 1
-    for (int step = 0; step < 5; ++step) {
-        double inv = 0.0, nxt = a;
-        if (lane < 30) nxt = lean_lu_step(step, li, lc, W, a, inv, ok);
-        __syncwarp();
-        if (lane < 30) { a = nxt; W[LW_AUG + lane] = a; }
-        if (lane == 0) W[LW_INV + step] = inv;
+            for (int step = 0; step < 5; ++step) {
+                double inv = 0.0, nxt = a;
+                if (lane < 30) nxt = lean_lu_step(step, li, lc, W, a, inv, ok);
+                __syncwarp();
+                if (lane < 30) { a = nxt; W[LW_AUG + lane] = a; }
+                if (lane == 0) W[LW_INV + step] = inv;
+                __syncwarp();
+            }
+            ok = __shfl_sync(0xffffffffu, (int)ok, 0) != 0;
+            double y[5];
+            lean_backsub(W, y);
+            if (lane < 5) {
+                const double yl = lane == 0 ? y[0] : (lane == 1 ? y[1] : (lane == 2 ? y[2] : (lane == 3 ? y[3] : y[4])));
+                W[LW_P + lane] = -yl;
+            }
+            __syncwarp();
+            return ok ? 1 : 0;
+        }
+    }
+    // thermodynamic functions (kinds 1, 2): finish_thermo_pre, written into the record staging line at their record offsets
+    {
+        double tacc[kThAcc], I0v[3];
+        const int off = kind == 1 ? kFtAcc : 0;
+#pragma unroll
+        for (int i = 0; i < kThAcc; ++i) tacc[i] = W[LW_S + off + i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) I0v[i] = W[LW_I0 + i];
+        Thermo th;
+        finish_thermo_pre(c_model, c, x, tacc, I0v, u, th);
+        bool fin = finite_d(th.omega) && finite_d(th.pressure) && finite_d(th.rho_norm) && finite_d(th.entropy) && finite_d(th.energy);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) fin = fin && finite_d(th.M[i]) && th.M[i] > 0.0;
+        rc = fin ? 1 : 0;
+        double* stage = mc_stage();
+        if (lane == 0) {
+            stage[PNJL_REC_OMEGA] = th.omega; stage[PNJL_REC_PRESSURE] = th.pressure; stage[PNJL_REC_RHO_NORM] = th.rho_norm;
+            stage[PNJL_REC_ENTROPY] = th.entropy; stage[PNJL_REC_ENERGY] = th.energy;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                stage[PNJL_REC_MASS + i] = th.M[i]; stage[PNJL_REC_NQ + i] = th.nq[i];
+                stage[PNJL_REC_NQBAR + i] = th.nqb[i]; stage[PNJL_REC_RHO + i] = th.rho[i];
+            }
+        }
         __syncwarp();
     }
-    ok = __shfl_sync(0xffffffffu, (int)ok, 0) != 0;
-    lean_backsub(W, p);
-#pragma unroll
-    for (int i = 0; i < 5; ++i) p[i] = -p[i];
-    return ok ? 1 : 0;
-}
-// Fused final pass: F(x) and the thermodynamic functions at x.  false: not tame.
-__device__ __forceinline__ bool lean_finish_ft(double T, double mu, double xi, const double x[5], double F[5], Thermo& th) {
-    const int lane = mc_lane();
-    double* W = mc_W();
-    PointCtx c;
-    make_ctx(c_model, T, mu, xi, x, c);
-    LeanConst k;
-    lean_consts(c_model, c.T, c.invT, k);
-    UTerms u;
-    if (!lean_phase_a<1>(c, x, k, u)) return false;
-    const int li = lane / 6, lc = lane - 6 * li;
-    if (lane < 30 && lc == 5) W[LW_AUG + lane] = lean_aug_entry(li, lc, k, W, 3, 4);
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 5; ++i) F[i] = W[LW_AUG + 6 * i + 5];
-    double tacc[kThAcc], I0v[3];
-#pragma unroll
-    for (int i = 0; i < kThAcc; ++i) tacc[i] = W[LW_S + kFtAcc + i];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) I0v[i] = W[LW_I0 + i];
-    finish_thermo_pre(c_model, c, x, tacc, I0v, u, th);
-    return true;
-}
-// Thermo pass.
-__device__ __forceinline__ bool lean_finish_th(double T, double mu, double xi, const double x[5], Thermo& th) {
-    double* W = mc_W();
-    PointCtx c;
-    make_ctx(c_model, T, mu, xi, x, c);
-    LeanConst k;
-    lean_consts(c_model, c.T, c.invT, k);
-    UTerms u;
-    if (!lean_phase_a<2>(c, x, k, u)) return false;
-    double tacc[kThAcc], I0v[3];
-#pragma unroll
-    for (int i = 0; i < kThAcc; ++i) tacc[i] = W[LW_S + i];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) I0v[i] = W[LW_I0 + i];
-    finish_thermo_pre(c_model, c, x, tacc, I0v, u, th);
-    return true;
+    return rc;
 }
 
 // Redundant-per-lane finishes (finish_fj / finish_f / finish_thermo with their libm fall-backs) for states that are not tame.
@@ -319,8 +399,21 @@ __device__ __noinline__ void cold_thermo(double T, double mu, double xi, const d
     finish_thermo(c_model, c, x, tacc, th);
 }
 
+// The thermodynamic functions march_finish left in the record staging line, as a Thermo (generic cascade only).
+__device__ __forceinline__ void thermo_from_stage(Thermo& th) {
+    const double* stage = mc_stage();
+    th.omega = stage[PNJL_REC_OMEGA]; th.pressure = stage[PNJL_REC_PRESSURE]; th.rho_norm = stage[PNJL_REC_RHO_NORM];
+    th.entropy = stage[PNJL_REC_ENTROPY]; th.energy = stage[PNJL_REC_ENERGY];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        th.M[i] = stage[PNJL_REC_MASS + i]; th.nq[i] = stage[PNJL_REC_NQ + i];
+        th.nqb[i] = stage[PNJL_REC_NQBAR + i]; th.rho[i] = stage[PNJL_REC_RHO + i];
+    }
+}
+
 // Evaluation policy of the generic cascade (Solver<WarpEval>: MultiSeed bootstrap, trust-region fallback, everything the
-// in-kernel fast path hands back).  Stateless: the context comes from threadIdx and constant memory.
+// in-kernel fast path hands back).  Stateless: the context comes from threadIdx and constant memory.  Sweeps go through the
+// general ws_worker_pass (every kind of state), finishes through march_finish with the cold versions as fall-back.
 struct WarpEval {
     __device__ __noinline__ void fj(double T, double mu, double xi, const double x[5], double F[5], double J[25]) {
         march_pass(WS_FJ, T, mu, xi, x[0], x[1], x[2], x[3], x[4]);
@@ -328,8 +421,11 @@ struct WarpEval {
     }
     __device__ __noinline__ bool fj_step(double T, double mu, double xi, const double x[5], double F[5], double p[5]) {
         march_pass(WS_FJ, T, mu, xi, x[0], x[1], x[2], x[3], x[4]);
-        const int rc = lean_finish_fj(T, mu, xi, x, F, p);
+        const int rc = march_finish(0, T, mu, xi, x[0], x[1], x[2], x[3], x[4]);
         if (rc < 0) return cold_fj_step(T, mu, xi, x, F, p);
+        const double* W = mc_W();
+#pragma unroll
+        for (int i = 0; i < 5; ++i) { F[i] = W[LW_F + i]; p[i] = W[LW_P + i]; }
         return rc != 0;
     }
     __device__ __noinline__ bool f_thermo(double T, double mu, double xi, const double x[5], double F[5], Thermo& th) {
@@ -338,12 +434,17 @@ struct WarpEval {
         const double k2max = c_mc.p2max + (xi > 0.0 ? xi * c_mc.pc2max : 0.0);
         if (!fast_path_ok(c.T, c.mu, c.Phi, c.Phib, k2max, c.M2)) return false;   // uniform over the team
         march_pass(WS_FT, T, mu, xi, x[0], x[1], x[2], x[3], x[4]);
-        if (!lean_finish_ft(T, mu, xi, x, F, th)) cold_f_thermo(T, mu, xi, x, F, th);
+        if (march_finish(1, T, mu, xi, x[0], x[1], x[2], x[3], x[4]) < 0) { cold_f_thermo(T, mu, xi, x, F, th); return true; }
+        const double* W = mc_W();
+#pragma unroll
+        for (int i = 0; i < 5; ++i) F[i] = W[LW_F + i];
+        thermo_from_stage(th);
         return true;
     }
     __device__ __noinline__ void thermo(double T, double mu, double xi, const double x[5], Thermo& th) {
         march_pass(WS_TH, T, mu, xi, x[0], x[1], x[2], x[3], x[4]);
-        if (!lean_finish_th(T, mu, xi, x, th)) cold_thermo(T, mu, xi, x, th);
+        if (march_finish(2, T, mu, xi, x[0], x[1], x[2], x[3], x[4]) < 0) { cold_thermo(T, mu, xi, x, th); return; }
+        thermo_from_stage(th);
     }
 };
 
@@ -441,7 +542,7 @@ __global__ void __launch_bounds__(32 * kMarchWarps, 1) k_march(const double* __r
             const int it = st.it_next;
             bool solved = false;
 #if PNJL_MARCH_LEAN
-            if (st.has_prev) {
+            if (st.has_prev && sp.isospin) {
                 // PhaseAwareContinuitySeed get_seed (SeedStrategies.jl:795-839) with a previous solution
                 const double Tm = a.T_MeV[it];
                 const double T = Tm / c_model.hbarc;
@@ -451,29 +552,43 @@ __global__ void __launch_bounds__(32 * kMarchWarps, 1) k_march(const double* __r
                 if (flip) seed_const(cur == PH_HADRON ? 0 : 1, x);
                 else copy5(x, st.prev);
                 const int hint = flip ? 0 : st.its_hint;
-                // ---- NLsolve newton_ (Solver::newton), common case only: every state on the integrand's fast path, every closed
-                //      form tame, F finite.  One pass site: kind = Jacobian pass or fused final pass (predicted), a mispredicted
-                //      final pass is followed by a Jacobian pass at the same x ("refresh").  Anything else -> generic cascade.
-                Thermo th;
+                // ---- NLsolve newton_ (Solver::newton), common case only: every state on the integrand's fast path with
+                //      phi_u == phi_d and |mu| <= 60 T, every closed form tame, F finite.  One pass site: kind = Jacobian pass or
+                //      fused final pass (predicted), a mispredicted final pass is followed by a Jacobian pass at the same x
+                //      ("refresh").  Anything else -> generic cascade, which redoes the point from its seed.
                 int n_fj = 0, n_th = 0, n_ft = 0, iters = 0, kind = WS_FJ;
-                bool xc = false, fc = false, have_th = false, nonsing = true, first = true, refresh = false, bail = false;
+                bool xc = false, fc = false, have_th = false, th_finite = false, nonsing = true, first = true, refresh = false;
+                bool bail = !one_log_ok(T, mu_fm) || !(T > 1e-300 && T < 1e300);
                 double res = 0.0;
                 const double k2max = c_mc.p2max + (xi > 0.0 ? xi * c_mc.pc2max : 0.0);
-                for (;;) {
+                // e^{+-mu/T}: per-point constants of the sweeps (make_fast_ctx's arithmetic)
+                double kapP = 1.0, kapM = 1.0;
+                if (!bail) {
+                    const double km = fast_exp_nonpos(-fabs(mu_fm) * fast_rcp(T));
+                    const double kp = fast_rcp(km);
+                    kapP = mu_fm >= 0.0 ? kp : km;
+                    kapM = mu_fm >= 0.0 ? km : kp;
+                }
+                const double* W = mc_W();
+                while (!bail) {
                     {
                         double M[3];
                         masses_of(c_model, x, M);
                         const double M2[3] = {M[0] * M[0], M[1] * M[1], M[2] * M[2]};
-                        if (!fast_path_ok(T, mu_fm, x[3], x[4], k2max, M2)) { bail = true; break; }
+                        if (!(x[0] == x[1]) || !fast_path_ok(T, mu_fm, x[3], x[4], k2max, M2)) { bail = true; break; }
                     }
-                    march_pass(kind, T, mu_fm, xi, x[0], x[1], x[2], x[3], x[4]);
+                    march_sweep(kind, T, mu_fm, xi, x[0], x[1], x[2], x[3], x[4], kapP, kapM);
+                    const int rc = march_finish(kind == WS_FJ ? 0 : 1, T, mu_fm, xi, x[0], x[1], x[2], x[3], x[4]);
+                    if (rc < 0) { bail = true; break; }
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) F[i] = W[LW_F + i];
                     if (kind == WS_FJ) {
-                        const int rc = lean_finish_fj(T, mu_fm, xi, x, F, p);
-                        if (rc < 0) { bail = true; break; }
+#pragma unroll
+                        for (int i = 0; i < 5; ++i) p[i] = W[LW_P + i];
                         nonsing = rc != 0;
                         ++n_fj;
                     } else {
-                        if (!lean_finish_ft(T, mu_fm, xi, x, F, th)) { bail = true; break; }
+                        th_finite = rc != 0;
                         ++n_ft;
                     }
                     if (!all_finite5(F)) { bail = true; break; }
@@ -497,7 +612,7 @@ __global__ void __launch_bounds__(32 * kMarchWarps, 1) k_march(const double* __r
                     }
                     ++iters;
                     if (!nonsing) { bail = true; break; }
-                    if (sp.isospin && x[0] == x[1]) p[1] = p[0];      // keep the exact u<->d symmetry of the equations
+                    p[1] = p[0];                                      // keep the exact u<->d symmetry of the equations (x[0] == x[1] here)
                     double pmax = 0.0;
 #pragma unroll
                     for (int i = 0; i < 5; ++i) { xold[i] = x[i]; x[i] = x[i] + p[i]; pmax = fmax(pmax, fabs(p[i])); }
@@ -505,42 +620,41 @@ __global__ void __launch_bounds__(32 * kMarchWarps, 1) k_march(const double* __r
                     const bool predict = sp.predict_tol > 0.0 && (pmax <= sp.xtol || (by_history ? iters == hint : res <= sp.predict_tol));
                     kind = predict ? WS_FT : WS_FJ;
                 }
-                if (!bail) {
-                    const double rfin = norm_inf5(F);
-                    // _nlsolve_with_tr_fallback (ImplicitSolver.jl:103-151): the trust-region fallback runs unless the primary solve
-                    // is f-converged with a finite residual <= residual_norm_max and a physical state -> generic cascade
-                    if (fc && finite_d(rfin) && rfin <= sp.residual_norm_max) {
-                        bool have = have_th;
-                        if (!have) {
-                            march_pass(WS_TH, T, mu_fm, xi, x[0], x[1], x[2], x[3], x[4]);
-                            have = lean_finish_th(T, mu_fm, xi, x, th);
-                            ++n_th;
-                        }
-                        bool phys = have && finite_d(x[3]) && finite_d(x[4]) && (-sp.phi_tol <= x[3] && x[3] <= 1 + sp.phi_tol) &&
-                                    (-sp.phi_tol <= x[4] && x[4] <= 1 + sp.phi_tol);
+                // _nlsolve_with_tr_fallback (ImplicitSolver.jl:103-151): the trust-region fallback runs unless the primary solve is
+                // f-converged with a finite residual <= residual_norm_max and a physical state -> anything else: generic cascade.
+                // A final pass that was not a fused one (x-converged on a Jacobian pass: rare) also goes there.
+                const double rfin = norm_inf5(F);
+                if (!bail && fc && have_th && th_finite && finite_d(rfin) && rfin <= sp.residual_norm_max &&
+                    finite_d(x[3]) && finite_d(x[4]) && (-sp.phi_tol <= x[3] && x[3] <= 1 + sp.phi_tol) &&
+                    (-sp.phi_tol <= x[4] && x[4] <= 1 + sp.phi_tol)) {
+                    solved = true;
+                    // the record: march_finish left the thermodynamic functions and the masses in the staging line; the rest here
+                    double* stage = mc_stage();
+                    if (part == 0) {
+                        __syncwarp();
+                        if (lane == 0) {
 #pragma unroll
-                        for (int i = 0; i < 3; ++i) phys = phys && finite_d(th.M[i]) && th.M[i] > 0.0;
-                        phys = phys && finite_d(th.omega) && finite_d(th.pressure) && finite_d(th.rho_norm) && finite_d(th.entropy) &&
-                               finite_d(th.energy);
-                        if (phys) {
-                            solved = true;
-                            PointRes r;
-                            copy5(r.x, x);
-                            r.th = th;
-                            r.res = rfin;
-                            r.it = iters;
-                            r.converged = true;
-                            r.status = PNJL_ST_CONVERGED | (flip ? PNJL_ST_PHASE_SWITCH : 0);
-                            double rec[PNJL_REC_DOUBLES];
-                            fill_record(r, T, mu_fm, xi, n_fj, n_th, n_ft, rec);
-                            march_store_row(rec, rows + (long long)PNJL_REC_DOUBLES * it);
-                            // tracker update! (SeedStrategies.jl:851-856) and the history for the next point
-                            copy5(st.prev, x);
-                            st.prev_phase = current_phase(&cfg->pt, ti, Tm, muq_MeV);
-                            st.its_hint = iters;
-                            st.it_next = it + 1;
+                            for (int i = 0; i < 5; ++i) stage[PNJL_REC_X + i] = x[i];
+                            const int status = PNJL_ST_CONVERGED | (flip ? PNJL_ST_PHASE_SWITCH : 0) |
+                                               (stage[PNJL_REC_MASS + 2] <= stage[PNJL_REC_MASS] ? PNJL_ST_MASS_INVERSION : 0);
+                            stage[PNJL_REC_RESNORM] = rfin;
+                            stage[PNJL_REC_ITER] = (double)iters;
+                            stage[PNJL_REC_STATUS] = (double)status;
+                            stage[PNJL_REC_NEVAL] = (double)n_fj;
+                            stage[PNJL_REC_NTHERMO] = (double)n_th;
+                            stage[PNJL_REC_T] = T; stage[PNJL_REC_MU] = mu_fm; stage[PNJL_REC_XI] = xi;
+                            stage[PNJL_REC_NFUSED] = (double)n_ft;
+                            stage[31] = 0.0;
                         }
+                        __syncwarp();
+                        rows[(long long)PNJL_REC_DOUBLES * it + lane] = stage[lane];
+                        __syncwarp();
                     }
+                    // tracker update! (SeedStrategies.jl:851-856) and the history for the next point
+                    copy5(st.prev, x);
+                    st.prev_phase = current_phase(&cfg->pt, ti, Tm, muq_MeV);
+                    st.its_hint = iters;
+                    st.it_next = it + 1;
                 }
             }
 #endif

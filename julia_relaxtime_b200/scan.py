@@ -91,6 +91,11 @@ class ScanOptions:
     p_num: int = 12
     t_num: int = 6
     max_iter: int = 40
+    resume_mode: str = "line"      # "line": a line with missing rows is re-marched from its first T (continuity seeding as in an
+                                   # uninterrupted run) and only the missing rows are appended;  "reference": like the script, the
+                                   # existing rows are skipped WITHOUT being solved, so the tracker is empty at the first missing T of a
+                                   # line, which is then bootstrapped with MultiSeed (run_gap_transport_scan.jl:417-443) — row for row
+                                   # what the reference writes when it resumes the same file
     T_values: Optional[Sequence[float]] = None     # explicit grids override the ranges
     muB_values: Optional[Sequence[float]] = None
     metadata: dict = field(default_factory=dict)
@@ -221,9 +226,15 @@ def solve_grid(grid: ScanGrid, p_num=12, t_num=6, max_iter=40, engine: Optional[
 def run_scan(opts: ScanOptions, engine: Optional[Engine] = None):
     """run_scan(opts) of run_gap_transport_scan.jl:362-550 for the equilibrium columns.
 
-    Resume works per line: a line is recomputed from its first T when any of its points is missing from the
-    existing file (continuity seeding makes later points depend on earlier ones), and only the missing rows
-    are appended — existing rows are never rewritten.  Returns the number of rows written."""
+    Resume (existing rows are never rewritten), two modes (ScanOptions.resume_mode):
+      "line" (default)  a line is recomputed from its first T when any of its points is missing from the existing file
+                        (continuity seeding makes later points depend on earlier ones) and only the missing rows are appended: the
+                        appended rows are those of an uninterrupted run.
+      "reference"       what the script does: rows already in the file are skipped without solving, so the line's tracker holds
+                        no previous solution at its first missing T — that point is bootstrapped with MultiSeed and continuity
+                        resumes from there.  Near the first-order line this can land on another branch / iteration count than
+                        "line" mode; it is the mode to use when the file is later compared row for row with one resumed upstream.
+    Returns the number of rows written."""
     out = opts.output
     d = os.path.dirname(out)
     if d and not os.path.isdir(d):
@@ -249,7 +260,28 @@ def run_scan(opts: ScanOptions, engine: Optional[Engine] = None):
             for k, v in meta.items():
                 io.write("# %s: %s\n" % (k, v))                 # scan_csv.jl:18-22
             io.write(",".join(HEADER) + "\n")
-        if todo:
+        if todo and opts.resume_mode == "reference":
+            # per line: the missing T values in ascending order form the march (a line's tracker never sees the skipped points)
+            e = engine if engine is not None else Engine(p_num=opts.p_num, t_num=opts.t_num, max_iter=opts.max_iter)
+            e.set_boundaries(grid.tables)
+            groups = {}
+            for l in todo:
+                miss = tuple(i for i, T in enumerate(grid.T_MeV)
+                             if (float(T), float(grid.muB_MeV[l]), float(grid.xi[l])) not in existing)
+                groups.setdefault(miss, []).append(l)
+            for miss, lines in groups.items():               # lines that miss the same T values share one launch
+                Tm = grid.T_MeV[list(miss)]
+                sel = np.asarray(lines)
+                rec = e.scan_lines(grid.muq_MeV[sel], grid.xi[sel], Tm, grid.table_idx[sel])
+                for j, l in enumerate(lines):
+                    cols = derived_columns(rec[j], Tm, grid.muq_MeV[l], grid.muB_MeV[l], grid.xi[l])
+                    for row in format_rows(cols, len(Tm)):
+                        io.write(row + "\n")
+                        written += 1
+                io.flush()
+        elif todo:
+            if opts.resume_mode != "line":
+                raise ValueError("resume_mode must be 'line' or 'reference'")
             rec = solve_grid(grid, opts.p_num, opts.t_num, opts.max_iter, engine, todo)
             for j, l in enumerate(todo):
                 cols = derived_columns(rec[j], grid.T_MeV, grid.muq_MeV[l], grid.muB_MeV[l], grid.xi[l])

@@ -104,6 +104,19 @@ def test_run_scan_reproduces_reference_csv(tmp_path):
     assert run_scan(opts) == 40
     again = read_scan_csv(out)
     assert len(again["T_MeV"]) == 406
+    # resume_mode="reference": rows in the file are skipped without solving, the first missing T of a line is bootstrapped with
+    # MultiSeed (what run_gap_transport_scan.jl does when it resumes); here the tail of the last lines is missing, far from
+    # the first-order region, so both modes must restore the same rows (the MultiSeed row to the selection tolerance)
+    open(out, "w").writelines(lines[:-40])
+    opts.resume_mode = "reference"
+    assert run_scan(opts) == 40
+    ref_mode = read_scan_csv(out)
+    assert len(ref_mode["T_MeV"]) == 406
+    for k in ("Phi", "m_u", "m_s", "omega_fm4inv"):
+        order_a = np.lexsort((again["T_MeV"], again["muB_MeV"], again["xi"]))
+        order_b = np.lexsort((ref_mode["T_MeV"], ref_mode["muB_MeV"], ref_mode["xi"]))
+        assert rel(ref_mode[k][order_b], again[k][order_a]).max() <= 1e-7, k
+    opts.resume_mode = "line"
     opts.overwrite = True
     assert run_scan(opts) == 406
 
