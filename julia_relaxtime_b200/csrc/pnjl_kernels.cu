@@ -1137,7 +1137,6 @@ struct pnjl_handle {
     int ws_workers = 14, ws_ctrl_warps = 2, ws_spw = 4, ws_slots = 0;
     int march_parts = 0;          // warps per team in k_march (0 = automatic)
     int march_quantum = 0;        // points per time slice in k_march (0 = automatic)
-    int march_lockstep = 0;       // phase alignment of the teams of a CTA in k_march (experiments: PNJL_MARCH_LOCKSTEP=1)
     bool iso_batch = false;       // option "isotropic_batch": the caller promises xi == 0 on every line (device entry points)
     bool iso_next = false;        // the next launch is all-isotropic (set by the host entry points, which see xi)
     DevBuf march_state, march_slots, march_counters;
@@ -1299,8 +1298,28 @@ int launch_points_ws(pnjl_handle* h, long long n, const double* T, const double*
     return launch_ws(h, t, st);
 }
 
-// Launch geometry of the line-march kernel.  Team size: one warp per line while there are at least half as many lines as
-// warps on the GPU; otherwise the largest power of two that still gives every line a team and every lane two nodes.
+// Shared-memory layout and launch constants of the line-march kernels; returns the dynamic shared memory size in bytes.
+static size_t march_layout(const pnjl_handle* h, int parts, MarchConst& mc) {
+    const int n_mesh = 3 * h->n_nodes + 2 * h->host_cfg.n_iso;
+    std::memset(&mc, 0, sizeof(mc));
+    mc.cfg = h->d_cfg;
+    mc.parts = parts;
+    for (mc.log2_parts = 0; (1 << mc.log2_parts) < parts; ++mc.log2_parts) {}
+    mc.stage0 = (n_mesh + 1) & ~1;
+    mc.lean0 = mc.stage0 + kMarchWarps * kStageDoubles;
+    mc.team0 = mc.lean0 + kMarchWarps * LW_END;
+    mc.cmd0 = mc.team0 + kMarchWarps * kBufStride;
+    mc.red0 = mc.cmd0 + kMarchWarps * kCmdDoubles;
+    mc.n = h->n_nodes; mc.n_iso = h->host_cfg.n_iso;
+    mc.p2max = h->host_cfg.p2max; mc.pc2max = h->host_cfg.pc2max;
+    mc.sp = h->host_cfg.sp;
+    return sizeof(double) * (size_t)(mc.red0 + kMarchWarps * kFJAcc * kRedStride);
+}
+
+// Launch geometry of the line-march kernel.  Team size: one warp per line while the GPU holds at least 3/4 as many lines
+// as warps; below that the teams grow (a leader and 1, 3, ... followers that only sweep) as long as there are fewer than
+// 1.5 teams' worth of lines per team slot and every lane keeps two nodes.  Measured on 1/2, 1/4, 1/8 shares of config 5
+// (4096 / 2048 / 1024 lines on 2368 warps): 1, 2 and 4 warps per team are the fastest there; surplus lines are time-sliced.
 int launch_march(pnjl_handle* h, long long n_lines, const double* muq, const double* xi, const int* tidx, int n_T,
                  const double* T, double* rec, cudaStream_t st) {
     const long long total_warps = (long long)h->sm_count * kMarchWarps;
@@ -1308,7 +1327,7 @@ int launch_march(pnjl_handle* h, long long n_lines, const double* muq, const dou
     h->iso_next = false;
     const int n_eff = iso ? h->host_cfg.n_iso : h->n_nodes;
     int parts = 1;
-    while (parts < kMarchWarps && n_lines * 2 * parts <= total_warps && n_eff / (64 * parts) >= 2) parts *= 2;
+    while (parts < kMarchWarps && n_lines * 2 * parts <= 3 * total_warps && n_eff / (64 * parts) >= 2) parts *= 2;
     if (h->march_parts > 0) parts = h->march_parts;
     if (parts != 1 && parts != 2 && parts != 4 && parts != 8 && parts != 16) return fail(PNJL_ERR_ARG, "march_parts must be 1, 2, 4, 8 or 16");
     const long long n_teams = total_warps / parts;
@@ -1327,20 +1346,8 @@ int launch_march(pnjl_handle* h, long long n_lines, const double* muq, const dou
     a.state = (LineState*)h->march_state.p;
     a.slots = (int*)h->march_slots.p;
     a.counters = (unsigned long long*)h->march_counters.p;
-    const int n_mesh = 3 * h->n_nodes + 2 * h->host_cfg.n_iso;
     MarchConst mc;
-    std::memset(&mc, 0, sizeof(mc));
-    mc.cfg = h->d_cfg;
-    mc.parts = parts;
-    mc.stage0 = (n_mesh + 1) & ~1;
-    mc.lean0 = mc.stage0 + kMarchWarps * kStageDoubles;
-    mc.team0 = mc.lean0 + kMarchWarps * LW_END;
-    mc.int0 = mc.team0 + 2 * kMarchWarps * kBufStride;
-    mc.n = h->n_nodes; mc.n_iso = h->host_cfg.n_iso;
-    mc.p2max = h->host_cfg.p2max; mc.pc2max = h->host_cfg.pc2max;
-    mc.sp = h->host_cfg.sp;
-    mc.lockstep = h->march_lockstep > 0 ? 1 : 0;     // measured (profiles/r02_*): no gain with few lines, large loss otherwise
-    const size_t smem = sizeof(double) * (size_t)(mc.int0 + kMarchWarps + 2);     // 2 x 16 + 2 ints at the end
+    const size_t smem = march_layout(h, parts, mc);
     cudaFuncAttributes fa;
     CUDA_TRY(cudaFuncGetAttributes(&fa, k_march));
     if (smem > 40 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_march, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1368,27 +1375,15 @@ int launch_march_points(pnjl_handle* h, long long n, const double* T, const doub
                         int n_seeds, const double* seeds, double* rec, cudaStream_t st) {
     const long long total_warps = (long long)h->sm_count * kMarchWarps;
     int parts = 1;
-    while (parts < kMarchWarps && n * 2 * parts <= total_warps && h->n_nodes / (64 * parts) >= 2) parts *= 2;
+    while (parts < kMarchWarps && n * 2 * parts <= 3 * total_warps && h->n_nodes / (64 * parts) >= 2) parts *= 2;
     if (h->march_parts > 0) parts = h->march_parts;
     if (parts != 1 && parts != 2 && parts != 4 && parts != 8 && parts != 16) return fail(PNJL_ERR_ARG, "march_parts must be 1, 2, 4, 8 or 16");
     MarchPointArgs a;
     std::memset(&a, 0, sizeof(a));
     a.n = n; a.T_fm = T; a.mu_fm = mu; a.xi = xi; a.seed_mode = seed_mode; a.n_seeds = n_seeds; a.seeds = seeds; a.records = rec;
     a.counter = h->d_counter;
-    const int n_mesh = 3 * h->n_nodes + 2 * h->host_cfg.n_iso;
     MarchConst mc;
-    std::memset(&mc, 0, sizeof(mc));
-    mc.cfg = h->d_cfg;
-    mc.parts = parts;
-    mc.stage0 = (n_mesh + 1) & ~1;
-    mc.lean0 = mc.stage0 + kMarchWarps * kStageDoubles;
-    mc.team0 = mc.lean0 + kMarchWarps * LW_END;
-    mc.int0 = mc.team0 + 2 * kMarchWarps * kBufStride;
-    mc.n = h->n_nodes; mc.n_iso = h->host_cfg.n_iso;
-    mc.p2max = h->host_cfg.p2max; mc.pc2max = h->host_cfg.pc2max;
-    mc.sp = h->host_cfg.sp;
-    mc.lockstep = 0;
-    const size_t smem = sizeof(double) * (size_t)(mc.int0 + kMarchWarps + 2);
+    const size_t smem = march_layout(h, parts, mc);
     cudaFuncAttributes fa;
     CUDA_TRY(cudaFuncGetAttributes(&fa, k_march_points));
     if (smem > 40 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_march_points, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1492,11 +1487,11 @@ int dispatch_lines(pnjl_handle* h, int layout, long long n_lines, const double* 
         case 16: return launch_lines<16>(h, n_lines, muq, xi, tidx, n_T, T, rec, st, mode);
         default: {
             // Which organisation marches the lines (measured on cfg5 / cfg4 shares, profiles/r02_*): the line-march kernel when
-            // a pass is short (all-isotropic batch: p_num nodes) or the GPU holds few lines (<= 10 per SM: multi-GPU shares of a
-            // fixed grid), where the latency of a pass decides; the warp-specialised kernel when there are enough lines to hide
+            // a pass is short (all-isotropic batch: p_num nodes) or the GPU holds few lines (<= 20 per SM: multi-GPU shares of a
+            // fixed grid; 2048 lines: 102 ms against 132, 4096 lines: a tie at 179 ms, 8192 lines: 343 against 309), where the latency of a pass decides; the warp-specialised kernel when there are enough lines to hide
             // its controller step (its workers' small code stays inside the instruction cache).
             const bool iso = (h->iso_next || h->iso_batch) && h->host_cfg.n_iso > 0;
-            const bool march = mode == 0 && (h->schedule == 3 || (h->schedule == 2 && (iso || n_lines <= 10LL * h->sm_count)));
+            const bool march = mode == 0 && (h->schedule == 3 || (h->schedule == 2 && (iso || n_lines <= 20LL * h->sm_count)));
             if (march) return launch_march(h, n_lines, muq, xi, tidx, n_T, T, rec, st);
             h->iso_next = false;
             if (h->schedule >= 1) return launch_lines_ws(h, n_lines, muq, xi, tidx, n_T, T, rec, st, mode);
@@ -1689,7 +1684,6 @@ int pnjl_create(const pnjl_config* c, pnjl_handle** out) {
         h->schedule = es ? atoi(es) : (c->schedule == 1 ? 0 : (c->schedule == 2 ? 1 : (c->schedule == 3 ? 3 : 2)));
         if (getenv("PNJL_MARCH_PARTS")) h->march_parts = atoi(getenv("PNJL_MARCH_PARTS"));
         if (getenv("PNJL_MARCH_Q")) h->march_quantum = atoi(getenv("PNJL_MARCH_Q"));
-        if (getenv("PNJL_MARCH_LOCKSTEP")) h->march_lockstep = atoi(getenv("PNJL_MARCH_LOCKSTEP"));
         if (getenv("PNJL_WS_WORKERS")) h->ws_workers = atoi(getenv("PNJL_WS_WORKERS"));
         if (getenv("PNJL_WS_CTRL")) h->ws_ctrl_warps = atoi(getenv("PNJL_WS_CTRL"));
         if (getenv("PNJL_WS_SPW")) h->ws_spw = atoi(getenv("PNJL_WS_SPW"));

@@ -48,11 +48,10 @@ struct MarchArgs {
 // a context object in (local) memory and the finish code takes its constants as constant-bank operands.
 struct MarchConst {
     const DeviceConfig* cfg;
-    int parts;                        // warps per team (1, 2, 4, 8 or 16)
-    int stage0, lean0, team0, int0;   // offsets (in doubles) into the dynamic shared memory: staging lines [16][32] | scratch
-                                      // lines [16][LW_END] | team buffers [2][16][24] | ints: popped line [16], pass parity [16]
+    int parts, log2_parts;            // warps per team (1, 2, 4, 8 or 16)
+    int stage0, lean0, team0, cmd0, red0;   // offsets (in doubles) into the dynamic shared memory: staging lines [16][32] | scratch
+                                      // lines [16][LW_END] | partial sums [16][24] | command blocks [16][16] | reduction scratch [16][20][33]
     int n, n_iso;
-    int lockstep;                     // 1: the teams of a CTA start every quadrature pass together (few lines per GPU, see march_phase_sync)
     double p2max, pc2max;
     SolverParams sp;
 };
@@ -77,11 +76,17 @@ __global__ void k_march_init(MarchArgs a) {
 // ---- per-warp context, recomputed where it is needed ----
 __device__ __forceinline__ int mc_lane() { return threadIdx.x & 31; }
 __device__ __forceinline__ int mc_warp() { return threadIdx.x >> 5; }
-__device__ __forceinline__ int mc_part() { return mc_warp() & (c_mc.parts - 1); }
-__device__ __forceinline__ int mc_team() { return mc_warp() / c_mc.parts; }
+// Team t = warps [t parts, (t + 1) parts); which of them is part 0 (the leader) rotates with t so that the leaders — the warps
+// that run the scalar phases — are spread evenly over the four schedulers of the SM (warp w issues on scheduler w & 3):
+// parts 2: leaders on schedulers 0, 2, 1, 3, ...; parts >= 4: 0, 3, 2, 1.
+__device__ __forceinline__ int mc_team() { return mc_warp() >> c_mc.log2_parts; }
+__device__ __forceinline__ int mc_part() {
+    const int t = mc_team();
+    const int rot = c_mc.parts >= 4 ? t : (t >> 1);
+    return (mc_warp() + rot) & (c_mc.parts - 1);
+}
 __device__ __forceinline__ double* mc_stage() { return g_smem + c_mc.stage0 + mc_warp() * kStageDoubles; }
 __device__ __forceinline__ double* mc_W() { return g_smem + c_mc.lean0 + mc_warp() * LW_END; }
-__device__ __forceinline__ int* mc_ints() { return reinterpret_cast<int*>(g_smem + c_mc.int0); }
 __device__ __forceinline__ void mc_mesh(MeshView& mv) {
     const int n = c_mc.n;
     mv.p2 = g_smem; mv.pc2 = g_smem + n; mv.coef = g_smem + 2 * n; mv.n = n;
@@ -93,83 +98,73 @@ __device__ __forceinline__ void mc_team_sync() {
     else __syncwarp();
 }
 
-// Phase alignment of the teams of a CTA (few lines per GPU: every team marches one line from start to end).  Left alone,
-// the teams drift apart: at any moment some sweep the mesh and others run their scalar finish, and the union of the code
-// in flight (~60 KB) overflows the SM's instruction cache, so that even the quadrature loop misses on 2/3 of its fetches.
-// Here the teams that currently hold a line start every pass together (a counting barrier in shared memory with dynamic
-// membership: join when a line is taken, leave when it is parked): sweeps coincide, the scalar phases that follow coincide
-// too and are fetched once for all teams.  The word packs (active teams << 16 | arrived teams).
-__device__ __forceinline__ void march_phase_join() {
-    atomicAdd(mc_ints() + 2 * kMarchWarps, 1 << 16);
-}
-__device__ __forceinline__ void march_phase_release(int* word, volatile int* gen) {
-    atomicAnd(word, (int)0xffff0000);
-    __threadfence_block();
-    atomicAdd((int*)gen, 1);
-}
-__device__ __forceinline__ void march_phase_leave() {
-    int* word = mc_ints() + 2 * kMarchWarps;
-    volatile int* gen = mc_ints() + 2 * kMarchWarps + 1;
-    const int old = atomicSub(word, 1 << 16);
-    const int active = (old >> 16) - 1;
-    if (active > 0 && (old & 0xffff) == active) march_phase_release(word, gen);     // everybody else is already waiting
-}
-__device__ __forceinline__ void march_phase_arrive_and_wait() {
-    int* word = mc_ints() + 2 * kMarchWarps;
-    volatile int* gen = mc_ints() + 2 * kMarchWarps + 1;
-    const int g = *gen;
-    const int old = atomicAdd(word, 1);
-    if ((old & 0xffff) + 1 == (old >> 16)) march_phase_release(word, gen);
-    else while (*gen == g) __nanosleep(64);
-}
+// ---- team protocol ---------------------------------------------------------------------------------------------------
+// Warp 0 of a team (the LEADER) runs the line: seeds, Newton logic, closed-form finishes, records.  The other warps (FOLLOWERS)
+// only sweep their share of the mesh: they wait at the team's named barrier, read the command the leader left in the team's
+// command block — kind of pass and the state (T, mu, xi, x) — sweep, leave their partial sums in the team buffer and meet
+// the leader at the barrier again.  What a follower executes is the prologue, the quadrature loop and the reduction (~6 KB);
+// the finish and the state machine (~17 KB) are fetched by one warp per team instead of all of them, which is what the
+// instruction cache of an SM with 16 desynchronised warps needs.  Two barriers per pass; the partial sums are added by the
+// leader in part order, so the result does not depend on which warp is faster.
+constexpr int kCmdDoubles = 16;       // op, T, mu, xi, x[5], kapP, kapM
+constexpr int MOP_EXIT = -1;          // op: -1 exit, WS_FJ / WS_FT / WS_TH generic sweep of that kind, MOP_LEAN + kind the lean sweep
+constexpr int MOP_LEAN = 8;
+constexpr int kRedStride = 33;        // row stride of the per-warp reduction scratch [kFJAcc][33]
+__device__ __forceinline__ double* mc_cmd() { return g_smem + c_mc.cmd0 + mc_team() * kCmdDoubles; }
+__device__ __forceinline__ double* mc_partial(int part) { return g_smem + c_mc.team0 + (mc_team() * c_mc.parts + part) * kBufStride; }
 
-// One quadrature pass of kind `type` at (T, mu, xi, x); afterwards the reduced sums of the whole mesh are in W[LW_S ..] of every
-// warp of the team.  Partial sums of the team's warps are added in part order (lane-parallel), so the result does not depend
-// on which warp is faster; the team buffers are double-buffered by pass parity, so one named barrier per pass suffices.
-__device__ __noinline__ void march_pass(int type, double T, double mu, double xi, double x0, double x1, double x2, double x3, double x4) {
+// Leader: publish a command (lane 0 writes, the barrier that follows orders it).
+__device__ __forceinline__ void march_post(int op, double T, double mu, double xi, double x0, double x1, double x2, double x3, double x4,
+                                           double kapP, double kapM) {
+    double* cmd = mc_cmd();
+    __syncwarp();
+    if (mc_lane() == 0) {
+        cmd[1] = T; cmd[2] = mu; cmd[3] = xi;
+        cmd[4] = x0; cmd[5] = x1; cmd[6] = x2; cmd[7] = x3; cmd[8] = x4;
+        cmd[9] = kapP; cmd[10] = kapM;
+        reinterpret_cast<int*>(cmd)[0] = op;
+    }
+    __syncwarp();
+}
+// Leader, after the closing barrier of a pass: the team's sums in part order -> W[LW_S ..].
+__device__ __forceinline__ void march_collect(bool lean) {
     const int lane = mc_lane();
-    double* stage = mc_stage();
     double* W = mc_W();
-    if (c_mc.lockstep) {
-        if (lane == 0 && mc_part() == 0) march_phase_arrive_and_wait();
-        mc_team_sync();
-    }
-    __syncwarp();
-    if (lane == 0) {
-        stage[0] = T; stage[1] = mu; stage[2] = xi;
-        stage[3] = x0; stage[4] = x1; stage[5] = x2; stage[6] = x3; stage[7] = x4;
-    }
-    __syncwarp();
-    MeshView mv;
-    mc_mesh(mv);
-    const int parts = c_mc.parts;
-    if (parts == 1) {
-        ws_worker_pass(c_mc.cfg, mv, stage, type, lane, 0, 1, W + LW_S);
-        __syncwarp();
-        return;
-    }
-    int* parity = mc_ints() + kMarchWarps + mc_warp();
-    double* base = g_smem + c_mc.team0 + (mc_team() * 2 + *parity) * parts * kBufStride;
-    ws_worker_pass(c_mc.cfg, mv, stage, type, lane, mc_part(), parts, base + mc_part() * kBufStride);
-    mc_team_sync();
+    const double* base = mc_partial(0);
     if (lane < kBufStride) {
         double v = base[lane];
         if (lane != 20)
-            for (int q = 1; q < parts; ++q) v += base[q * kBufStride + lane];
-        W[LW_S + lane] = v;
+            for (int q = 1; q < c_mc.parts; ++q) v += base[q * kBufStride + lane];
+        W[LW_S + lane] = (lean && lane == 20) ? 1.0 : v;
     }
-    if (lane == 0) *parity ^= 1;
     __syncwarp();
 }
 
+// One quadrature pass of kind `type` at (T, mu, xi, x) through the general ws_worker_pass (any kind of state); afterwards
+// the sums of the whole mesh are in the leader's W[LW_S ..].  Leader only.
+__device__ __noinline__ void march_pass(int type, double T, double mu, double xi, double x0, double x1, double x2, double x3, double x4) {
+    march_post(type, T, mu, xi, x0, x1, x2, x3, x4, 0.0, 0.0);
+    MeshView mv;
+    mc_mesh(mv);
+    if (c_mc.parts == 1) {
+        ws_worker_pass(c_mc.cfg, mv, mc_cmd() + 1, type, mc_lane(), 0, 1, mc_W() + LW_S);
+        __syncwarp();
+        return;
+    }
+    mc_team_sync();
+    ws_worker_pass(c_mc.cfg, mv, mc_cmd() + 1, type, mc_lane(), 0, c_mc.parts, mc_partial(0));
+    mc_team_sync();
+    march_collect(false);
+}
+
 // ---- the hot sweep ---------------------------------------------------------------------------------------------------
-// A Jacobian pass (WS_FJ) or a fused final pass (WS_FT) for the state every continuity point is in: on the integrand's fast
-// path, phi_u == phi_d bitwise, |mu|/T <= 60 (one logarithm per node) — the caller checks.  Same inline loops as
-// ws_worker_pass (fj_pair_fast / th_pair_fast<true, true>: identical sums), but ONE small function for both kinds with one
-// copy of the warp reduction, the per-point constants e^{+-mu/T} supplied by the caller, and everything in registers: what
-// the 16 desynchronised warps of an SM execute per pass has to stay inside the 32 KB instruction cache.
-__device__ __noinline__ void march_sweep(int type, double T, double mu, double xi, double x0, double x1, double x2, double x3, double x4,
-                                         double kapP, double kapM) {
+// This warp's share of a Jacobian pass (WS_FJ) or a fused final pass (WS_FT) for the state every continuity point is in: on
+// the integrand's fast path, phi_u == phi_d bitwise, |mu|/T <= 60 (one logarithm per node) — the leader checks.  Same inline
+// loops as ws_worker_pass (fj_pair_fast / th_pair_fast<true, true>), but ONE small function for both kinds, the per-point
+// constants e^{+-mu/T} supplied by the caller, and the warp reduction through shared memory (20 stores, a rolled loop of
+// 32 loads and adds per sum: ~50 instructions instead of the ~300 of the shuffle network).  Sums go to out[0 .. 19].
+__device__ __noinline__ void march_sweep_part(int type, double T, double mu, double xi, double x0, double x1, double x2, double x3, double x4,
+                                              double kapP, double kapM, double* out) {
     const int lane = mc_lane();
     const double x[5] = {x0, x1, x2, x3, x4};
     PointCtx c;
@@ -188,57 +183,90 @@ __device__ __noinline__ void march_sweep(int type, double T, double mu, double x
     const double* pc2 = iso ? p2 : g_smem + n;
     const double* coef = iso ? g_smem + 3 * n + c_mc.n_iso : g_smem + 2 * n;
     const int nn = iso ? c_mc.n_iso : n;
-    const int parts = c_mc.parts, part = mc_part();
-    const int stride = 32 * parts;
-    double acc[kFJAcc];
+    const int stride = 32 * c_mc.parts;
+    double* R = g_smem + c_mc.red0 + mc_warp() * (kFJAcc * kRedStride) + lane;
     if (type == WS_FJ) {
         double fu[5] = {0, 0, 0, 0, 0}, fs[5] = {0, 0, 0, 0, 0}, sh[5] = {0, 0, 0, 0, 0};
 #pragma unroll 1
-        for (int k = lane + 32 * part; k < nn; k += stride) {
+        for (int k = lane + 32 * mc_part(); k < nn; k += stride) {
             const double k2 = f_fma(xi, pc2[k], p2[k]);
             fj_pair_fast(fc, c.M2[0], c.M2[2], k2, coef[k], fu, fs, sh);
         }
 #pragma unroll
         for (int q = 0; q < 5; ++q) {
-            acc[3 * q + 0] = fu[q];
-            acc[3 * q + 1] = fu[q];
-            acc[3 * q + 2] = fs[q];
-            acc[15 + q] = sh[q];
+            R[(3 * q + 0) * kRedStride] = fu[q];
+            R[(3 * q + 1) * kRedStride] = fu[q];
+            R[(3 * q + 2) * kRedStride] = fs[q];
+            R[(15 + q) * kRedStride] = sh[q];
         }
     } else {
         double tu[4] = {0, 0, 0, 0}, ts[4] = {0, 0, 0, 0}, s1u = 0, s1s = 0, gsh[2] = {0, 0};
 #pragma unroll 1
-        for (int k = lane + 32 * part; k < nn; k += stride) {
+        for (int k = lane + 32 * mc_part(); k < nn; k += stride) {
             const double k2 = f_fma(xi, pc2[k], p2[k]);
             th_pair_fast<true, true>(fc, mu, c.M2[0], c.M2[2], k2, coef[k], tu, ts, s1u, s1s, gsh);
         }
         th_pair_finish(mu, tu, ts);
-        acc[0] = s1u; acc[1] = s1u; acc[2] = s1s; acc[3] = gsh[0]; acc[4] = gsh[1];
-        acc[kFtAcc + TH_NP + 0] = tu[0]; acc[kFtAcc + TH_NP + 1] = tu[0]; acc[kFtAcc + TH_NP + 2] = ts[0];
-        acc[kFtAcc + TH_NM + 0] = tu[1]; acc[kFtAcc + TH_NM + 1] = tu[1]; acc[kFtAcc + TH_NM + 2] = ts[1];
-        acc[kFtAcc + TH_L] = f_fma(2.0, tu[2], ts[2]);
-        acc[kFtAcc + TH_T] = f_fma(2.0, tu[3], ts[3]);
-#pragma unroll
-        for (int q = kFtAcc + kThAcc; q < kFJAcc; ++q) acc[q] = 0.0;
+        R[0 * kRedStride] = s1u; R[1 * kRedStride] = s1u; R[2 * kRedStride] = s1s;
+        R[3 * kRedStride] = gsh[0]; R[4 * kRedStride] = gsh[1];
+        R[(kFtAcc + TH_NP + 0) * kRedStride] = tu[0]; R[(kFtAcc + TH_NP + 1) * kRedStride] = tu[0]; R[(kFtAcc + TH_NP + 2) * kRedStride] = ts[0];
+        R[(kFtAcc + TH_NM + 0) * kRedStride] = tu[1]; R[(kFtAcc + TH_NM + 1) * kRedStride] = tu[1]; R[(kFtAcc + TH_NM + 2) * kRedStride] = ts[1];
+        R[(kFtAcc + TH_L) * kRedStride] = f_fma(2.0, tu[2], ts[2]);
+        R[(kFtAcc + TH_T) * kRedStride] = f_fma(2.0, tu[3], ts[3]);
     }
-    double* W = mc_W();
-    int* parity = mc_ints() + kMarchWarps + mc_warp();
-    double* base = g_smem + c_mc.team0 + (mc_team() * 2 + *parity) * parts * kBufStride;
     __syncwarp();
-    warp_sum_store(acc, lane, parts == 1 ? W + LW_S : base + part * kBufStride);      // one copy of the shuffle network
-    if (parts == 1) {
-        if (lane == 0) W[LW_S + 20] = 1.0;
+    const int n_sums = type == WS_FJ ? kFJAcc : kFtAcc + kThAcc;
+    if (lane < kFJAcc) {
+        const double* col = R - lane + lane * kRedStride;         // row `lane` of this warp's scratch
+        double v0 = 0.0, v1 = 0.0;
+        if (lane < n_sums) {
+            v0 = col[0]; v1 = col[1];
+#pragma unroll 5
+            for (int j = 2; j < 32; j += 2) { v0 += col[j]; v1 += col[j + 1]; }       // ten loads in flight per trip
+        }
+        out[lane] = v0 + v1;
+    }
+    __syncwarp();
+}
+
+// Leader: one lean pass; afterwards the sums of the whole mesh are in W[LW_S ..] (and the fast-path flag W[LW_S + 20] = 1).
+__device__ __forceinline__ void march_sweep(int type, double T, double mu, double xi, double x0, double x1, double x2, double x3, double x4,
+                                            double kapP, double kapM) {
+    if (c_mc.parts == 1) {
+        double* W = mc_W();
+        march_sweep_part(type, T, mu, xi, x0, x1, x2, x3, x4, kapP, kapM, W + LW_S);
+        if (mc_lane() == 0) W[LW_S + 20] = 1.0;
         __syncwarp();
         return;
     }
+    march_post(MOP_LEAN + type, T, mu, xi, x0, x1, x2, x3, x4, kapP, kapM);
     mc_team_sync();
-    if (lane < kFJAcc) {
-        double v = base[lane];
-        for (int q = 1; q < parts; ++q) v += base[q * kBufStride + lane];
-        W[LW_S + lane] = v;
+    march_sweep_part(type, T, mu, xi, x0, x1, x2, x3, x4, kapP, kapM, mc_partial(0));
+    mc_team_sync();
+    march_collect(true);
+}
+
+// Follower: serve the leader's passes until it says exit.
+__device__ __noinline__ void march_follow() {
+    const int lane = mc_lane(), part = mc_part();
+    const double* cmd = mc_cmd();
+    double* mine = mc_partial(part);
+    MeshView mv;
+    mc_mesh(mv);
+    for (;;) {
+        mc_team_sync();
+        const int op = reinterpret_cast<const int*>(cmd)[0];
+        if (op < 0) break;
+        if (op >= MOP_LEAN) march_sweep_part(op - MOP_LEAN, cmd[1], cmd[2], cmd[3], cmd[4], cmd[5], cmd[6], cmd[7], cmd[8], cmd[9], cmd[10], mine);
+        else ws_worker_pass(c_mc.cfg, mv, cmd + 1, op, lane, part, c_mc.parts, mine);
+        mc_team_sync();
     }
-    if (lane == 0) { W[LW_S + 20] = 1.0; *parity ^= 1; }
-    __syncwarp();
+}
+// Leader, when it has no more work: release the followers.
+__device__ __forceinline__ void march_dismiss() {
+    if (c_mc.parts == 1) return;
+    march_post(MOP_EXIT, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
+    mc_team_sync();
 }
 
 // ---- the unified lean finish -----------------------------------------------------------------------------------------
@@ -450,7 +478,6 @@ struct WarpEval {
 
 // Record writer of a team: warp 0 of the team stages the row in its shared-memory line and the 32 lanes store it.
 __device__ __forceinline__ void march_store_row(const double rec[PNJL_REC_DOUBLES], double* row) {
-    if (mc_part() != 0) return;
     const int lane = mc_lane();
     double* stage = mc_stage();
     __syncwarp();
@@ -482,46 +509,35 @@ __device__ __noinline__ void march_generic_point(const PhaseTables* pt, int ti, 
     scan_line_slice(sv, pt, ti, muq_MeV, xi, n_T, T_MeV, st, 1, sink);
 }
 
-// Dynamic shared memory: mesh [3 n + 2 n_iso] | staging lines [16][32] | scratch lines [16][LW_END] | team buffers [16][2][24] |
-// ints: popped line per team [16], pass parity per warp [16]
+// Dynamic shared memory: mesh [3 n + 2 n_iso] | staging lines [16][32] | scratch lines [16][LW_END] | partial sums [16][24] |
+// command blocks [16][16] | reduction scratch [16][20][33]
 __global__ void __launch_bounds__(32 * kMarchWarps, 1) k_march(const double* __restrict__ g_mesh, MarchArgs a) {
     const DeviceConfig* cfg = c_mc.cfg;
     const int n_mesh = 3 * c_mc.n + 2 * c_mc.n_iso;
     for (int i = threadIdx.x; i < n_mesh; i += blockDim.x) g_smem[i] = g_mesh[i];
-    if (threadIdx.x < 2 * kMarchWarps + 2) mc_ints()[threadIdx.x] = 0;
     __syncthreads();
+    if (mc_part() != 0) { march_follow(); return; }
     const int lane = mc_lane();
-    const int parts = c_mc.parts;
-    const int part = mc_part();
     const SolverParams& sp = c_mc.sp;
     volatile int* slots = a.slots;
     volatile unsigned long long* done = a.counters + 2;
     for (;;) {
-        // ---- pop: the team leader takes a ticket and waits for the line that goes with it (or for the end of the scan) ----
+        // ---- pop: take a ticket and wait for the line that goes with it (or for the end of the scan) ----
         int line = -1;
-        if (part == 0) {
-            if (lane == 0) {
-                const unsigned long long t = atomicAdd(a.counters + 0, 1ULL);
-                for (;;) {
-                    if ((long long)t < a.capacity) {
-                        line = slots[t];
-                        if (line >= 0) break;
-                    }
-                    if (*done >= (unsigned long long)a.n_lines) { line = -1; break; }
-                    __nanosleep(500);
+        if (lane == 0) {
+            const unsigned long long t = atomicAdd(a.counters + 0, 1ULL);
+            for (;;) {
+                if ((long long)t < a.capacity) {
+                    line = slots[t];
+                    if (line >= 0) break;
                 }
-                __threadfence();
+                if (*done >= (unsigned long long)a.n_lines) { line = -1; break; }
+                __nanosleep(500);
             }
-            line = __shfl_sync(0xffffffffu, line, 0);
-            if (parts > 1 && lane == 0) mc_ints()[mc_team()] = line;
+            __threadfence();
         }
-        if (parts > 1) {
-            mc_team_sync();
-            line = mc_ints()[mc_team()];
-            mc_team_sync();          // everybody has read the slot before the leader can overwrite it
-        }
+        line = __shfl_sync(0xffffffffu, line, 0);
         if (line < 0) break;
-        if (c_mc.lockstep && part == 0 && lane == 0) march_phase_join();
         // ---- this line's parameters and parked tracker state ----
         LineState st;
         {
@@ -630,7 +646,7 @@ __global__ void __launch_bounds__(32 * kMarchWarps, 1) k_march(const double* __r
                     solved = true;
                     // the record: march_finish left the thermodynamic functions and the masses in the staging line; the rest here
                     double* stage = mc_stage();
-                    if (part == 0) {
+                    {
                         __syncwarp();
                         if (lane == 0) {
 #pragma unroll
@@ -661,8 +677,7 @@ __global__ void __launch_bounds__(32 * kMarchWarps, 1) k_march(const double* __r
             if (!solved) march_generic_point(&cfg->pt, ti, muq_MeV, xi, a.n_T, a.T_MeV, st, rows);
         }
         // ---- park the line (or retire it) ----
-        if (c_mc.lockstep && part == 0 && lane == 0) march_phase_leave();
-        if (part == 0 && lane == 0) {
+        if (lane == 0) {
             if (st.it_next < a.n_T) {
                 LineState* g = a.state + line;
 #pragma unroll
@@ -678,6 +693,7 @@ __global__ void __launch_bounds__(32 * kMarchWarps, 1) k_march(const double* __r
             }
         }
     }
+    march_dismiss();
 }
 
 // ---- independent points, one warp (team) per point ----------------------------------------------------------------
@@ -696,26 +712,15 @@ struct MarchPointArgs {
 __global__ void __launch_bounds__(32 * kMarchWarps, 1) k_march_points(const double* __restrict__ g_mesh, MarchPointArgs a) {
     const int n_mesh = 3 * c_mc.n + 2 * c_mc.n_iso;
     for (int i = threadIdx.x; i < n_mesh; i += blockDim.x) g_smem[i] = g_mesh[i];
-    if (threadIdx.x < 2 * kMarchWarps + 2) mc_ints()[threadIdx.x] = 0;
     __syncthreads();
+    if (mc_part() != 0) { march_follow(); return; }
     const int lane = mc_lane();
-    const int parts = c_mc.parts;
-    const int part = mc_part();
     WarpEval ev;
     Solver<WarpEval> sv(c_model, c_mc.sp, ev);
     for (;;) {
         long long i = 0;
-        if (part == 0) {
-            if (lane == 0) i = (long long)atomicAdd(a.counter, 1ULL);
-            i = __shfl_sync(0xffffffffu, i, 0);
-            if (parts > 1 && lane == 0) mc_ints()[mc_team()] = (int)(i < a.n ? i : -1);
-        }
-        if (parts > 1) {
-            mc_team_sync();
-            const int v = mc_ints()[mc_team()];
-            mc_team_sync();
-            i = v < 0 ? a.n : (long long)v;
-        }
+        if (lane == 0) i = (long long)atomicAdd(a.counter, 1ULL);
+        i = __shfl_sync(0xffffffffu, i, 0);
         if (i >= a.n) break;
         const double T = a.T_fm[i], mu = a.mu_fm[i], x_i = a.xi[i];
         sv.set_point(T, mu, x_i);
@@ -739,4 +744,5 @@ __global__ void __launch_bounds__(32 * kMarchWarps, 1) k_march_points(const doub
         fill_record(r, T, mu, x_i, sv.n_fj, sv.n_th, sv.n_ft, rec);
         march_store_row(rec, a.records + (long long)PNJL_REC_DOUBLES * i);
     }
+    march_dismiss();
 }

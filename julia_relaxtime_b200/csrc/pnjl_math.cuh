@@ -171,6 +171,32 @@ PNJL_HD double fast_log_pos(double x) {
 #endif
 }
 
+// Guarded versions for arguments that are not known to be tame (the general integrand path, pivots of the elimination): the
+// fast sequence for normal, finite arguments well inside the exponent range, the IEEE / libm routine out of line otherwise
+// (NaN fails every comparison and goes there too).  Non-physical Newton iterates (MultiSeed bootstraps, Phi < 0) spend their
+// sweeps here: libm exp + IEEE division + rsqrt were 30 % of the samples of a config-3 run.
+PNJL_HD_NOINL double cold_rcp(double v) { return 1.0 / v; }   // out of line: IEEE division is ~100 instructions
+PNJL_HD_NOINL double cold_exp(double t) { return exp(t); }
+PNJL_HD_NOINL double cold_log(double x) { return log(x); }
+PNJL_HD_NOINL double cold_rsqrt(double x) { return f_rsqrt(x); }
+PNJL_HD double guarded_rcp(double v) {
+    const double a = fabs(v);
+    if (a > 1e-280 && a < 1e280) return fast_rcp(v);
+    return cold_rcp(v);
+}
+PNJL_HD double guarded_rsqrt(double x) {
+    if (x > 1e-280 && x < 1e280) return fast_rsqrt(x);
+    return cold_rsqrt(x);
+}
+PNJL_HD double guarded_exp_nonpos(double t) {       // exp(t), t <= 0
+    if (t >= -708.0) return fast_exp_nonpos(t);
+    return cold_exp(t);
+}
+PNJL_HD double guarded_log(double x) {
+    if (x > 1e-300 && x < 1e300) return fast_log_pos(x);
+    return cold_log(x);
+}
+
 // ------------------------------------------------------------------------------------------------
 // One Polyakov-loop species term L = ln(1 + 3 P1 y + 3 P2 y^2 + y^3), y = e^a, evaluated in the
 // scale-free form of Integrals.jl:203-235: with w = e^{-|a|}
@@ -188,7 +214,7 @@ struct Species {
 
 PNJL_HD Species species_eval(double a, double P1x3, double P2x3) {
     Species s;
-    const double w = f_exp(-fabs(a));
+    const double w = guarded_exp_nonpos(-fabs(a));
     const double w2 = w * w;
     const double w3 = w2 * w;
     s.pos = a > 0.0;
@@ -200,7 +226,7 @@ PNJL_HD Species species_eval(double a, double P1x3, double P2x3) {
     D = f_fma(P2x3, t2, D);
     D += t3;
     const bool floored = D < kPolyakovEps;
-    const double inv = f_rcp(D);
+    const double inv = guarded_rcp(D);
     s.r1 = floored ? 0.0 : t1 * inv;
     s.r2 = floored ? 0.0 : t2 * inv;
     s.r3 = floored ? (s.pos ? 1.0 : 0.0) : t3 * inv;
@@ -247,7 +273,7 @@ PNJL_HD void make_ctx(const Model& m, double T, double mu, double xi, const doub
 template <int FL>
 PNJL_HD void fj_node(const PointCtx& c, double k2, double coef, double acc[kFJAcc]) {
     const double E2 = k2 + c.M2[FL];
-    const double rE = f_rsqrt(E2);
+    const double rE = guarded_rsqrt(E2);
     const double E = E2 * rE;
     const double a = (c.mu - E) * c.invT;   // -(E - mu)/T
     const double b = -(E + c.mu) * c.invT;  // -(E + mu)/T
@@ -922,7 +948,7 @@ enum { TH_NP = 0, TH_NM = 3, TH_L = 6, TH_T = 7 };
 template <int FL>
 PNJL_HD void thermo_node(const PointCtx& c, double k2, double coef, double acc[kThAcc]) {
     const double E2 = k2 + c.M2[FL];
-    const double rE = f_rsqrt(E2);
+    const double rE = guarded_rsqrt(E2);
     const double E = E2 * rE;
     const double a = (c.mu - E) * c.invT;
     const double b = -(E + c.mu) * c.invT;
@@ -930,7 +956,7 @@ PNJL_HD void thermo_node(const PointCtx& c, double k2, double coef, double acc[k
     const Species sm = species_eval(b, c.Phib3, c.Phi3);
     const double np = f_fma(c.Phi, sp.r1, f_fma(2.0 * c.Phib, sp.r2, sp.r3));
     const double nm = f_fma(c.Phib, sm.r1, f_fma(2.0 * c.Phi, sm.r2, sm.r3));
-    double L = f_log(sp.D * sm.D);
+    double L = guarded_log(sp.D * sm.D);
     if (sp.pos) L = f_fma(3.0, a, L);
     if (sm.pos) L = f_fma(3.0, b, L);
     acc[TH_NP + FL] = f_fma(coef, np, acc[TH_NP + FL]);
@@ -1117,7 +1143,7 @@ enum { DT_A1 = 0, DT_B1 = 3, DT_AG = 6, DT_BG = 7, DT_AGB = 8, DT_BGB = 9, DT_A2
 template <int FL>
 PNJL_HD void dtheta_node(const PointCtx& c, double k2, double coef, double acc[kDtAcc]) {
     const double E2 = k2 + c.M2[FL];
-    const double rE = f_rsqrt(E2);
+    const double rE = guarded_rsqrt(E2);
     const double E = E2 * rE;
     const double a = (c.mu - E) * c.invT;
     const double b = -(E + c.mu) * c.invT;
@@ -1258,12 +1284,6 @@ PNJL_HD_NOINL bool lu_solve5(const double A_in[25], const double b_in[5], double
 
 // Same elimination order as lu_solve5, fully unrolled with select-based row swaps so that A, b and y live in
 // registers (used in the fused quadrature-pass epilogue; A and b are destroyed).
-PNJL_HD_NOINL double cold_rcp(double v) { return 1.0 / v; }   // out of line: IEEE division is ~100 instructions
-PNJL_HD double guarded_rcp(double v) {
-    const double a = fabs(v);
-    if (a > 1e-280 && a < 1e280) return fast_rcp(v);
-    return cold_rcp(v);
-}
 PNJL_HD bool lu_solve5_regs(double A[25], double b[5], double y[5]) {
     bool ok = true;
     double inv[5];
