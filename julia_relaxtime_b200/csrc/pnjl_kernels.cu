@@ -1348,9 +1348,10 @@ int launch_march(pnjl_handle* h, long long n_lines, const double* muq, const dou
     a.counters = (unsigned long long*)h->march_counters.p;
     MarchConst mc;
     const size_t smem = march_layout(h, parts, mc);
+    const auto kernel = parts == 1 ? k_march<false> : k_march<true>;
     cudaFuncAttributes fa;
-    CUDA_TRY(cudaFuncGetAttributes(&fa, k_march));
-    if (smem > 40 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_march, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaFuncGetAttributes(&fa, kernel));
+    if (smem > 40 * 1024) CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int blocks = (int)(n_lines < h->sm_count ? n_lines : h->sm_count);
     h->stats.regs_per_thread = fa.numRegs;
     h->stats.smem_bytes = (int)smem;
@@ -1364,7 +1365,7 @@ int launch_march(pnjl_handle* h, long long n_lines, const double* muq, const dou
     const long long n_init = a.capacity > n_lines ? a.capacity : n_lines;
     k_march_init<<<(unsigned)((n_init + 255) / 256), 256, 0, st>>>(a);
     CUDA_TRY(cudaGetLastError());
-    k_march<<<blocks, 32 * kMarchWarps, smem, st>>>(h->d_mesh, a);
+    kernel<<<blocks, 32 * kMarchWarps, smem, st>>>(h->d_mesh, a);
     CUDA_TRY(cudaGetLastError());
     h->stats.kernel_launches += 2;
     return PNJL_OK;

@@ -230,9 +230,10 @@ __device__ __noinline__ void march_sweep_part(int type, double T, double mu, dou
 }
 
 // Leader: one lean pass; afterwards the sums of the whole mesh are in W[LW_S ..] (and the fast-path flag W[LW_S + 20] = 1).
+template <bool TEAMS>
 __device__ __forceinline__ void march_sweep(int type, double T, double mu, double xi, double x0, double x1, double x2, double x3, double x4,
                                             double kapP, double kapM) {
-    if (c_mc.parts == 1) {
+    if (!TEAMS || c_mc.parts == 1) {
         double* W = mc_W();
         march_sweep_part(type, T, mu, xi, x0, x1, x2, x3, x4, kapP, kapM, W + LW_S);
         if (mc_lane() == 0) W[LW_S + 20] = 1.0;
@@ -511,12 +512,15 @@ __device__ __noinline__ void march_generic_point(const PhaseTables* pt, int ti, 
 
 // Dynamic shared memory: mesh [3 n + 2 n_iso] | staging lines [16][32] | scratch lines [16][LW_END] | partial sums [16][24] |
 // command blocks [16][16] | reduction scratch [16][20][33]
+// TEAMS = false: the instantiation for one warp per line (launch_march picks it when parts == 1): no team code in the hot loop —
+// what 16 leaders per SM fetch per pass is what bounds that case (config 4: every pass is two trips of the quadrature loop).
+template <bool TEAMS>
 __global__ void __launch_bounds__(32 * kMarchWarps, 1) k_march(const double* __restrict__ g_mesh, MarchArgs a) {
     const DeviceConfig* cfg = c_mc.cfg;
     const int n_mesh = 3 * c_mc.n + 2 * c_mc.n_iso;
     for (int i = threadIdx.x; i < n_mesh; i += blockDim.x) g_smem[i] = g_mesh[i];
     __syncthreads();
-    if (mc_part() != 0) { march_follow(); return; }
+    if (TEAMS && mc_part() != 0) { march_follow(); return; }
     const int lane = mc_lane();
     const SolverParams& sp = c_mc.sp;
     volatile int* slots = a.slots;
@@ -593,7 +597,7 @@ __global__ void __launch_bounds__(32 * kMarchWarps, 1) k_march(const double* __r
                         const double M2[3] = {M[0] * M[0], M[1] * M[1], M[2] * M[2]};
                         if (!(x[0] == x[1]) || !fast_path_ok(T, mu_fm, x[3], x[4], k2max, M2)) { bail = true; break; }
                     }
-                    march_sweep(kind, T, mu_fm, xi, x[0], x[1], x[2], x[3], x[4], kapP, kapM);
+                    march_sweep<TEAMS>(kind, T, mu_fm, xi, x[0], x[1], x[2], x[3], x[4], kapP, kapM);
                     const int rc = march_finish(kind == WS_FJ ? 0 : 1, T, mu_fm, xi, x[0], x[1], x[2], x[3], x[4]);
                     if (rc < 0) { bail = true; break; }
 #pragma unroll
@@ -693,7 +697,7 @@ __global__ void __launch_bounds__(32 * kMarchWarps, 1) k_march(const double* __r
             }
         }
     }
-    march_dismiss();
+    if (TEAMS) march_dismiss();
 }
 
 // ---- independent points, one warp (team) per point ----------------------------------------------------------------
