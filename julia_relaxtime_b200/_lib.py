@@ -34,7 +34,7 @@ def build(force=False, verbose=False):
         return LIB_PATH
     os.makedirs(BUILD_DIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, SOURCES[0]]
+    cmd = [nvcc] + NVCC_FLAGS + os.environ.get("PNJL_NVCC_EXTRA", "").split() + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, SOURCES[0]]
     try:
         out = subprocess.run(cmd, check=True, capture_output=True, text=True)
     except (OSError, subprocess.CalledProcessError) as e:

@@ -1304,7 +1304,23 @@ static size_t march_layout(const pnjl_handle* h, int parts, MarchConst& mc) {
     std::memset(&mc, 0, sizeof(mc));
     mc.cfg = h->d_cfg;
     mc.parts = parts;
-    for (mc.log2_parts = 0; (1 << mc.log2_parts) < parts; ++mc.log2_parts) {}
+    // teams of consecutive warps; in team t the leader is the warp whose scheduler (w & 3) has the fewest leaders so far
+    {
+        const int n_teams = kMarchWarps / parts;
+        int leaders_on[4] = {0, 0, 0, 0};
+        for (int w = 0; w < kMarchWarps; ++w) { mc.team_of[w] = -1; mc.role_of[w] = 0; }
+        for (int t = 0; t < n_teams; ++t) {
+            int lead = t * parts;
+            for (int w = t * parts; w < (t + 1) * parts; ++w)
+                if (leaders_on[w & 3] < leaders_on[lead & 3]) lead = w;
+            ++leaders_on[lead & 3];
+            int role = 1;
+            for (int w = t * parts; w < (t + 1) * parts; ++w) {
+                mc.team_of[w] = (signed char)t;
+                mc.role_of[w] = (signed char)(w == lead ? 0 : role++);
+            }
+        }
+    }
     mc.stage0 = (n_mesh + 1) & ~1;
     mc.lean0 = mc.stage0 + kMarchWarps * kStageDoubles;
     mc.team0 = mc.lean0 + kMarchWarps * LW_END;
@@ -1329,8 +1345,8 @@ int launch_march(pnjl_handle* h, long long n_lines, const double* muq, const dou
     int parts = 1;
     while (parts < kMarchWarps && n_lines * 2 * parts <= 3 * total_warps && n_eff / (64 * parts) >= 2) parts *= 2;
     if (h->march_parts > 0) parts = h->march_parts;
-    if (parts != 1 && parts != 2 && parts != 4 && parts != 8 && parts != 16) return fail(PNJL_ERR_ARG, "march_parts must be 1, 2, 4, 8 or 16");
-    const long long n_teams = total_warps / parts;
+    if (parts < 1 || parts > kMarchWarps) return fail(PNJL_ERR_ARG, "march_parts must be 1 .. 16");
+    const long long n_teams = (long long)h->sm_count * (kMarchWarps / parts);
     int quantum = h->march_quantum > 0 ? h->march_quantum : (n_lines <= n_teams ? n_T : 32);
     if (quantum > n_T) quantum = n_T;
     const long long n_quanta = (n_T + quantum - 1) / quantum;
@@ -1378,7 +1394,7 @@ int launch_march_points(pnjl_handle* h, long long n, const double* T, const doub
     int parts = 1;
     while (parts < kMarchWarps && n * 2 * parts <= 3 * total_warps && h->n_nodes / (64 * parts) >= 2) parts *= 2;
     if (h->march_parts > 0) parts = h->march_parts;
-    if (parts != 1 && parts != 2 && parts != 4 && parts != 8 && parts != 16) return fail(PNJL_ERR_ARG, "march_parts must be 1, 2, 4, 8 or 16");
+    if (parts < 1 || parts > kMarchWarps) return fail(PNJL_ERR_ARG, "march_parts must be 1 .. 16");
     MarchPointArgs a;
     std::memset(&a, 0, sizeof(a));
     a.n = n; a.T_fm = T; a.mu_fm = mu; a.xi = xi; a.seed_mode = seed_mode; a.n_seeds = n_seeds; a.seeds = seeds; a.records = rec;
@@ -1821,8 +1837,7 @@ int pnjl_set_option(pnjl_handle* h, const char* key, int64_t value) {
         if (value < 0 || value > 3) return fail(PNJL_ERR_ARG, "schedule: 0 automatic, 1 one warp per line, 2 worker/controller warps, 3 line march");
         h->schedule = value == 1 ? 0 : (value == 2 ? 1 : (value == 3 ? 3 : 2));
     } else if (k == "march_parts") {
-        if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8 && value != 16)
-            return fail(PNJL_ERR_ARG, "march_parts must be 0 (automatic), 1, 2, 4, 8 or 16");
+        if (value < 0 || value > kMarchWarps) return fail(PNJL_ERR_ARG, "march_parts must be 0 (automatic) .. 16");
         h->march_parts = (int)value;
     } else if (k == "march_quantum") {
         if (value < 0 || value > (1 << 30)) return fail(PNJL_ERR_ARG, "march_quantum out of range");

@@ -26,6 +26,12 @@
 #ifndef PNJL_MARCH_LEAN
 #define PNJL_MARCH_LEAN 1
 #endif
+#ifndef PNJL_MARCH_UNROLL
+#define PNJL_MARCH_UNROLL 1
+#endif
+// Unroll factor of the lean sweep loops.  Two nodes per trip (four independent FP64 chains per warp) was measured SLOWER on
+// every share of config 5 (1/8 share 64.8 -> 69.0 ms, full grid 363 -> 429 ms): the loop is 2.3x the code for no extra issue rate.
+constexpr int kMarchUnroll = PNJL_MARCH_UNROLL;
 
 constexpr int kMarchWarps = 16;      // warps per CTA (512 threads x 128 registers = the register file of an SM)
 constexpr int kBufStride = 24;       // doubles per reduced-sum block: 20 sums + the fast-path flag, padded
@@ -48,7 +54,9 @@ struct MarchArgs {
 // a context object in (local) memory and the finish code takes its constants as constant-bank operands.
 struct MarchConst {
     const DeviceConfig* cfg;
-    int parts, log2_parts;            // warps per team (1, 2, 4, 8 or 16)
+    int parts;                        // warps per team (1 .. 16); 16 / parts teams per CTA, left-over warps exit at once
+    signed char team_of[kMarchWarps]; // team of warp w (-1: no team)
+    signed char role_of[kMarchWarps]; // share of a sweep warp w takes in its team: 0 = the leader, 1 .. parts-1 the followers
     int stage0, lean0, team0, cmd0, red0;   // offsets (in doubles) into the dynamic shared memory: staging lines [16][32] | scratch
                                       // lines [16][LW_END] | partial sums [16][24] | command blocks [16][16] | reduction scratch [16][20][33]
     int n, n_iso;
@@ -76,15 +84,10 @@ __global__ void k_march_init(MarchArgs a) {
 // ---- per-warp context, recomputed where it is needed ----
 __device__ __forceinline__ int mc_lane() { return threadIdx.x & 31; }
 __device__ __forceinline__ int mc_warp() { return threadIdx.x >> 5; }
-// Team t = warps [t parts, (t + 1) parts); which of them is part 0 (the leader) rotates with t so that the leaders — the warps
-// that run the scalar phases — are spread evenly over the four schedulers of the SM (warp w issues on scheduler w & 3):
-// parts 2: leaders on schedulers 0, 2, 1, 3, ...; parts >= 4: 0, 3, 2, 1.
-__device__ __forceinline__ int mc_team() { return mc_warp() >> c_mc.log2_parts; }
-__device__ __forceinline__ int mc_part() {
-    const int t = mc_team();
-    const int rot = c_mc.parts >= 4 ? t : (t >> 1);
-    return (mc_warp() + rot) & (c_mc.parts - 1);
-}
+// Team and role of a warp: tables in constant memory, filled by the launcher (march_layout) so that the leaders — the warps
+// that run the scalar phases — are spread evenly over the four schedulers of the SM (warp w issues on scheduler w & 3).
+__device__ __forceinline__ int mc_team() { return c_mc.team_of[mc_warp()]; }
+__device__ __forceinline__ int mc_part() { return c_mc.role_of[mc_warp()]; }
 __device__ __forceinline__ double* mc_stage() { return g_smem + c_mc.stage0 + mc_warp() * kStageDoubles; }
 __device__ __forceinline__ double* mc_W() { return g_smem + c_mc.lean0 + mc_warp() * LW_END; }
 __device__ __forceinline__ void mc_mesh(MeshView& mv) {
@@ -187,7 +190,7 @@ __device__ __noinline__ void march_sweep_part(int type, double T, double mu, dou
     double* R = g_smem + c_mc.red0 + mc_warp() * (kFJAcc * kRedStride) + lane;
     if (type == WS_FJ) {
         double fu[5] = {0, 0, 0, 0, 0}, fs[5] = {0, 0, 0, 0, 0}, sh[5] = {0, 0, 0, 0, 0};
-#pragma unroll 1
+#pragma unroll kMarchUnroll
         for (int k = lane + 32 * mc_part(); k < nn; k += stride) {
             const double k2 = f_fma(xi, pc2[k], p2[k]);
             fj_pair_fast(fc, c.M2[0], c.M2[2], k2, coef[k], fu, fs, sh);
@@ -201,7 +204,7 @@ __device__ __noinline__ void march_sweep_part(int type, double T, double mu, dou
         }
     } else {
         double tu[4] = {0, 0, 0, 0}, ts[4] = {0, 0, 0, 0}, s1u = 0, s1s = 0, gsh[2] = {0, 0};
-#pragma unroll 1
+#pragma unroll kMarchUnroll
         for (int k = lane + 32 * mc_part(); k < nn; k += stride) {
             const double k2 = f_fma(xi, pc2[k], p2[k]);
             th_pair_fast<true, true>(fc, mu, c.M2[0], c.M2[2], k2, coef[k], tu, ts, s1u, s1s, gsh);
@@ -520,6 +523,7 @@ __global__ void __launch_bounds__(32 * kMarchWarps, 1) k_march(const double* __r
     const int n_mesh = 3 * c_mc.n + 2 * c_mc.n_iso;
     for (int i = threadIdx.x; i < n_mesh; i += blockDim.x) g_smem[i] = g_mesh[i];
     __syncthreads();
+    if (TEAMS && mc_team() < 0) return;
     if (TEAMS && mc_part() != 0) { march_follow(); return; }
     const int lane = mc_lane();
     const SolverParams& sp = c_mc.sp;
@@ -717,6 +721,7 @@ __global__ void __launch_bounds__(32 * kMarchWarps, 1) k_march_points(const doub
     const int n_mesh = 3 * c_mc.n + 2 * c_mc.n_iso;
     for (int i = threadIdx.x; i < n_mesh; i += blockDim.x) g_smem[i] = g_mesh[i];
     __syncthreads();
+    if (mc_team() < 0) return;
     if (mc_part() != 0) { march_follow(); return; }
     const int lane = mc_lane();
     WarpEval ev;
