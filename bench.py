@@ -558,7 +558,7 @@ def main():
         traffic = None
         pj = os.path.join(ROOT, "profiles", "top_kernel.json")
         static = None
-        if os.path.exists(pj) and world == 1:
+        if os.path.exists(pj) and world == 1 and w == "cfg5":      # the committed capture is the cfg5 launch of k_solve_ws
             try:
                 prof = json.load(open(pj))
                 if prof.get("dram_bytes_per_point") is not None:

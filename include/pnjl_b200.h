@@ -170,7 +170,7 @@ int pnjl_gauleg(double a, double b, int32_t n, double* nodes, double* weights);
 
 /* Run-time options of a handle (launch geometry, nothing that changes results beyond round-off):
  *   "schedule"        0 (automatic), 1, 2, 3: as pnjl_config.schedule
- *   "march_parts"     warps per line in the line-march kernel: 0 automatic, 1, 2, 4, 8, 16
+ *   "march_parts"     warps per line (a leader and followers that only sweep) in the line-march kernel: 0 automatic, 1 .. 16
  *   "march_quantum"   points per time slice of a line in the line-march kernel (0 automatic)
  *   "isotropic_batch" 1: the caller promises xi == 0 on every line of the following *_device calls (the host entry points
  *                     look at xi themselves), so teams are sized for p_num nodes instead of p_num * t_num */

@@ -1329,7 +1329,8 @@ static size_t march_layout(const pnjl_handle* h, int parts, MarchConst& mc) {
     mc.n = h->n_nodes; mc.n_iso = h->host_cfg.n_iso;
     mc.p2max = h->host_cfg.p2max; mc.pc2max = h->host_cfg.pc2max;
     mc.sp = h->host_cfg.sp;
-    return sizeof(double) * (size_t)(mc.red0 + kMarchWarps * kFJAcc * kRedStride);
+    mc.state0 = mc.red0 + kMarchWarps * kFJAcc * kRedStride;
+    return sizeof(double) * (size_t)(mc.state0 + kMarchWarps * kStateDoubles);
 }
 
 // Launch geometry of the line-march kernel.  Team size: one warp per line while the GPU holds at least 3/4 as many lines

@@ -57,6 +57,7 @@ struct MarchConst {
     int parts;                        // warps per team (1 .. 16); 16 / parts teams per CTA, left-over warps exit at once
     signed char team_of[kMarchWarps]; // team of warp w (-1: no team)
     signed char role_of[kMarchWarps]; // share of a sweep warp w takes in its team: 0 = the leader, 1 .. parts-1 the followers
+    int state0;                       // line states [16][32] (doubles)
     int stage0, lean0, team0, cmd0, red0;   // offsets (in doubles) into the dynamic shared memory: staging lines [16][32] | scratch
                                       // lines [16][LW_END] | partial sums [16][24] | command blocks [16][16] | reduction scratch [16][20][33]
     int n, n_iso;
@@ -513,26 +514,215 @@ __device__ __noinline__ void march_generic_point(const PhaseTables* pt, int ti, 
     scan_line_slice(sv, pt, ti, muq_MeV, xi, n_T, T_MeV, st, 1, sink);
 }
 
+// ---- the line of a leader: its state lives in shared memory --------------------------------------------------------------
+// Everything a line carries from pass to pass — the Newton iterate, the tracker of PhaseAwareContinuitySeed, counters, flags —
+// sits in a per-warp block of shared memory and every step below loads what it needs and stores what it changed.  Kept in
+// registers, that state is live across the calls of the sweep and the finish and ptxas spills it to local memory around
+// each of them (~100 LDL/STL per pass); with 512 threads x 4 KB of stack per SM those slots miss in L1 and main() waited on
+// them for 15 % of a config-4 run (profiles/r02b_march_cfg4.md: long scoreboard).
+enum { DS_X = 0, DS_XOLD = 5, DS_T = 10, DS_MU = 11, DS_XI = 12, DS_KAPP = 13, DS_KAPM = 14, DS_K2MAX = 15, DS_RES = 16, DS_TM = 17,
+       DS_MUQ = 18, DS_PREV = 19, DS_ROWS = 24, DS_INTS = 25 };
+enum { DJ_LINE = 0, DJ_IT = 1, DJ_ITEND = 2, DJ_KIND = 3, DJ_ITERS = 4, DJ_NFJ = 5, DJ_NFT = 6, DJ_HINT = 7, DJ_FLAGS = 8,
+       DJ_PREVPH = 9, DJ_HASPREV = 10, DJ_ITSHINT = 11, DJ_TI = 12 };
+enum { DF_FIRST = 1, DF_REFRESH = 2, DF_HAVETH = 4, DF_THFINITE = 8, DF_NONSING = 16, DF_XC = 32, DF_FC = 64, DF_FLIP = 128 };
+constexpr int kStateDoubles = 32;     // 25 doubles + 13 ints
+__device__ __forceinline__ double* mc_state() { return g_smem + c_mc.state0 + mc_warp() * kStateDoubles; }
+
+// Generic cascade for the current point of this warp's line (bootstrap, fall-backs, anything the lean path hands back).
+__device__ __noinline__ void march_generic_step(const MarchArgs& a) {
+    double* S = mc_state();
+    int* J = reinterpret_cast<int*>(S + DS_INTS);
+    LineState st;
+#pragma unroll
+    for (int q = 0; q < 5; ++q) st.prev[q] = S[DS_PREV + q];
+    st.it_next = J[DJ_IT]; st.prev_phase = J[DJ_PREVPH]; st.has_prev = J[DJ_HASPREV]; st.its_hint = J[DJ_ITSHINT];
+    double* rows = *reinterpret_cast<double**>(S + DS_ROWS);
+    march_generic_point(&c_mc.cfg->pt, J[DJ_TI], S[DS_MUQ], S[DS_XI], a.n_T, a.T_MeV, st, rows);
+    __syncwarp();
+    if (mc_lane() == 0) {
+#pragma unroll
+        for (int q = 0; q < 5; ++q) S[DS_PREV + q] = st.prev[q];
+        J[DJ_IT] = st.it_next; J[DJ_PREVPH] = st.prev_phase; J[DJ_HASPREV] = st.has_prev; J[DJ_ITSHINT] = st.its_hint;
+    }
+    __syncwarp();
+}
+
+// One point of the line on the lean path: NLsolve newton_ (Solver::newton), common case only — every state on the integrand's
+// fast path with phi_u == phi_d and |mu| <= 60 T, every closed form tame, F finite.  One pass site: kind = Jacobian pass or
+// fused final pass (predicted), a mispredicted final pass is followed by a Jacobian pass at the same x ("refresh").  Returns
+// true when the point was solved and its record written; anything else -> false, the generic cascade redoes the point from
+// its seed.
+template <bool TEAMS>
+__device__ __forceinline__ bool march_lean_point(const MarchArgs& a) {
+    const int lane = mc_lane();
+    const SolverParams& sp = c_mc.sp;
+    double* const S = mc_state();
+    int* const J = reinterpret_cast<int*>(S + DS_INTS);
+    {
+        // PhaseAwareContinuitySeed get_seed (SeedStrategies.jl:795-839) with a previous solution
+        const double Tm = a.T_MeV[J[DJ_IT]];
+        const double T = Tm / c_model.hbarc;
+        const double mu_fm = S[DS_MU];
+        if (!one_log_ok(T, mu_fm) || !(T > 1e-300 && T < 1e300)) return false;
+        const int cur = current_phase(&c_mc.cfg->pt, J[DJ_TI], T * 197.327, mu_fm * 197.327);
+        const int pp = J[DJ_PREVPH];
+        const bool flip = (pp == PH_HADRON && cur == PH_QUARK) || (pp == PH_QUARK && cur == PH_HADRON);
+        double x[5];
+        if (flip) seed_const(cur == PH_HADRON ? 0 : 1, x);
+        else {
+#pragma unroll
+            for (int q = 0; q < 5; ++q) x[q] = S[DS_PREV + q];
+        }
+        // e^{+-mu/T}: per-point constants of the sweeps (make_fast_ctx's arithmetic)
+        const double km = fast_exp_nonpos(-fabs(mu_fm) * fast_rcp(T));
+        const double kp = fast_rcp(km);
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+            for (int q = 0; q < 5; ++q) S[DS_X + q] = x[q];
+            S[DS_T] = T; S[DS_TM] = Tm;
+            S[DS_KAPP] = mu_fm >= 0.0 ? kp : km;
+            S[DS_KAPM] = mu_fm >= 0.0 ? km : kp;
+            S[DS_RES] = 0.0;
+            J[DJ_HINT] = flip ? 0 : J[DJ_ITSHINT];
+            J[DJ_KIND] = WS_FJ; J[DJ_ITERS] = 0; J[DJ_NFJ] = 0; J[DJ_NFT] = 0;
+            J[DJ_FLAGS] = DF_FIRST | DF_NONSING | (flip ? DF_FLIP : 0);
+        }
+        __syncwarp();
+    }
+    for (;;) {
+        {
+            // pre-sweep test, then the sweep
+            double x[5];
+#pragma unroll
+            for (int q = 0; q < 5; ++q) x[q] = S[DS_X + q];
+            const double T = S[DS_T], mu_fm = S[DS_MU];
+            double M[3];
+            masses_of(c_model, x, M);
+            const double M2[3] = {M[0] * M[0], M[1] * M[1], M[2] * M[2]};
+            if (!(x[0] == x[1]) || !fast_path_ok(T, mu_fm, x[3], x[4], S[DS_K2MAX], M2)) return false;
+            march_sweep<TEAMS>(J[DJ_KIND], T, mu_fm, S[DS_XI], x[0], x[1], x[2], x[3], x[4], S[DS_KAPP], S[DS_KAPM]);
+        }
+        int rc;
+        {
+            rc = march_finish(J[DJ_KIND] == WS_FJ ? 0 : 1, S[DS_T], S[DS_MU], S[DS_XI], S[DS_X], S[DS_X + 1], S[DS_X + 2], S[DS_X + 3], S[DS_X + 4]);
+            if (rc < 0) return false;
+        }
+        // ---- Newton logic on what the finish left in the scratch line ----
+        double x[5], xold[5], F[5], p[5];
+        const double* W = mc_W();
+#pragma unroll
+        for (int q = 0; q < 5; ++q) { x[q] = S[DS_X + q]; xold[q] = S[DS_XOLD + q]; F[q] = W[LW_F + q]; p[q] = W[LW_P + q]; }
+        int kind = J[DJ_KIND], iters = J[DJ_ITERS], n_fj = J[DJ_NFJ], n_ft = J[DJ_NFT], flags = J[DJ_FLAGS];
+        double res = S[DS_RES];
+        if (kind == WS_FJ) {
+            flags = rc != 0 ? (flags | DF_NONSING) : (flags & ~DF_NONSING);
+            ++n_fj;
+        } else {
+            flags = rc != 0 ? (flags | DF_THFINITE) : (flags & ~DF_THFINITE);
+            ++n_ft;
+        }
+        if (!all_finite5(F)) return false;
+        bool leave = false, again = false;
+        if (flags & DF_REFRESH) {
+            flags &= ~(DF_REFRESH | DF_HAVETH);       // J(x) is known now; the convergence tests of this x were made on the fused pass
+        } else {
+            if (flags & DF_FIRST) {
+                flags &= ~DF_FIRST;
+            } else {
+                double dx = 0.0;
+#pragma unroll
+                for (int i = 0; i < 5; ++i) dx = fmax(dx, fabs(x[i] - xold[i]));
+                flags = dx <= sp.xtol ? (flags | DF_XC) : (flags & ~DF_XC);
+                flags = kind == WS_FT ? (flags | DF_HAVETH) : (flags & ~DF_HAVETH);
+            }
+            res = norm_inf5(F);
+            flags = res <= sp.ftol ? (flags | DF_FC) : (flags & ~DF_FC);
+            if ((flags & (DF_XC | DF_FC)) || iters >= sp.max_iter) leave = true;
+            else if (kind == WS_FT) { kind = WS_FJ; flags |= DF_REFRESH; again = true; }
+        }
+        if (!leave && !again) {
+            ++iters;
+            if (!(flags & DF_NONSING)) return false;
+            p[1] = p[0];                                      // keep the exact u<->d symmetry of the equations (x[0] == x[1] here)
+            double pmax = 0.0;
+#pragma unroll
+            for (int i = 0; i < 5; ++i) { xold[i] = x[i]; x[i] = x[i] + p[i]; pmax = fmax(pmax, fabs(p[i])); }
+            const int hint = J[DJ_HINT];
+            const bool by_history = hint > 0 && iters <= hint;
+            const bool predict = sp.predict_tol > 0.0 && (pmax <= sp.xtol || (by_history ? iters == hint : res <= sp.predict_tol));
+            kind = predict ? WS_FT : WS_FJ;
+        }
+        if (!leave) {
+            __syncwarp();
+            if (lane == 0) {
+#pragma unroll
+                for (int q = 0; q < 5; ++q) { S[DS_X + q] = x[q]; S[DS_XOLD + q] = xold[q]; }
+                S[DS_RES] = res;
+                J[DJ_KIND] = kind; J[DJ_ITERS] = iters; J[DJ_NFJ] = n_fj; J[DJ_NFT] = n_ft; J[DJ_FLAGS] = flags;
+            }
+            __syncwarp();
+            continue;
+        }
+        // _nlsolve_with_tr_fallback (ImplicitSolver.jl:103-151): the trust-region fallback runs unless the primary solve is
+        // f-converged with a finite residual <= residual_norm_max and a physical state -> anything else: generic cascade.
+        // A final pass that was not a fused one (x-converged on a Jacobian pass: rare) also goes there.
+        const double rfin = norm_inf5(F);
+        if (!((flags & DF_FC) && (flags & DF_HAVETH) && (flags & DF_THFINITE) && finite_d(rfin) && rfin <= sp.residual_norm_max &&
+              finite_d(x[3]) && finite_d(x[4]) && (-sp.phi_tol <= x[3] && x[3] <= 1 + sp.phi_tol) &&
+              (-sp.phi_tol <= x[4] && x[4] <= 1 + sp.phi_tol)))
+            return false;
+        // the record: march_finish left the thermodynamic functions and the masses in the staging line; the rest here
+        double* stage = mc_stage();
+        double* rows = *reinterpret_cast<double**>(S + DS_ROWS);
+        const int it = J[DJ_IT];
+        const int ph_now = current_phase(&c_mc.cfg->pt, J[DJ_TI], S[DS_TM], S[DS_MUQ]);
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 5; ++i) stage[PNJL_REC_X + i] = x[i];
+            const int status = PNJL_ST_CONVERGED | ((flags & DF_FLIP) ? PNJL_ST_PHASE_SWITCH : 0) |
+                               (stage[PNJL_REC_MASS + 2] <= stage[PNJL_REC_MASS] ? PNJL_ST_MASS_INVERSION : 0);
+            stage[PNJL_REC_RESNORM] = rfin;
+            stage[PNJL_REC_ITER] = (double)iters;
+            stage[PNJL_REC_STATUS] = (double)status;
+            stage[PNJL_REC_NEVAL] = (double)n_fj;
+            stage[PNJL_REC_NTHERMO] = 0.0;
+            stage[PNJL_REC_T] = S[DS_T]; stage[PNJL_REC_MU] = S[DS_MU]; stage[PNJL_REC_XI] = S[DS_XI];
+            stage[PNJL_REC_NFUSED] = (double)n_ft;
+            stage[31] = 0.0;
+            // tracker update! (SeedStrategies.jl:851-856) and the history for the next point
+#pragma unroll
+            for (int q = 0; q < 5; ++q) S[DS_PREV + q] = x[q];
+            J[DJ_PREVPH] = ph_now; J[DJ_ITSHINT] = iters; J[DJ_IT] = it + 1;
+        }
+        __syncwarp();
+        rows[(long long)PNJL_REC_DOUBLES * it + lane] = stage[lane];
+        __syncwarp();
+        return true;
+    }
+}
+
 // Dynamic shared memory: mesh [3 n + 2 n_iso] | staging lines [16][32] | scratch lines [16][LW_END] | partial sums [16][24] |
-// command blocks [16][16] | reduction scratch [16][20][33]
+// command blocks [16][16] | reduction scratch [16][20][33] | line states [16][32]
 // TEAMS = false: the instantiation for one warp per line (launch_march picks it when parts == 1): no team code in the hot loop —
 // what 16 leaders per SM fetch per pass is what bounds that case (config 4: every pass is two trips of the quadrature loop).
 template <bool TEAMS>
 __global__ void __launch_bounds__(32 * kMarchWarps, 1) k_march(const double* __restrict__ g_mesh, MarchArgs a) {
-    const DeviceConfig* cfg = c_mc.cfg;
     const int n_mesh = 3 * c_mc.n + 2 * c_mc.n_iso;
     for (int i = threadIdx.x; i < n_mesh; i += blockDim.x) g_smem[i] = g_mesh[i];
     __syncthreads();
     if (TEAMS && mc_team() < 0) return;
     if (TEAMS && mc_part() != 0) { march_follow(); return; }
     const int lane = mc_lane();
-    const SolverParams& sp = c_mc.sp;
-    volatile int* slots = a.slots;
-    volatile unsigned long long* done = a.counters + 2;
+    double* const S = mc_state();
+    int* const J = reinterpret_cast<int*>(S + DS_INTS);
     for (;;) {
         // ---- pop: take a ticket and wait for the line that goes with it (or for the end of the scan) ----
         int line = -1;
         if (lane == 0) {
+            volatile int* slots = a.slots;
+            volatile unsigned long long* done = a.counters + 2;
             const unsigned long long t = atomicAdd(a.counters + 0, 1ULL);
             for (;;) {
                 if ((long long)t < a.capacity) {
@@ -547,159 +737,49 @@ __global__ void __launch_bounds__(32 * kMarchWarps, 1) k_march(const double* __r
         line = __shfl_sync(0xffffffffu, line, 0);
         if (line < 0) break;
         // ---- this line's parameters and parked tracker state ----
-        LineState st;
-        {
+        if (lane == 0) {
             const LineState* g = a.state + line;
 #pragma unroll
-            for (int q = 0; q < 5; ++q) st.prev[q] = __ldcg(&g->prev[q]);
-            st.it_next = __ldcg(&g->it_next); st.prev_phase = __ldcg(&g->prev_phase);
-            st.has_prev = __ldcg(&g->has_prev); st.its_hint = __ldcg(&g->its_hint);
+            for (int q = 0; q < 5; ++q) S[DS_PREV + q] = __ldcg(&g->prev[q]);
+            const int it0 = __ldcg(&g->it_next);
+            J[DJ_IT] = it0; J[DJ_PREVPH] = __ldcg(&g->prev_phase);
+            J[DJ_HASPREV] = __ldcg(&g->has_prev); J[DJ_ITSHINT] = __ldcg(&g->its_hint);
+            J[DJ_ITEND] = (it0 + a.quantum < a.n_T) ? it0 + a.quantum : a.n_T;
+            const long long row = a.out_index ? a.out_index[line] : (long long)line;
+            *reinterpret_cast<double**>(S + DS_ROWS) = a.records + (long long)PNJL_REC_DOUBLES * a.n_T * row;
+            const double muq = a.muq_MeV[line], xi = a.xi[line];
+            S[DS_MUQ] = muq; S[DS_XI] = xi; S[DS_MU] = muq / c_model.hbarc;
+            S[DS_K2MAX] = c_mc.p2max + (xi > 0.0 ? xi * c_mc.pc2max : 0.0);
+            J[DJ_TI] = a.table_idx ? a.table_idx[line] : -1;
+            J[DJ_LINE] = line;
         }
-        const long long row = a.out_index ? a.out_index[line] : (long long)line;
-        double* rows = a.records + (long long)PNJL_REC_DOUBLES * a.n_T * row;
-        const double muq_MeV = a.muq_MeV[line], xi = a.xi[line];
-        const int ti = a.table_idx ? a.table_idx[line] : -1;
-        const double mu_fm = muq_MeV / c_model.hbarc;
-        const int it_end = (st.it_next + a.quantum < a.n_T) ? st.it_next + a.quantum : a.n_T;
+        __syncwarp();
         // ---- one time slice ----
-        while (st.it_next < it_end) {
-            const int it = st.it_next;
+        while (J[DJ_IT] < J[DJ_ITEND]) {
             bool solved = false;
 #if PNJL_MARCH_LEAN
-            if (st.has_prev && sp.isospin) {
-                // PhaseAwareContinuitySeed get_seed (SeedStrategies.jl:795-839) with a previous solution
-                const double Tm = a.T_MeV[it];
-                const double T = Tm / c_model.hbarc;
-                const int cur = current_phase(&cfg->pt, ti, T * 197.327, mu_fm * 197.327);
-                const bool flip = (st.prev_phase == PH_HADRON && cur == PH_QUARK) || (st.prev_phase == PH_QUARK && cur == PH_HADRON);
-                double x[5], xold[5], F[5], p[5];
-                if (flip) seed_const(cur == PH_HADRON ? 0 : 1, x);
-                else copy5(x, st.prev);
-                const int hint = flip ? 0 : st.its_hint;
-                // ---- NLsolve newton_ (Solver::newton), common case only: every state on the integrand's fast path with
-                //      phi_u == phi_d and |mu| <= 60 T, every closed form tame, F finite.  One pass site: kind = Jacobian pass or
-                //      fused final pass (predicted), a mispredicted final pass is followed by a Jacobian pass at the same x
-                //      ("refresh").  Anything else -> generic cascade, which redoes the point from its seed.
-                int n_fj = 0, n_th = 0, n_ft = 0, iters = 0, kind = WS_FJ;
-                bool xc = false, fc = false, have_th = false, th_finite = false, nonsing = true, first = true, refresh = false;
-                bool bail = !one_log_ok(T, mu_fm) || !(T > 1e-300 && T < 1e300);
-                double res = 0.0;
-                const double k2max = c_mc.p2max + (xi > 0.0 ? xi * c_mc.pc2max : 0.0);
-                // e^{+-mu/T}: per-point constants of the sweeps (make_fast_ctx's arithmetic)
-                double kapP = 1.0, kapM = 1.0;
-                if (!bail) {
-                    const double km = fast_exp_nonpos(-fabs(mu_fm) * fast_rcp(T));
-                    const double kp = fast_rcp(km);
-                    kapP = mu_fm >= 0.0 ? kp : km;
-                    kapM = mu_fm >= 0.0 ? km : kp;
-                }
-                const double* W = mc_W();
-                while (!bail) {
-                    {
-                        double M[3];
-                        masses_of(c_model, x, M);
-                        const double M2[3] = {M[0] * M[0], M[1] * M[1], M[2] * M[2]};
-                        if (!(x[0] == x[1]) || !fast_path_ok(T, mu_fm, x[3], x[4], k2max, M2)) { bail = true; break; }
-                    }
-                    march_sweep<TEAMS>(kind, T, mu_fm, xi, x[0], x[1], x[2], x[3], x[4], kapP, kapM);
-                    const int rc = march_finish(kind == WS_FJ ? 0 : 1, T, mu_fm, xi, x[0], x[1], x[2], x[3], x[4]);
-                    if (rc < 0) { bail = true; break; }
-#pragma unroll
-                    for (int i = 0; i < 5; ++i) F[i] = W[LW_F + i];
-                    if (kind == WS_FJ) {
-#pragma unroll
-                        for (int i = 0; i < 5; ++i) p[i] = W[LW_P + i];
-                        nonsing = rc != 0;
-                        ++n_fj;
-                    } else {
-                        th_finite = rc != 0;
-                        ++n_ft;
-                    }
-                    if (!all_finite5(F)) { bail = true; break; }
-                    if (refresh) {
-                        refresh = false;          // J(x) is known now; the convergence tests of this x were made on the fused pass
-                        have_th = false;
-                    } else {
-                        if (first) {
-                            first = false;
-                        } else {
-                            double dx = 0.0;
-#pragma unroll
-                            for (int i = 0; i < 5; ++i) dx = fmax(dx, fabs(x[i] - xold[i]));
-                            xc = dx <= sp.xtol;
-                            have_th = kind == WS_FT;
-                        }
-                        res = norm_inf5(F);
-                        fc = res <= sp.ftol;
-                        if (xc || fc || iters >= sp.max_iter) break;
-                        if (kind == WS_FT) { kind = WS_FJ; refresh = true; continue; }
-                    }
-                    ++iters;
-                    if (!nonsing) { bail = true; break; }
-                    p[1] = p[0];                                      // keep the exact u<->d symmetry of the equations (x[0] == x[1] here)
-                    double pmax = 0.0;
-#pragma unroll
-                    for (int i = 0; i < 5; ++i) { xold[i] = x[i]; x[i] = x[i] + p[i]; pmax = fmax(pmax, fabs(p[i])); }
-                    const bool by_history = hint > 0 && iters <= hint;
-                    const bool predict = sp.predict_tol > 0.0 && (pmax <= sp.xtol || (by_history ? iters == hint : res <= sp.predict_tol));
-                    kind = predict ? WS_FT : WS_FJ;
-                }
-                // _nlsolve_with_tr_fallback (ImplicitSolver.jl:103-151): the trust-region fallback runs unless the primary solve is
-                // f-converged with a finite residual <= residual_norm_max and a physical state -> anything else: generic cascade.
-                // A final pass that was not a fused one (x-converged on a Jacobian pass: rare) also goes there.
-                const double rfin = norm_inf5(F);
-                if (!bail && fc && have_th && th_finite && finite_d(rfin) && rfin <= sp.residual_norm_max &&
-                    finite_d(x[3]) && finite_d(x[4]) && (-sp.phi_tol <= x[3] && x[3] <= 1 + sp.phi_tol) &&
-                    (-sp.phi_tol <= x[4] && x[4] <= 1 + sp.phi_tol)) {
-                    solved = true;
-                    // the record: march_finish left the thermodynamic functions and the masses in the staging line; the rest here
-                    double* stage = mc_stage();
-                    {
-                        __syncwarp();
-                        if (lane == 0) {
-#pragma unroll
-                            for (int i = 0; i < 5; ++i) stage[PNJL_REC_X + i] = x[i];
-                            const int status = PNJL_ST_CONVERGED | (flip ? PNJL_ST_PHASE_SWITCH : 0) |
-                                               (stage[PNJL_REC_MASS + 2] <= stage[PNJL_REC_MASS] ? PNJL_ST_MASS_INVERSION : 0);
-                            stage[PNJL_REC_RESNORM] = rfin;
-                            stage[PNJL_REC_ITER] = (double)iters;
-                            stage[PNJL_REC_STATUS] = (double)status;
-                            stage[PNJL_REC_NEVAL] = (double)n_fj;
-                            stage[PNJL_REC_NTHERMO] = (double)n_th;
-                            stage[PNJL_REC_T] = T; stage[PNJL_REC_MU] = mu_fm; stage[PNJL_REC_XI] = xi;
-                            stage[PNJL_REC_NFUSED] = (double)n_ft;
-                            stage[31] = 0.0;
-                        }
-                        __syncwarp();
-                        rows[(long long)PNJL_REC_DOUBLES * it + lane] = stage[lane];
-                        __syncwarp();
-                    }
-                    // tracker update! (SeedStrategies.jl:851-856) and the history for the next point
-                    copy5(st.prev, x);
-                    st.prev_phase = current_phase(&cfg->pt, ti, Tm, muq_MeV);
-                    st.its_hint = iters;
-                    st.it_next = it + 1;
-                }
-            }
+            if (J[DJ_HASPREV] && c_mc.sp.isospin) solved = march_lean_point<TEAMS>(a);
 #endif
-            if (!solved) march_generic_point(&cfg->pt, ti, muq_MeV, xi, a.n_T, a.T_MeV, st, rows);
+            if (!solved) march_generic_step(a);
         }
         // ---- park the line (or retire it) ----
         if (lane == 0) {
-            if (st.it_next < a.n_T) {
+            const int it = J[DJ_IT];
+            if (it < a.n_T) {
                 LineState* g = a.state + line;
 #pragma unroll
-                for (int q = 0; q < 5; ++q) __stcg(&g->prev[q], st.prev[q]);
-                __stcg(&g->it_next, st.it_next); __stcg(&g->prev_phase, st.prev_phase);
-                __stcg(&g->has_prev, st.has_prev); __stcg(&g->its_hint, st.its_hint);
+                for (int q = 0; q < 5; ++q) __stcg(&g->prev[q], S[DS_PREV + q]);
+                __stcg(&g->it_next, it); __stcg(&g->prev_phase, J[DJ_PREVPH]);
+                __stcg(&g->has_prev, J[DJ_HASPREV]); __stcg(&g->its_hint, J[DJ_ITSHINT]);
                 __threadfence();
                 const unsigned long long t = atomicAdd(a.counters + 1, 1ULL);
-                if ((long long)t < a.capacity) slots[t] = line;
+                if ((long long)t < a.capacity) ((volatile int*)a.slots)[t] = line;
             } else {
                 __threadfence();
                 atomicAdd(a.counters + 2, 1ULL);
             }
         }
+        __syncwarp();
     }
     if (TEAMS) march_dismiss();
 }
