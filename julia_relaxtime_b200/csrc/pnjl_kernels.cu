@@ -1505,11 +1505,11 @@ int dispatch_lines(pnjl_handle* h, int layout, long long n_lines, const double* 
         case 16: return launch_lines<16>(h, n_lines, muq, xi, tidx, n_T, T, rec, st, mode);
         default: {
             // Which organisation marches the lines (measured on cfg5 / cfg4 shares, profiles/r02_*): the line-march kernel when
-            // a pass is short (all-isotropic batch: p_num nodes) or the GPU holds few lines (<= 20 per SM: multi-GPU shares of a
-            // fixed grid; 2048 lines: 102 ms against 132, 4096 lines: a tie at 179 ms, 8192 lines: 343 against 309), where the latency of a pass decides; the warp-specialised kernel when there are enough lines to hide
+            // a pass is short (all-isotropic batch: p_num nodes) or the GPU holds few lines (<= 32 per SM: multi-GPU shares of a
+            // fixed grid; 2048 lines: 100 ms against 132, 4096 lines: 171 against 183, 8192 lines: 332 against 312), where the latency of a pass decides; the warp-specialised kernel when there are enough lines to hide
             // its controller step (its workers' small code stays inside the instruction cache).
             const bool iso = (h->iso_next || h->iso_batch) && h->host_cfg.n_iso > 0;
-            const bool march = mode == 0 && (h->schedule == 3 || (h->schedule == 2 && (iso || n_lines <= 20LL * h->sm_count)));
+            const bool march = mode == 0 && (h->schedule == 3 || (h->schedule == 2 && (iso || n_lines <= 32LL * h->sm_count)));
             if (march) return launch_march(h, n_lines, muq, xi, tidx, n_T, T, rec, st);
             h->iso_next = false;
             if (h->schedule >= 1) return launch_lines_ws(h, n_lines, muq, xi, tidx, n_T, T, rec, st, mode);
