@@ -447,13 +447,35 @@ __device__ __forceinline__ void thermo_from_stage(Thermo& th) {
 // Evaluation policy of the generic cascade (Solver<WarpEval>: MultiSeed bootstrap, trust-region fallback, everything the
 // in-kernel fast path hands back).  Stateless: the context comes from threadIdx and constant memory.  Sweeps go through the
 // general ws_worker_pass (every kind of state), finishes through march_finish with the cold versions as fall-back.
+// A pass of the generic cascade: through the lean sweep (march_sweep, the small loop that is hot in the instruction cache)
+// when the state qualifies for it — integrand fast path, phi_u == phi_d bitwise, |mu| <= 60 T: true for nearly every iterate
+// of a bootstrap at T >= 50 MeV — and through the general ws_worker_pass otherwise.  The sums land in W[LW_S ..] in the same
+// layout either way (fast-path flag at W[LW_S + 20]).  Before this, the 3 % of the passes of a full config-5 grid that belong
+// to the cascade (first point of every line, phase flips) took 38 % of the kernel's time: ws_worker_pass is 100 KB of code
+// that every warp walked alone, at 86 cycles per instruction (profiles/r02c_march_cfg5_full.md).
+__device__ __noinline__ void march_pass_any(int type, double T, double mu, double xi, const double x[5]) {
+    if (type != WS_TH && c_mc.sp.isospin && x[0] == x[1] && one_log_ok(T, mu) && T > 1e-300 && T < 1e300) {
+        double M[3];
+        masses_of(c_model, x, M);
+        const double M2[3] = {M[0] * M[0], M[1] * M[1], M[2] * M[2]};
+        const double k2max = c_mc.p2max + (xi > 0.0 ? xi * c_mc.pc2max : 0.0);
+        if (fast_path_ok(T, mu, x[3], x[4], k2max, M2)) {
+            const double km = fast_exp_nonpos(-fabs(mu) * fast_rcp(T));
+            const double kp = fast_rcp(km);
+            march_sweep<true>(type, T, mu, xi, x[0], x[1], x[2], x[3], x[4], mu >= 0.0 ? kp : km, mu >= 0.0 ? km : kp);
+            return;
+        }
+    }
+    march_pass(type, T, mu, xi, x[0], x[1], x[2], x[3], x[4]);
+}
+
 struct WarpEval {
     __device__ __noinline__ void fj(double T, double mu, double xi, const double x[5], double F[5], double J[25]) {
-        march_pass(WS_FJ, T, mu, xi, x[0], x[1], x[2], x[3], x[4]);
+        march_pass_any(WS_FJ, T, mu, xi, x);
         cold_fj(T, mu, xi, x, F, J);                     // only the trust-region method wants J itself
     }
     __device__ __noinline__ bool fj_step(double T, double mu, double xi, const double x[5], double F[5], double p[5]) {
-        march_pass(WS_FJ, T, mu, xi, x[0], x[1], x[2], x[3], x[4]);
+        march_pass_any(WS_FJ, T, mu, xi, x);
         const int rc = march_finish(0, T, mu, xi, x[0], x[1], x[2], x[3], x[4]);
         if (rc < 0) return cold_fj_step(T, mu, xi, x, F, p);
         const double* W = mc_W();
@@ -466,7 +488,7 @@ struct WarpEval {
         make_ctx(c_model, T, mu, xi, x, c);
         const double k2max = c_mc.p2max + (xi > 0.0 ? xi * c_mc.pc2max : 0.0);
         if (!fast_path_ok(c.T, c.mu, c.Phi, c.Phib, k2max, c.M2)) return false;   // uniform over the team
-        march_pass(WS_FT, T, mu, xi, x[0], x[1], x[2], x[3], x[4]);
+        march_pass_any(WS_FT, T, mu, xi, x);
         if (march_finish(1, T, mu, xi, x[0], x[1], x[2], x[3], x[4]) < 0) { cold_f_thermo(T, mu, xi, x, F, th); return true; }
         const double* W = mc_W();
 #pragma unroll
