@@ -212,7 +212,10 @@ struct Species {
     bool pos;    // a > 0
 };
 
-PNJL_HD Species species_eval(double a, double P1x3, double P2x3) {
+// Out of line on the device: the general-path loops call it six times per node, and inlined (with libm's exp) their bodies
+// grow to tens of KB that no instruction cache level holds — 86 cycles per instruction were measured on the general path of
+// the line-march kernel.  The fast path does not come here.
+PNJL_HD_NOINL Species species_eval(double a, double P1x3, double P2x3) {
     Species s;
     const double w = guarded_exp_nonpos(-fabs(a));
     const double w2 = w * w;
@@ -690,6 +693,41 @@ PNJL_HD MeshView select_mesh(const MeshView& mv, double xi) {
     return r;
 }
 
+// General path of an FJ pass (floors / rescaling live), out of line: its code and its registers stay out of the fast-path
+// loops of the callers (the warp-specialised kernel's workers run those and nothing else in steady state).
+// iso: M_u == M_d bitwise, the d flavour is the u flavour.  u is then evaluated with twice the coefficient — the
+// flavour-summed slots hold 2 c (u terms) + c (s terms) — and its own slots are halved afterwards (exact: powers of two).
+PNJL_HD_NOINL void fj_partial_general(const PointCtx& c, bool iso, const MeshView& mv, int lane, int stride, double* out) {
+    double acc[kFJAcc];
+#pragma unroll
+    for (int i = 0; i < kFJAcc; ++i) acc[i] = 0.0;
+    if (iso) {
+#pragma unroll 1
+        for (int k = lane; k < mv.n; k += stride) {
+            const double k2 = f_fma(c.xi, mv.pc2[k], mv.p2[k]);
+            const double cf = mv.coef[k];
+            fj_node<0>(c, k2, 2.0 * cf, acc);
+            fj_node<2>(c, k2, cf, acc);
+        }
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            acc[3 * q + 0] *= 0.5;
+            acc[3 * q + 1] = acc[3 * q + 0];
+        }
+    } else {
+#pragma unroll 1
+        for (int k = lane; k < mv.n; k += stride) {
+            const double k2 = f_fma(c.xi, mv.pc2[k], mv.p2[k]);
+            const double cf = mv.coef[k];
+            fj_node<0>(c, k2, cf, acc);
+            fj_node<1>(c, k2, cf, acc);
+            fj_node<2>(c, k2, cf, acc);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < kFJAcc; ++i) out[i] = acc[i];
+}
+
 // Per-lane partial sums of one FJ pass in the canonical 20-slot layout (to be summed over the lanes of
 // the group, then finish_fj).  Chooses, uniformly for the whole group, between
 //   fast + isospin (x[0] == x[1] bitwise -> M_u == M_d bitwise: the d flavour is the u flavour, 2 flavours evaluated),
@@ -736,15 +774,7 @@ PNJL_HD bool fj_partial(const Model& m, bool isospin, const PointCtx& c, const d
         }
         return true;
     }
-#pragma unroll
-    for (int i = 0; i < kFJAcc; ++i) acc[i] = 0.0;
-    for (int k = lane; k < mv.n; k += stride) {
-        const double k2 = f_fma(c.xi, mv.pc2[k], mv.p2[k]);
-        const double cf = mv.coef[k];
-        fj_node<0>(c, k2, cf, acc);
-        fj_node<1>(c, k2, cf, acc);
-        fj_node<2>(c, k2, cf, acc);
-    }
+    fj_partial_general(c, isospin && x[0] == x[1], mv, lane, stride, acc);
     return false;
 }
 
@@ -965,6 +995,35 @@ PNJL_HD void thermo_node(const PointCtx& c, double k2, double coef, double acc[k
     acc[TH_T] = f_fma(coef, f_fma(np, E - c.mu, nm * (E + c.mu)), acc[TH_T]);
 }
 
+// General path of a thermo pass, out of line (see fj_partial_general; same isospin shortcut).
+PNJL_HD_NOINL void thermo_partial_general(const PointCtx& c, bool iso, const MeshView& mv, int lane, int stride, double* out) {
+    double acc[kThAcc];
+#pragma unroll
+    for (int i = 0; i < kThAcc; ++i) acc[i] = 0.0;
+    if (iso) {
+#pragma unroll 1
+        for (int k = lane; k < mv.n; k += stride) {
+            const double k2 = f_fma(c.xi, mv.pc2[k], mv.p2[k]);
+            const double cf = mv.coef[k];
+            thermo_node<0>(c, k2, 2.0 * cf, acc);
+            thermo_node<2>(c, k2, cf, acc);
+        }
+        acc[TH_NP + 0] *= 0.5; acc[TH_NP + 1] = acc[TH_NP + 0];
+        acc[TH_NM + 0] *= 0.5; acc[TH_NM + 1] = acc[TH_NM + 0];
+    } else {
+#pragma unroll 1
+        for (int k = lane; k < mv.n; k += stride) {
+            const double k2 = f_fma(c.xi, mv.pc2[k], mv.p2[k]);
+            const double cf = mv.coef[k];
+            thermo_node<0>(c, k2, cf, acc);
+            thermo_node<1>(c, k2, cf, acc);
+            thermo_node<2>(c, k2, cf, acc);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < kThAcc; ++i) out[i] = acc[i];
+}
+
 // Per-lane partial sums of one thermo pass in the canonical 8-slot layout.
 PNJL_HD void thermo_partial(const Model& m, bool isospin, const PointCtx& c, const double x[5], const MeshView& mv_in, int lane,
                             int stride, double acc[kThAcc]) {
@@ -1013,15 +1072,7 @@ PNJL_HD void thermo_partial(const Model& m, bool isospin, const PointCtx& c, con
         acc[TH_T] = (t0[3] + t1[3]) + t2[3];
         return;
     }
-#pragma unroll
-    for (int i = 0; i < kThAcc; ++i) acc[i] = 0.0;
-    for (int k = lane; k < mv.n; k += stride) {
-        const double k2 = f_fma(c.xi, mv.pc2[k], mv.p2[k]);
-        const double cf = mv.coef[k];
-        thermo_node<0>(c, k2, cf, acc);
-        thermo_node<1>(c, k2, cf, acc);
-        thermo_node<2>(c, k2, cf, acc);
-    }
+    thermo_partial_general(c, isospin && x[0] == x[1], mv, lane, stride, acc);
 }
 
 // Per-lane partial sums of a fused "final pass": facc[0..2] = S1 per flavour, facc[3] = GP, facc[4] = GPB (flavour

@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_parity_configs.py -m gpu -x -q --timeout 600 2>&1 | tail -3
+for w in "cfg3 --schedule 2 --n-t 60000" "cfg3 --schedule 3 --n-t 60000" "cfg5 --schedule 3" "cfg5 --schedule 2" "cfg5 --ranks 2 --rank 1 --schedule 3" "cfg5 --ranks 8 --rank 3 --schedule 0" "cfg4 --schedule 0"; do
+  echo "== $w"; timeout 300 python scripts/dev_bench.py --workload $w 2>&1 | tail -1 | sed 's/ | lanes/\n   lanes/'
+done
