@@ -1345,6 +1345,8 @@ int launch_march(pnjl_handle* h, long long n_lines, const double* muq, const dou
     const int n_eff = iso ? h->host_cfg.n_iso : h->n_nodes;
     int parts = 1;
     while (parts < kMarchWarps && n_lines * 2 * parts <= 3 * total_warps && n_eff / (64 * parts) >= 2) parts *= 2;
+    // more lines than four teams per SM can hold at once: five teams of three (1/8 share of config 5: 60.5 ms against 62.5)
+    if (parts == 4 && n_lines > 4LL * h->sm_count) parts = 3;
     if (h->march_parts > 0) parts = h->march_parts;
     if (parts < 1 || parts > kMarchWarps) return fail(PNJL_ERR_ARG, "march_parts must be 1 .. 16");
     const long long n_teams = (long long)h->sm_count * (kMarchWarps / parts);

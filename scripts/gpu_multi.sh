@@ -7,8 +7,8 @@ run() { # N, port, extra args, output stem
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $port bench.py --gpus $n --steps 3 --warmup 3 "$@" > gpurun_out/$stem.json 2> gpurun_out/$stem.err
   echo "== $stem rc=$?"; tail -c 1800 gpurun_out/$stem.json; tail -2 gpurun_out/$stem.err | cut -c1-300
 }
-run 8 29521 bench_r2_cfg5_n8
-run 8 29522 bench_r2_cfg4_n8 --workload cfg4 --no-weak
-run 4 29523 bench_r2_cfg5_n4 --no-weak
-run 2 29524 bench_r2_cfg5_n2 --no-weak
+run 8 29521 bench_cfg5_n8
+run 8 29522 bench_cfg4_n8 --workload cfg4 --no-weak
+run 4 29523 bench_cfg5_n4 --no-weak
+run 2 29524 bench_cfg5_n2 --no-weak
 timeout 600 python -m pytest tests/test_peer_gather.py -m gpu -x -q --timeout 500 2>&1 | tail -2
