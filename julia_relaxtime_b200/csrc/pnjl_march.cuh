@@ -97,9 +97,12 @@ __device__ __forceinline__ void mc_mesh(MeshView& mv) {
     mv.p2max = c_mc.p2max; mv.pc2max = c_mc.pc2max;
     mv.p2_iso = g_smem + 3 * n; mv.coef_iso = g_smem + 3 * n + c_mc.n_iso; mv.n_iso = c_mc.n_iso;
 }
-__device__ __forceinline__ void mc_team_sync() {
+// The team barrier.  Out of line on purpose: leader and followers then arrive through the SAME bar.sync instruction.  The
+// hardware does not care, but compute-sanitizer's synccheck reports (and aborts on) a named barrier that its participants
+// reach from different instructions, even in a minimal producer/consumer program (scripts/microbench_named_barrier.cu).
+__device__ __noinline__ void mc_team_sync() {
+    __syncwarp();
     if (c_mc.parts > 1) asm volatile("bar.sync %0, %1;" ::"r"(1 + mc_team()), "r"(32 * c_mc.parts) : "memory");
-    else __syncwarp();
 }
 
 // ---- team protocol ---------------------------------------------------------------------------------------------------
