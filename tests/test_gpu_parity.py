@@ -349,12 +349,13 @@ def test_isotropic_collapse_equals_full_mesh(p_num, t_num):
         assert ec.stats()["lanes_per_solve"] > 32
 
 
-@pytest.mark.parametrize("schedule,parts", [(0, 1), (0, 2), (0, 4), (0, 16), (1, 1), (2, 1), (2, 2)])
+@pytest.mark.parametrize("schedule,parts", [(0, 1), (0, 2), (0, 3), (0, 4), (0, 16), (1, 1), (2, 1), (2, 2), (3, 2)])
 def test_kernel_organisations_agree(schedule, parts, monkeypatch):
-    """The three kernel organisations against the oracle on lines and on MultiSeed points at 64x16 nodes — line march
-    (schedule 0; one warp per line or teams of 2/4/16 warps splitting every pass; points go through the warp-specialised
-    kernel), one warp per line with phase-aligned CTAs (1), warp-specialised worker/controller warps (2; passes whole or
-    split over 2 workers): same converged flags, ≤ 1e-9 on the state."""
+    """The kernel organisations against the oracle on lines and on MultiSeed points at 64x16 nodes — line march (schedule 0:
+    picked automatically for these few lines; one warp per line or teams of 2/3/4/16 warps, a leader and followers that only
+    sweep; points go through the warp-specialised kernel), one warp per line with phase-aligned CTAs (1), warp-specialised
+    worker/controller warps (2; passes whole or split over 2 workers), line march forced for lines AND points (3: one team
+    per point, k_march_points): same converged flags, ≤ 1e-9 on the state."""
     monkeypatch.setenv("PNJL_WS_PARTS", str(min(parts, 4)))
     monkeypatch.setenv("PNJL_MARCH_PARTS", str(parts))
     o = Oracle(p_num=64, t_num=16, max_iter=40)
@@ -368,7 +369,7 @@ def test_kernel_organisations_agree(schedule, parts, monkeypatch):
     res = o.scan_lines(muq, xi, T, tables, tidx)
     rec = e.scan_lines(muq, xi, T, tidx)
     assert_state_parity(rec, res, label="org-lines")
-    if schedule == 0:
+    if schedule in (0, 3):
         assert e.stats()["lanes_per_solve"] == 32 * parts and e.stats()["threads"] == 512
         # time-slicing: a line parked after every 1, 5 or 12 points gives bit-identical records
         for q in (1, 5, 12):
@@ -381,7 +382,7 @@ def test_kernel_organisations_agree(schedule, parts, monkeypatch):
     resp = o.solve_points(Tp, mup, xip, "multi")
     recp = e.solve_points(Tp, mup, xip, A.SEED_MULTI)
     assert_state_parity(recp, resp, label="org-points", max_wander=2)
-    assert e.stats()["lanes_per_solve"] == (32 if schedule == 1 else 32 * min(parts, 4))
+    assert e.stats()["lanes_per_solve"] == (32 if schedule == 1 else (32 * parts if schedule == 3 else 32 * min(parts, 4)))
 
 
 def test_full_size_config5_slab_properties_and_spot_lines():
