@@ -549,7 +549,7 @@ enum { DS_X = 0, DS_XOLD = 5, DS_T = 10, DS_MU = 11, DS_XI = 12, DS_KAPP = 13, D
        DS_MUQ = 18, DS_PREV = 19, DS_ROWS = 24, DS_INTS = 25 };
 enum { DJ_LINE = 0, DJ_IT = 1, DJ_ITEND = 2, DJ_KIND = 3, DJ_ITERS = 4, DJ_NFJ = 5, DJ_NFT = 6, DJ_HINT = 7, DJ_FLAGS = 8,
        DJ_PREVPH = 9, DJ_HASPREV = 10, DJ_ITSHINT = 11, DJ_TI = 12 };
-enum { DF_FIRST = 1, DF_REFRESH = 2, DF_HAVETH = 4, DF_THFINITE = 8, DF_NONSING = 16, DF_XC = 32, DF_FC = 64, DF_FLIP = 128 };
+enum { DF_FIRST = 1, DF_REFRESH = 2, DF_HAVETH = 4, DF_THFINITE = 8, DF_NONSING = 16, DF_XC = 32, DF_FC = 64, DF_FLIP = 128, DF_FINALTH = 256 };
 constexpr int kStateDoubles = 32;     // 25 doubles + 13 ints
 __device__ __forceinline__ double* mc_state() { return g_smem + c_mc.state0 + mc_warp() * kStateDoubles; }
 
@@ -649,7 +649,12 @@ __device__ __forceinline__ bool march_lean_point(const MarchArgs& a) {
         }
         if (!all_finite5(F)) return false;
         bool leave = false, again = false;
-        if (flags & DF_REFRESH) {
+        if (flags & DF_FINALTH) {
+            // the fused pass that follows a solve which ended on a Jacobian pass (below): the thermodynamic functions of the
+            // converged x; the convergence tests were made on that Jacobian pass and its residual is the one reported
+            flags |= DF_HAVETH;
+            leave = true;
+        } else if (flags & DF_REFRESH) {
             flags &= ~(DF_REFRESH | DF_HAVETH);       // J(x) is known now; the convergence tests of this x were made on the fused pass
         } else {
             if (flags & DF_FIRST) {
@@ -678,6 +683,15 @@ __device__ __forceinline__ bool march_lean_point(const MarchArgs& a) {
             const bool predict = sp.predict_tol > 0.0 && (pmax <= sp.xtol || (by_history ? iters == hint : res <= sp.predict_tol));
             kind = predict ? WS_FT : WS_FJ;
         }
+        if (leave && (flags & DF_FC) && !(flags & DF_HAVETH) && kind == WS_FJ) {
+            // f-converged on a Jacobian pass — the prediction expected one more iteration (0.5 % of the points of config 5):
+            // NLsolve is done; what is missing are the thermodynamic functions of this x.  One fused pass at the same x
+            // provides them (handing the point to the generic cascade instead re-solved it from its seed through ~60 KB of
+            // cold code).
+            flags |= DF_FINALTH;
+            kind = WS_FT;
+            leave = false;
+        }
         if (!leave) {
             __syncwarp();
             if (lane == 0) {
@@ -692,7 +706,7 @@ __device__ __forceinline__ bool march_lean_point(const MarchArgs& a) {
         // _nlsolve_with_tr_fallback (ImplicitSolver.jl:103-151): the trust-region fallback runs unless the primary solve is
         // f-converged with a finite residual <= residual_norm_max and a physical state -> anything else: generic cascade.
         // A final pass that was not a fused one (x-converged on a Jacobian pass: rare) also goes there.
-        const double rfin = norm_inf5(F);
+        const double rfin = (flags & DF_FINALTH) ? res : norm_inf5(F);
         if (!((flags & DF_FC) && (flags & DF_HAVETH) && (flags & DF_THFINITE) && finite_d(rfin) && rfin <= sp.residual_norm_max &&
               finite_d(x[3]) && finite_d(x[4]) && (-sp.phi_tol <= x[3] && x[3] <= 1 + sp.phi_tol) &&
               (-sp.phi_tol <= x[4] && x[4] <= 1 + sp.phi_tol)))
