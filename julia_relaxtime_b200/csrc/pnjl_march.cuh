@@ -1,26 +1,25 @@
 // pnjl_march.cuh — the line-march kernel k_march (included by pnjl_kernels.cu inside namespace pnjl, after pnjl_lean.cuh).
 //
-// One warp (or a team of 2/4/8/16 warps when a GPU holds fewer lines than warps) owns a (xi, mu) line and runs its whole
-// continuity march — seed, Newton iterations, final thermodynamics, record — in its own registers
-// (run_gap_transport_scan.jl:407-443, ImplicitSolver.jl:211-328 through Solver<WarpEval>):
-//   * a quadrature pass is the same paired FP64 loop as in k_solve_ws (ws_worker_pass: lanes stride the mesh in shared
-//     memory, transposed shuffle butterfly); the 20 sums land in the warp's shared-memory scratch line and the closed-form
-//     finish + the 5x5 elimination run in the same warp right away, LANE-PARALLEL (pnjl_lean.cuh: one flavour / one matrix
-//     entry per lane) — no hand-over, no controller warps, no polling;
+// One LEADER warp owns a (xi, mu) line and runs its whole continuity march — seed, Newton iterations, final thermodynamics,
+// record (run_gap_transport_scan.jl:407-443, ImplicitSolver.jl:211-328) — alone, or with 1..15 FOLLOWER warps that only sweep
+// the mesh for it when a GPU holds fewer lines than warps:
+//   * a quadrature pass is the paired FP64 loop of k_solve_ws's workers in one small function (march_sweep_part: lanes
+//     stride the mesh in shared memory, warp reduction through shared memory); the sums land in the leader's scratch line
+//     and the closed-form finish + the 5x5 elimination run there right away, LANE-PARALLEL (march_finish, pnjl_lean.cuh: one
+//     flavour / one matrix entry per lane) — no controller warps, no polling;
 //   * the common case — plain Newton from the continuity seed converges to a physical state (ImplicitSolver.jl:103-128) — is
-//     a small state machine inlined in the kernel (one pass site, registers only, constants from constant memory): the
-//     per-pass code is ~10 KB including the quadrature loop, so 16 desynchronised warps stay inside the SM's 32 KB
-//     instruction cache (the redundant-per-lane version ran 1.8x slower for that reason alone).  Everything else
-//     (MultiSeed bootstrap, trust-region fallback, unphysical or floored states) goes through the generic Solver<WarpEval>
-//     cascade out of line;
-//   * lines are time-sliced: a global ticket queue hands out (line, next T index) quanta of `quantum` points; a warp that
+//     a small state machine (march_lean_point) whose state lives in shared memory, so that nothing is spilled around the
+//     calls of sweep and finish; what a warp walks per pass has to fit the SM's 32 KB instruction cache next to the other
+//     warps' code — every version that shrank it got faster.  Everything else (MultiSeed bootstrap,
+//     trust-region fallback, unphysical or floored states) goes through the generic Solver<WarpEval> cascade out of line,
+//     which redoes the point from its seed;
+//   * lines are time-sliced: a global ticket queue hands out (line, next T index) quanta of `quantum` points; a leader that
 //     finishes a quantum parks the line's tracker state (64 bytes) in global memory, re-queues the line and takes the oldest
-//     waiting one.  All lines therefore advance at the same pace on ALL SMs (no per-SM imbalance, the tail is one quantum),
-//     and any number of lines per GPU keeps every warp busy;
-//   * few lines per GPU (multi-GPU slabs of a fixed grid, the CEP window of config 4): the warps of a team split every pass
-//     by nodes, add their partial sums in a fixed order through shared memory behind one named barrier per pass, and run the
-//     scalar part redundantly, so the latency of a pass drops with the team size;
-//   * a record leaves as one coalesced 256-byte row written by the 32 lanes of the owning warp.
+//     waiting one.  All lines therefore advance at the same pace on ALL SMs (no per-SM imbalance, the tail is one quantum);
+//   * teams (few lines per GPU: multi-GPU shares of a fixed grid): the leader posts the pass in the team's command block,
+//     leader and followers sweep their node ranges between two named barriers, and the leader adds the partial sums in part
+//     order — the result does not depend on who was faster.  Followers never execute finish or state machine;
+//   * a record leaves as one coalesced 256-byte row written by the 32 lanes of the leader.
 #pragma once
 
 #ifndef PNJL_MARCH_LEAN
