@@ -182,6 +182,24 @@ function eval_state(e::Engine, T_fm::Vector{Float64}, mu_fm::Vector{Float64}, xi
     return out
 end
 
+"""`eval_state` plus the partial derivatives in (T, μ) at fixed `x` that ThermoDerivatives.jl gets from ForwardDiff
+(`:80-109`, `:186-262`, `:342-467`), as closed-form quadrature sums: `Matrix{Float64}(64, n)` — rows 1:48 as `eval_state`, then
+∂F/∂T 49:53, ∂F/∂μ 54:58, ∂s/∂T 59, ∂s/∂μ 60, ∂n_B/∂T 61, ∂n_B/∂μ 62 (n_B = Σρ_i/3)."""
+function eval_derivs(e::Engine, T_fm::Vector{Float64}, mu_fm::Vector{Float64}, xi::Vector{Float64}, x::Matrix{Float64})
+    n = length(T_fm)
+    out = Matrix{Float64}(undef, 64, n)
+    check(ccall((:pnjl_eval_derivs_host, LIB), Cint,
+                (Ptr{Cvoid}, Int64, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+                e.handle, n, T_fm, mu_fm, xi, x, out), "pnjl_eval_derivs_host")
+    return out
+end
+
+"""dx/dT and dx/dμ along the solution curve, dx/dθ = −J⁻¹ ∂F/∂θ (ThermoDerivatives.jl:80-109), from one column of `eval_derivs`."""
+function state_derivatives(col::AbstractVector{Float64})
+    J = permutedims(reshape(col[6:30], 5, 5))          # row-major in the record
+    return -(J \ col[49:53]), -(J \ col[54:58])
+end
+
 # ---- one-loop integral A and effective couplings (build_K_data, run_gap_transport_scan.jl:297-305) -----------------
 """Replace the rule of A (default: DEFAULT_MOMENTUM_NODES / DEFAULT_MOMENTUM_WEIGHTS)."""
 function set_oneloop_rule!(e::Engine, nodes::Vector{Float64}, weights::Vector{Float64})
