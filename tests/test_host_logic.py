@@ -33,6 +33,25 @@ def test_c_abi_exports_every_declared_symbol():
     assert abs(cfg.Lambda - 602.3 / 197.327) < 1e-15 and abs(cfg.G - 1.835 / cfg.Lambda ** 2) < 1e-15
 
 
+def test_julia_shim_binds_only_exported_symbols_with_the_declared_arity():
+    """julia/PNJLB200.jl cannot be executed here (no Julia in the image): at least every `ccall` in it must name a symbol
+    include/pnjl_b200.h declares, with as many argument types as the C prototype has parameters."""
+    root = ROOT
+    src = open(os.path.join(root, "julia", "PNJLB200.jl")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(root, "include", "pnjl_b200.h")).read(), flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(pnjl_\w+)\s*\(([^;{]*?)\)\s*;", hdr):
+        args = m.group(2).strip()
+        protos[m.group(1)] = 0 if args in ("", "void") else len(args.split(","))
+    calls = list(re.finditer(r"ccall\(\(:(pnjl_\w+), LIB\),\s*\w+,\s*\(([^)]*)\)", src))
+    assert len(calls) >= 15
+    for m in calls:
+        name, types = m.group(1), [t for t in m.group(2).split(",") if t.strip()]
+        assert name in protos, name
+        assert len(types) == protos[name], (name, len(types), protos[name])
+
+
+
 def test_no_cpu_fallback_without_gpu():
     import torch
     if torch.cuda.is_available():
